@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched pendulum swing-up cubature i2c (BASELINE.json configs[2]:
+4096 random initial states x T=200 per B200), metric = problem-timestep updates / s.
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port, all host cores)
+
+One "step" = one EM iteration (I2cGraph.learn_msgs: forward + backward + M-step, i2c/i2c.py:1238-1245) over the
+whole batch; one problem-timestep update = one cell through one such iteration.  Under torchrun every rank owns an
+independent shard of problems (weak scaling, no data-path collective); the only collective is the final NCCL
+all_gather of controllers / costs, timed in the end-to-end leg.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "input-inference-for-control_b200"))
+
+METRIC = "problem-timestep updates/sec (fp64, batched)"
+UNIT = "updates/s"
+# SURVEY.md section 8(d), pendulum row: algorithmic work per problem-timestep update
+F_ALG, B_ALG = 3192.0, 704.0
+FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
+
+
+def make_inputs(B, T, seed):
+    """Config 3 of SURVEY.md 8(d): x0[b] = [pi,0] + [0.3,0.5] * N(0,I), mu_u[b] = 1e-2 N(0,1)."""
+    rng = np.random.default_rng(seed)
+    x0 = np.array([np.pi, 0.0]) + np.array([0.3, 0.5]) * rng.normal(size=(B, 2))
+    mu_u = 1e-2 * rng.normal(size=(B, T, 1))
+    return x0, mu_u
+
+
+HYPER = dict(Q=np.diag([1.0, 100.0, 1.0]), R=np.diag([2.0]), alpha=100.0, tol=0.0, sig_u=2.0 * np.eye(1))
+
+
+# ----------------------------------------------------------------------------- CPU reference arm / baseline
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    from oracle import i2c_oracle as O
+
+    seed, Bs, T, steps, warmup = args
+    x0, mu_u = make_inputs(Bs, T, seed)
+    g = O.make_graph("PendulumKnown", T, HYPER["Q"], HYPER["R"], HYPER["Q"], HYPER["alpha"], HYPER["tol"], mu_u,
+                     HYPER["sig_u"], B=Bs, x0=x0)
+    for _ in range(warmup):
+        g.learn_msgs()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        g.learn_msgs()
+    return time.perf_counter() - t0
+
+
+def cpu_rate(T, steps, warmup, per_core, cores):
+    """Oracle port (batched NumPy restatement of the reference) on `cores` processes, `per_core` problems each."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(1000 + i, per_core, T, steps, warmup) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    dt = max(times)
+    return cores * per_core * T * steps / dt, dt, wall
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_core = 64
+    T = args.horizon
+    rate, dt, wall = cpu_rate(T, args.steps, min(args.warmup, 1), per_core, cores)
+    sample = f"{cores} procs x {per_core} problems x T={T}, {args.steps} EM iterations (of the {args.problems}-problem job)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"pendulum swing-up cubature i2c, {args.problems} problems/GPU x T={T} (BASELINE configs[2])",
+                   "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+def run_cuda(args, rank, world, local_rank):
+    import torch
+    import __graft_entry__ as ge
+
+    if rank == 0:
+        ge.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.barrier()
+    if rank != 0:
+        ge.build()
+    import i2c_b200
+    from i2c_b200 import capi
+
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    B, T, K, W = args.problems, args.horizon, args.steps, args.warmup
+    x0, mu_u = make_inputs(B, T, 1234 + rank)
+    g = i2c_b200.BatchedI2c("PendulumKnown", B, T, HYPER["Q"], HYPER["R"], HYPER["Q"], HYPER["alpha"], HYPER["tol"], mu_u,
+                            HYPER["sig_u"], x0=x0, device=dev, max_iters=max(K, W, 1))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput: K EM iterations, inputs already in HBM, one persistent launch
+    g.run(max(W, 3), capi.PH_LEARN, collect=False)  # warm-up (>= 3 iterations)
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    l0 = g.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.perf_counter()
+    e0.record()
+    g.run(K, capi.PH_LEARN, collect=False)
+    e1.record()
+    barrier()
+    t_end = time.perf_counter()
+    launches = g.kernel_launches() - l0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    kernel_ms = max_over_ranks(g.last_run_ms())
+    clocks = sampler.stop(t_start, t_end) if rank == 0 else None
+    st, _ = g.status()
+    n_fail = int(np.count_nonzero(st))
+    value = world * B * T * K / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (the reference's i2c_run.py loop, :89-98): every
+    # step uploads the start-state belief (sys.x0 / sys.sig_x0 are re-read by every sweep), runs one learn_msgs,
+    # reads the per-problem cost / alpha scalars and the controller (get_local_linear_policy) back to the host.
+    Ke = max(3, min(K, 10))
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
+    h_x0, h_s0 = pin(B, 2), pin(B, 2, 2)
+    h_x0[:], h_s0[:] = g.x0, g.sig_x0
+    h_K, h_k, h_s, h_m = pin(B, T, 1, 2), pin(B, T, 1), pin(B, T, 1, 1), pin(1, B)
+    L = g.lib
+
+    def e2e_step():
+        capi.check(L.i2c_set_initial_state(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))
+        capi.check(L.i2c_run(g._h, 1, capi.PH_LEARN))
+        for m in ("alpha", "cost_m"):
+            capi.check(L.i2c_get_metric(g._h, capi.METRICS[m], capi.ptr(h_m), 1))
+        capi.check(L.i2c_get_policy(g._h, capi.ptr(h_K), capi.ptr(h_k), capi.ptr(h_s)))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    if dist is not None:
+        # the path's only collective: final gather of controllers and costs over NVLink
+        Kd, kd, sd = g.policy_device_tensors()
+        outs = [[torch.empty_like(x) for _ in range(world)] for x in (Kd, kd, sd)]
+        for o, x in zip(outs, (Kd, kd, sd)):
+            dist.all_gather(o, x)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = world * B * T * Ke / (e2e_ms * 1e-3)
+    h2d = h_x0.nbytes + h_s0.nbytes
+    d2h = h_K.nbytes + h_k.nbytes + h_s.nbytes + 2 * h_m.nbytes
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    per_gpu_rate = B * T * K / (kernel_ms * 1e-3)
+    achieved = B_ALG * per_gpu_rate / 1e9
+    try:
+        fp64_peak = capi.dfma_peak(dev)
+    except Exception:
+        fp64_peak = None
+    fp64_ach = F_ALG * per_gpu_rate / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"pendulum swing-up cubature i2c, {B} problems/GPU x T={T} (BASELINE configs[2])",
+                   "problems_per_gpu": B, "horizon": T, "em_iterations_timed": K, "updates_per_step": world * B * T,
+                   "l2": "per-iteration working set (prior+posterior+filtered records) = %.0f MB > 126 MB L2; no flush needed"
+                         % ((13 + 13 + 20) * 8 * B * T / 1e6),
+                   "launch": "one persistent kernel launch runs all K iterations (forward, backward, M-step fused)",
+                   "failed_problems": n_fail},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "what": "per step: H2D start-state belief, one learn_msgs, D2H cost+alpha per problem and K,k,sigK"
+                        + ("; + final NCCL all_gather of controllers" if world > 1 else "")},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "em_kernel<EnvPendulum>",
+                     "kernel_ms_per_launch": kernel_ms,
+                     "algorithmic_bytes_per_update": B_ALG, "algorithmic_flops_per_update": F_ALG,
+                     "fp64": {"achieved_tflops": fp64_ach, "peak_measured_tflops": fp64_peak,
+                              "frac_of_measured": (fp64_ach / fp64_peak) if fp64_peak else None,
+                              "peak_nominal_tflops": FP64_NOMINAL_TFLOPS, "frac_of_nominal": fp64_ach / FP64_NOMINAL_TFLOPS}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, dt, wall = cpu_rate(T, 2, 1, 64, cores)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{cores} procs x 64 problems x T={T}, 2 EM iterations after 1 warm-up "
+                                          f"(oracle/i2c_oracle.py, batched NumPy restatement)", "seconds": wall}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--problems", type=int, default=4096, help="problems per GPU")
+    ap.add_argument("--horizon", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_cuda(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,245 @@
+// In-kernel environment definitions: dynamics (one Euler step, input clipped), cost-feature maps
+// observe / observe_terminal, and the quadrotor measurement map.  Restated from the reference's
+// NumPy functions (cited per env; paths relative to the reference root).
+//
+// Sigma points are m +- sf*L[:,j] with L lower triangular, so coordinate i of the points built from
+// column j > i equals the centre m_i exactly: the trigonometric features of an angle stored at state
+// index a only need fresh sin/cos for columns j <= a.  Every map therefore takes the column index j
+// (compile-time after unrolling; j < 0 = centre) and a `Trig` cache evaluated once at the centre.
+#pragma once
+#include "linalg.cuh"
+
+namespace i2c {
+
+template <int NA>
+struct Trig {
+  double s[NA > 0 ? NA : 1], c[NA > 0 ? NA : 1];
+};
+
+// ------------------------------------------------------------------ linear systems
+// LinearDef / LinearBase: env_def.py:139-191, model.py:226-242.  Per-problem parameters
+// par = [A00 A01 A10 A11 B0 B1 a0 a1].
+struct EnvLinear {
+  static constexpr int DX = 2, DU = 1, DZ = 3, DZT = 2, NP = 8, DY = 0, NA = 0;
+  static constexpr bool HAS_TERM = true;
+  using TrigT = Trig<NA>;
+  __device__ static void center(const double*, TrigT&) {}
+  __device__ static void dyn(const double* xu, int, const TrigT&, const double* par, double* y) {
+    y[0] = fma(par[0], xu[0], fma(par[1], xu[1], fma(par[4], xu[2], par[6])));
+    y[1] = fma(par[2], xu[0], fma(par[3], xu[1], fma(par[5], xu[2], par[7])));
+  }
+  __device__ static void obs(const double* xu, int, const TrigT&, double* z) {
+    z[0] = xu[0]; z[1] = xu[1]; z[2] = xu[2];
+  }
+  __device__ static void obs_term(const double* x, int, const TrigT&, double* z) { z[0] = x[0]; z[1] = x[1]; }
+  __device__ static void measure(const double*, int, const TrigT&, double*) {}
+};
+
+// LinearMinimumEnergyDef: env_def.py:194-230 (cost on u only).
+struct EnvLinearMinEnergy : EnvLinear {
+  static constexpr int DZ = 1;
+  __device__ static void obs(const double* xu, int, const TrigT&, double* z) { z[0] = xu[2]; }
+};
+
+// ------------------------------------------------------------------ pendulum
+// env_autograd.py:5-19 (dynamics), env_def.py:273-291 (features [sin th, cos th, thd, u]).
+struct EnvPendulum {
+  static constexpr int DX = 2, DU = 1, DZ = 4, DZT = 3, NP = 0, DY = 0, NA = 1;
+  static constexpr bool HAS_TERM = true;
+  using TrigT = Trig<NA>;
+  __device__ static void center(const double* m, TrigT& t) { sincos(m[0], &t.s[0], &t.c[0]); }
+  __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
+    if (j != 0) { s = c.s[0]; co = c.c[0]; } else { sincos(x[0], &s, &co); }
+  }
+  __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
+    const double dt = 0.05, d = 1e-2, g = 9.80665;
+    double s, co;
+    trig(xu, j, c, s, co);
+    (void)co;
+    double u = fmin(fmax(xu[2], -2.0), 2.0);
+    // the reference evaluates np.sin(th + np.pi); sin(th + pi) == -sin(th) up to the rounding of th + pi
+    double acc = -3.0 * g / 2.0 * (-s) - d * xu[1];
+    acc += 3.0 * u;
+    double xd = fma(acc, dt, xu[1]);
+    y[0] = fma(xd, dt, xu[0]);
+    y[1] = xd;
+  }
+  __device__ static void obs(const double* xu, int j, const TrigT& c, double* z) {
+    trig(xu, j, c, z[0], z[1]);
+    z[2] = xu[1];
+    z[3] = xu[2];
+  }
+  __device__ static void obs_term(const double* x, int j, const TrigT& c, double* z) {
+    trig(x, j, c, z[0], z[1]);
+    z[2] = x[1];
+  }
+  __device__ static void measure(const double*, int, const TrigT&, double*) {}
+};
+
+// PendulumKnownActReg: env_def.py:312-346 (cost on u only, no terminal features).
+struct EnvPendulumActReg : EnvPendulum {
+  static constexpr int DZ = 1, DZT = 1;
+  static constexpr bool HAS_TERM = false;
+  __device__ static void obs(const double* xu, int, const TrigT&, double* z) { z[0] = xu[2]; }
+  __device__ static void obs_term(const double*, int, const TrigT&, double* z) { z[0] = 0.0; }
+};
+
+// ------------------------------------------------------------------ cart-pole
+// env_autograd.py:25-54, env_def.py:537-570 (features [x, sin th, cos th, xd, thd, u]).
+struct EnvCartpole {
+  static constexpr int DX = 4, DU = 1, DZ = 6, DZT = 5, NP = 0, DY = 0, NA = 1;
+  static constexpr bool HAS_TERM = true;
+  using TrigT = Trig<NA>;
+  __device__ static void center(const double* m, TrigT& t) { sincos(m[1], &t.s[0], &t.c[0]); }
+  __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
+    if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { sincos(x[1], &s, &co); }
+  }
+  __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
+    const double g = 9.81, Mc = 0.37, Mp = 0.127, Mt = Mc + Mp, l = 0.3365, dt = 1.0 / 250.0;
+    double u = fmin(fmax(xu[4], -5.0), 5.0);
+    double sth, cth;
+    trig(xu, j, c, sth, cth);
+    double dth2 = xu[3] * xu[3];
+    double num = -Mp * l * sth * cth * dth2 + Mt * g * sth - u * cth;
+    double den = l * ((4.0 / 3.0) * Mt - Mp * cth * cth);
+    double th_acc = num / den;
+    double x_acc = (Mp * l * sth * dth2 - Mp * l * th_acc * cth + u) / Mt;
+    y[0] = fma(dt, xu[2], xu[0]);
+    y[1] = fma(dt, xu[3], xu[1]);
+    y[2] = fma(dt, x_acc, xu[2]);
+    y[3] = fma(dt, th_acc, xu[3]);
+  }
+  __device__ static void obs(const double* xu, int j, const TrigT& c, double* z) {
+    z[0] = xu[0];
+    trig(xu, j, c, z[1], z[2]);
+    z[3] = xu[2]; z[4] = xu[3]; z[5] = xu[4];
+  }
+  __device__ static void obs_term(const double* x, int j, const TrigT& c, double* z) {
+    z[0] = x[0];
+    trig(x, j, c, z[1], z[2]);
+    z[3] = x[2]; z[4] = x[3];
+  }
+  __device__ static void measure(const double*, int, const TrigT&, double*) {}
+};
+
+// ------------------------------------------------------------------ double cart-pole
+// env_autograd.py:60-167, env_def.py:682-732
+// (features [x, sin th1, cos th1, sin th2, cos th2, xd, thd1, thd2, u]).
+struct EnvDoubleCartpole {
+  static constexpr int DX = 6, DU = 1, DZ = 9, DZT = 8, NP = 0, DY = 0, NA = 2;
+  static constexpr bool HAS_TERM = true;
+  using TrigT = Trig<NA>;
+  __device__ static void center(const double* m, TrigT& t) {
+    sincos(m[1], &t.s[0], &t.c[0]);
+    sincos(m[2], &t.s[1], &t.c[1]);
+  }
+  __device__ static void trig1(const double* x, int j, const TrigT& c, double& s, double& co) {
+    if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { sincos(x[1], &s, &co); }
+  }
+  __device__ static void trig2(const double* x, int j, const TrigT& c, double& s, double& co) {
+    if (j < 0 || j > 2) { s = c.s[1]; co = c.c[1]; } else { sincos(x[2], &s, &co); }
+  }
+  __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
+    const double dt = 1.0 / 125.0, g = 9.81, Mc = 0.37, Mp1 = 0.127, Mp2 = 0.127, Mt = Mc + Mp1 + Mp2;
+    const double L1 = 0.3365, L2 = 0.3365, l1 = L1 / 2, l2 = L2 / 2, J1 = Mp1 * L1 / 12, J2 = Mp2 * L2 / 12;
+    const double a12 = Mp1 * l1 + Mp2 * L2, a13 = Mp2 * l2, a23 = L1 * l2 * Mp2;
+    const double M11 = Mt, M22 = l1 * l1 * Mp1 + L1 * L1 * Mp2 + J1, M33 = l2 * l2 * Mp2 + J2;
+    double s1, c1, s2, c2, sd, cd;
+    trig1(xu, j, c, s1, c1);
+    trig2(xu, j, c, s2, c2);
+    sincos(xu[1] - xu[2], &sd, &cd);
+    double M12 = a12 * c1, M13 = a13 * c2, M23 = a23 * cd;
+    double qd = xu[3], td1 = xu[4], td2 = xu[5];
+    double C12 = -a12 * td1 * s1, C13 = -a13 * td2 * s2, C23 = a23 * td2 * sd, C32 = -a23 * td1 * sd;
+    double G2 = -(Mp1 * l1 + Mp2 * L1) * g * s1, G3 = -Mp2 * l2 * g * s2;
+    double u = 3.0 * fmin(fmax(xu[6], -10.0), 10.0);
+    (void)qd;
+    double r1 = u - (C12 * td1 + C13 * td2);
+    double r2 = -(C23 * td2) - G2;
+    double r3 = -(C32 * td1) - G3;
+    // solve the SPD 3x3 system M qdd = r by Cholesky (the reference forms inv(M) @ r)
+    double l11 = sqrt(M11), i11 = 1.0 / l11;
+    double l21 = M12 * i11, l31 = M13 * i11;
+    double l22 = sqrt(M22 - l21 * l21), i22 = 1.0 / l22;
+    double l32 = (M23 - l31 * l21) * i22;
+    double l33 = sqrt(M33 - l31 * l31 - l32 * l32), i33 = 1.0 / l33;
+    double y1 = r1 * i11;
+    double y2 = (r2 - l21 * y1) * i22;
+    double y3 = (r3 - l31 * y1 - l32 * y2) * i33;
+    double a3 = y3 * i33;
+    double a2 = (y2 - l32 * a3) * i22;
+    double a1 = (y1 - l21 * a2 - l31 * a3) * i11;
+    double v1 = fma(a1, dt, xu[3]), v2 = fma(a2, dt, xu[4]), v3 = fma(a3, dt, xu[5]);
+    y[0] = fma(v1, dt, xu[0]);
+    y[1] = fma(v2, dt, xu[1]);
+    y[2] = fma(v3, dt, xu[2]);
+    y[3] = v1; y[4] = v2; y[5] = v3;
+  }
+  __device__ static void obs(const double* xu, int j, const TrigT& c, double* z) {
+    z[0] = xu[0];
+    trig1(xu, j, c, z[1], z[2]);
+    trig2(xu, j, c, z[3], z[4]);
+    z[5] = xu[3]; z[6] = xu[4]; z[7] = xu[5]; z[8] = xu[6];
+  }
+  __device__ static void obs_term(const double* x, int j, const TrigT& c, double* z) {
+    z[0] = x[0];
+    trig1(x, j, c, z[1], z[2]);
+    trig2(x, j, c, z[3], z[4]);
+    z[5] = x[3]; z[6] = x[4]; z[7] = x[5];
+  }
+  __device__ static void measure(const double*, int, const TrigT&, double*) {}
+};
+
+// ------------------------------------------------------------------ planar quadrotor
+// fp64 restatement of QuadrotorDef.step (Box2D single free body, mpc_quad.py:325-350) -- see
+// oracle/envs.py:Quadrotor for the statement and DESIGN.md "parity unpinned"; measure(): mpc_quad.py:371-383
+// (typos in the right-rotor velocities reproduced).  observe is the identity.
+struct EnvQuadrotor {
+  static constexpr int DX = 6, DU = 2, DZ = 8, DZT = 6, NP = 0, DY = 8, NA = 1;
+  static constexpr bool HAS_TERM = true;
+  using TrigT = Trig<NA>;
+  static constexpr double VDX = 0.8;                                      // W/25
+  static constexpr double MASS = 5.0 * (2 * 0.8) * (2 * (400.0 / 30.0 / 100.0));
+  static constexpr double INERTIA = MASS * ((2 * 0.8) * (2 * 0.8) + (2 * (400.0 / 30.0 / 100.0)) * (2 * (400.0 / 30.0 / 100.0))) / 12.0;
+  __device__ static void center(const double* m, TrigT& t) { sincos(m[2], &t.s[0], &t.c[0]); }
+  __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
+    if (j < 0 || j > 2) { s = c.s[0]; co = c.c[0]; } else { sincos(x[2], &s, &co); }
+  }
+  __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
+    const double h = 0.1;
+    double u1 = fmin(fmax(xu[6], 0.0), 30.0), u2 = fmin(fmax(xu[7], 0.0), 30.0);
+    double s, co;
+    trig(xu, j, c, s, co);
+    double f = u1 + u2;
+    double vx = xu[3] + h * ((-s * f) / MASS);
+    double vy = xu[4] + h * (-9.81 + (co * f) / MASS);
+    double w = xu[5] + h * (VDX * (u2 - u1)) / INERTIA;
+    w = w * (1.0 / (1.0 + h * 0.5));
+    y[0] = xu[0] + h * vx;
+    y[1] = xu[1] + h * vy;
+    y[2] = xu[2] + h * w;
+    y[3] = vx; y[4] = vy; y[5] = w;
+  }
+  __device__ static void obs(const double* xu, int, const TrigT&, double* z) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = xu[i];
+  }
+  __device__ static void obs_term(const double* x, int, const TrigT&, double* z) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) z[i] = x[i];
+  }
+  __device__ static void measure(const double* x, int j, const TrigT& c, double* yv) {
+    double s, co;
+    trig(x, j, c, s, co);
+    yv[0] = x[0] - VDX * co;
+    yv[1] = x[1] - VDX * s;
+    yv[2] = x[0] + VDX * co;
+    yv[3] = x[1] + VDX * s;
+    yv[4] = x[3] - VDX * -s * x[5];
+    yv[5] = x[4] - VDX * co * x[5];
+    yv[6] = x[3] + VDX - s * x[5];
+    yv[7] = x[4] + VDX + co * x[5];
+  }
+};
+
+}  // namespace i2c

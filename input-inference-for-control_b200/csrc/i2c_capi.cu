@@ -1,0 +1,1087 @@
+// C-ABI of the B200 i2c library (declared in include/i2c_b200.h): handle management, conversion between
+// the canonical host layout ([B][T][rows][cols], full symmetric matrices) and the tiled device layout,
+// and the launch of the persistent EM kernel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "i2c_types.h"
+
+using namespace i2c;
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(x)                                                                                       \
+  do {                                                                                                   \
+    cudaError_t e_ = (x);                                                                                \
+    if (e_ != cudaSuccess) return set_err(-100 - (int)e_, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+#define REQUIRE(c, msg) \
+  do {                  \
+    if (!(c)) return set_err(-1, msg); \
+  } while (0)
+
+struct EnvDims {
+  int dx, du, dz, dzt, np, dy;
+};
+static const EnvDims kEnv[I2C_ENV_COUNT] = {
+    {2, 1, 3, 2, 8, 0}, {2, 1, 1, 2, 8, 0}, {2, 1, 4, 3, 0, 0}, {2, 1, 1, 1, 0, 0},
+    {4, 1, 6, 5, 0, 0}, {6, 1, 9, 8, 0, 0}, {6, 2, 8, 6, 0, 8},
+};
+static const bool kHasTerm[I2C_ENV_COUNT] = {true, true, true, false, true, true, true};
+
+static inline int tri(int n) { return n * (n + 1) / 2; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct i2c_handle_s {
+  i2c_config_t cfg;
+  EnvDims d;
+  RecDims r;
+  int B, Bpad, ntiles, T;
+  cudaStream_t stream;
+  bool own_ws;
+  char* ws;
+  size_t ws_bytes;
+  // device buffers (inside ws)
+  double *recA, *recB, *filt, *auxf, *auxb, *pf, *term, *x0, *sig_x0, *alpha, *alpha_cell, *z_cell, *envpar, *metrics,
+      *scratch;
+  int32_t *cell_flags_dev, *cell_index_dev, *status, *info;
+  size_t scratch_elems;
+  // host state
+  int prior_is_A;   // forward reads recA (1) or recB (0)
+  int latest_is_A;  // most recent posterior record
+  std::vector<int32_t> flags, index;
+  int cell_head;
+  int tau;
+  double temp, dtemp;
+  KParams kp;  // constants + pointers template
+  int last_n_iter;
+  long long launches;
+  cudaEvent_t ev0, ev1;
+  bool problem_set;
+  std::vector<double> mu_u_init_last, sig_u_host;
+};
+
+// ----------------------------------------------------------------------------------------- kernels
+// canonical [B][nt][rows][cols] (host order) <-> tiled record elements.  kind 0: dense rows x cols at
+// `off`; kind 1: symmetric d x d stored packed-lower at `off`; kind 2: sub-block of a packed-lower
+// matrix of order `ld` starting at (r0, c0) (used for the u-marginal views).
+struct FieldMap {
+  int E, off, kind, rows, cols, r0, c0, per_cell;
+};
+
+__device__ __forceinline__ int rec_elem(const FieldMap& f, int r, int c) {
+  if (f.kind == 0) return f.off + r * f.cols + c;
+  int i = r + f.r0, j = c + f.c0;
+  return f.off + (i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i);
+}
+
+__global__ void unpack_kernel(const double* __restrict__ rec, FieldMap f, int t0, int nt, int T, int head, int B, int ntiles,
+                              double* __restrict__ out) {
+  const size_t per = (size_t)f.rows * f.cols;
+  const size_t total = (size_t)B * nt * per;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % f.cols);
+    int r = (int)((i / f.cols) % f.rows);
+    int t = (int)((i / per) % nt);
+    int b = (int)(i / (per * nt));
+    int slot = f.per_cell ? (t0 + t + head) % T : 0;
+    size_t src = (((size_t)slot * ntiles + b / TILE) * f.E + rec_elem(f, r, c)) * TILE + (b % TILE);
+    out[i] = rec[src];
+  }
+}
+
+// pack with padding: problems b >= B replicate problem B-1 so that padded lanes do well-posed work
+__global__ void pack_kernel(double* __restrict__ rec, FieldMap f, int t0, int nt, int T, int head, int B, int Bpad,
+                            int ntiles, const double* __restrict__ in, int bcast_b) {
+  const size_t per = (size_t)f.rows * f.cols;
+  const size_t total = (size_t)Bpad * nt * per;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % f.cols);
+    int r = (int)((i / f.cols) % f.rows);
+    int t = (int)((i / per) % nt);
+    int b = (int)(i / (per * nt));
+    if (f.kind != 0 && (r + f.r0) < (c + f.c0)) continue;  // packed lower: take the lower triangle
+    int bs = bcast_b ? 0 : (b < B ? b : B - 1);
+    int slot = f.per_cell ? (t0 + t + head) % T : 0;
+    size_t dst = (((size_t)slot * ntiles + b / TILE) * f.E + rec_elem(f, r, c)) * TILE + (b % TILE);
+    rec[dst] = in[((size_t)bs * nt + t) * per + (size_t)r * f.cols + c];
+  }
+}
+
+// constructor state of the cells [t0, t0+nt): prior == posterior == N([x0; mu_u], blkdiag(sig_x0, sig_u)), K = 0,
+// k = mu_u, sigK = sig_u  (I2cCell.__init__, i2c.py:92-100,135-136)
+struct InitArgs {
+  int dx, du, n, E, T, head, Bpad, ntiles, bcast_u;
+  double sig_u[3];
+};
+__global__ void init_cells_kernel(double* recA, double* recB, InitArgs a, int t0, int nt, const double* __restrict__ x0,
+                                  const double* __restrict__ sig_x0, const double* __restrict__ mu_u /*[B|1][nt][du]*/, int B) {
+  const size_t total = (size_t)a.Bpad * nt;
+  const int n = a.n, dx = a.dx, du = a.du;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int b = (int)(i % a.Bpad), t = (int)(i / a.Bpad);
+    int bs = a.bcast_u ? 0 : (b < B ? b : B - 1);
+    int slot = (t0 + t + a.head) % a.T;
+    size_t base = (((size_t)slot * a.ntiles + b / TILE) * a.E) * TILE + (b % TILE);
+    size_t xb = ((size_t)(b / TILE) * dx) * TILE + (b % TILE);
+    size_t sb = ((size_t)(b / TILE) * (dx * (dx + 1) / 2)) * TILE + (b % TILE);
+    int e = 0;
+    for (int k = 0; k < dx; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = x0[xb + (size_t)k * TILE];
+    for (int k = 0; k < du; ++k, ++e)
+      recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = mu_u[((size_t)bs * nt + t) * du + k];
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c <= r; ++c, ++e) {
+        double v = 0.0;
+        if (r < dx) v = sig_x0[sb + (size_t)(r * (r + 1) / 2 + c) * TILE];
+        else if (c >= dx) v = a.sig_u[(r - dx) * (r - dx + 1) / 2 + (c - dx)];
+        recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = v;
+      }
+    for (int k = 0; k < du * dx; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = 0.0;
+    for (int k = 0; k < du; ++k, ++e)
+      recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = mu_u[((size_t)bs * nt + t) * du + k];
+    for (int k = 0; k < du * (du + 1) / 2; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = a.sig_u[k];
+  }
+}
+
+// fp64 FMA-pipe peak probe (roofline denominator: MEASURED_PEAKS.json has no fp64 figure): 8 independent
+// DFMA chains per thread, enough warps to saturate every sub-partition.
+__global__ void dfma_peak_kernel(double* out, int iters, double b, double c) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3,
+         a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void fill_kernel(double* p, size_t n, double v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline int nblocks(size_t total) {
+  size_t b = (total + 255) / 256;
+  return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+// ----------------------------------------------------------------------------------------- layout
+struct WsLayout {
+  size_t recA, recB, filt, auxf, auxb, pf, term, x0, sig_x0, alpha, alpha_cell, z_cell, envpar, metrics, scratch, flags,
+      index, status, info, total, scratch_elems;
+};
+
+static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
+  WsLayout w;
+  RecDims r{d.dx, d.du, d.dx + d.du, d.dz, d.dzt};
+  size_t Bpad = align_up((size_t)c.n_problems, TILE), nt = Bpad / TILE, T = c.horizon;
+  size_t off = 0;
+  auto take = [&](size_t elems, size_t esz) {
+    size_t o = off;
+    off = align_up(off + elems * esz, 256);
+    return o;
+  };
+  w.recA = take(T * nt * r.e_post() * TILE, 8);
+  w.recB = take(T * nt * r.e_post() * TILE, 8);
+  w.filt = take(T * nt * r.e_filt() * TILE, 8);
+  w.auxf = take(c.enable_aux ? T * nt * r.e_auxf() * TILE : 0, 8);
+  w.auxb = take(c.enable_aux ? T * nt * r.e_auxb() * TILE : 0, 8);
+  w.pf = take(c.enable_aux ? T * nt * r.e_pf() * TILE : 0, 8);
+  w.term = take(nt * r.e_term() * TILE, 8);
+  w.x0 = take(nt * d.dx * TILE, 8);
+  w.sig_x0 = take(nt * tri(d.dx) * TILE, 8);
+  w.alpha = take(Bpad, 8);
+  w.alpha_cell = take(T * Bpad, 8);
+  w.z_cell = take(c.z_per_problem ? T * nt * d.dz * TILE : T * d.dz, 8);
+  w.envpar = take(nt * (d.np > 0 ? d.np : 1) * TILE, 8);
+  w.metrics = take((size_t)I2C_M_COUNT * c.max_iters * Bpad, 8);
+  size_t n = d.dx + d.du;
+  size_t big = n * n;
+  if ((size_t)(d.dz * d.dz) > big) big = d.dz * d.dz;
+  w.scratch_elems = Bpad * T * big;
+  w.scratch = take(w.scratch_elems, 8);
+  w.flags = take(T, 4);
+  w.index = take(T, 4);
+  w.status = take(Bpad, 4);
+  w.info = take(Bpad, 4);
+  w.total = off;
+  return w;
+}
+
+static int check_cfg(const i2c_config_t* cfg) {
+  REQUIRE(cfg != nullptr, "cfg is NULL");
+  REQUIRE(cfg->abi_version == I2C_ABI_VERSION, "ABI version mismatch");
+  REQUIRE(cfg->env >= 0 && cfg->env < I2C_ENV_COUNT, "unknown env id (no CPU fallback for unregistered envs)");
+  REQUIRE(cfg->inference == I2C_INF_CUBATURE, "only cubature inference runs through i2c_run");
+  REQUIRE(cfg->n_problems >= 1 && cfg->horizon >= 1 && cfg->horizon < 65536, "bad B or H");
+  REQUIRE(cfg->max_iters >= 1, "max_iters must be >= 1");
+  REQUIRE(cfg->quad_alpha > 0.0, "cubature alpha must be > 0");
+  return 0;
+}
+
+extern "C" {
+
+const char* i2c_last_error(void) { return g_err.c_str(); }
+const char* i2c_build_info(void) { return "i2c_b200 abi=1 arch=sm_100a fp64 tile=32 " __DATE__ " " __TIME__; }
+
+int i2c_env_dims(int32_t env, int32_t* dx, int32_t* du, int32_t* dz, int32_t* dzt, int32_t* n_par, int32_t* dy) {
+  REQUIRE(env >= 0 && env < I2C_ENV_COUNT, "unknown env id");
+  const EnvDims& d = kEnv[env];
+  if (dx) *dx = d.dx;
+  if (du) *du = d.du;
+  if (dz) *dz = d.dz;
+  if (dzt) *dzt = d.dzt;
+  if (n_par) *n_par = d.np;
+  if (dy) *dy = d.dy;
+  return 0;
+}
+
+int i2c_workspace_bytes(const i2c_config_t* cfg, size_t* bytes) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  REQUIRE(bytes != nullptr, "bytes is NULL");
+  *bytes = plan(*cfg, kEnv[cfg->env]).total;
+  return 0;
+}
+
+int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_bytes, void* stream, i2c_handle_t* out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  REQUIRE(out != nullptr, "out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return set_err(-2, "no CUDA device available: the i2c hot path has no CPU fallback");
+  REQUIRE(cfg->device >= 0 && cfg->device < ndev, "bad device ordinal");
+  CUDA_OK(cudaSetDevice(cfg->device));
+  i2c_handle_s* h = new i2c_handle_s();
+  h->cfg = *cfg;
+  h->d = kEnv[cfg->env];
+  h->r = RecDims{h->d.dx, h->d.du, h->d.dx + h->d.du, h->d.dz, h->d.dzt};
+  h->B = cfg->n_problems;
+  h->Bpad = (int)align_up((size_t)h->B, TILE);
+  h->ntiles = h->Bpad / TILE;
+  h->T = cfg->horizon;
+  h->stream = (cudaStream_t)stream;
+  WsLayout w = plan(*cfg, h->d);
+  if (workspace_dev) {
+    if (workspace_bytes < w.total) {
+      delete h;
+      return set_err(-1, "workspace too small");
+    }
+    h->ws = (char*)workspace_dev;
+    h->own_ws = false;
+  } else {
+    cudaError_t ce = cudaMalloc((void**)&h->ws, w.total);
+    if (ce != cudaSuccess) {
+      delete h;
+      return set_err(-100 - (int)ce, std::string("cudaMalloc workspace: ") + cudaGetErrorString(ce));
+    }
+    h->own_ws = true;
+  }
+  h->ws_bytes = w.total;
+  h->recA = (double*)(h->ws + w.recA);
+  h->recB = (double*)(h->ws + w.recB);
+  h->filt = (double*)(h->ws + w.filt);
+  h->auxf = cfg->enable_aux ? (double*)(h->ws + w.auxf) : nullptr;
+  h->auxb = cfg->enable_aux ? (double*)(h->ws + w.auxb) : nullptr;
+  h->pf = cfg->enable_aux ? (double*)(h->ws + w.pf) : nullptr;
+  h->term = (double*)(h->ws + w.term);
+  h->x0 = (double*)(h->ws + w.x0);
+  h->sig_x0 = (double*)(h->ws + w.sig_x0);
+  h->alpha = (double*)(h->ws + w.alpha);
+  h->alpha_cell = (double*)(h->ws + w.alpha_cell);
+  h->z_cell = (double*)(h->ws + w.z_cell);
+  h->envpar = (double*)(h->ws + w.envpar);
+  h->metrics = (double*)(h->ws + w.metrics);
+  h->scratch = (double*)(h->ws + w.scratch);
+  h->scratch_elems = w.scratch_elems;
+  h->cell_flags_dev = (int32_t*)(h->ws + w.flags);
+  h->cell_index_dev = (int32_t*)(h->ws + w.index);
+  h->status = (int32_t*)(h->ws + w.status);
+  h->info = (int32_t*)(h->ws + w.info);
+  h->problem_set = false;
+  h->launches = 0;
+  h->last_n_iter = 0;
+  h->cell_head = 0;
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  CUDA_OK(cudaMemsetAsync(h->ws, 0, w.total, h->stream));
+  *out = h;
+  return 0;
+}
+
+int i2c_destroy(i2c_handle_t h) {
+  if (!h) return 0;
+  cudaStreamSynchronize(h->stream);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  if (h->own_ws) cudaFree(h->ws);
+  delete h;
+  return 0;
+}
+
+}  // extern "C"
+
+// ----------------------------------------------------------------------------------------- helpers
+static int stage_in(i2c_handle_t h, const double* host, size_t elems, double** dev) {
+  REQUIRE(elems <= h->scratch_elems, "internal: staging buffer too small");
+  CUDA_OK(cudaMemcpyAsync(h->scratch, host, elems * 8, cudaMemcpyHostToDevice, h->stream));
+  *dev = h->scratch;
+  return 0;
+}
+
+static int pack(i2c_handle_t h, double* rec, const FieldMap& f, int t0, int nt, const double* host, bool bcast_b) {
+  size_t per = (size_t)f.rows * f.cols;
+  size_t elems = (size_t)(bcast_b ? 1 : h->B) * nt * per;
+  double* dev;
+  int rc = stage_in(h, host, elems, &dev);
+  if (rc) return rc;
+  size_t total = (size_t)h->Bpad * nt * per;
+  pack_kernel<<<nblocks(total), 256, 0, h->stream>>>(rec, f, t0, nt, h->T, f.per_cell ? h->cell_head : 0, h->B, h->Bpad,
+                                                     h->ntiles, dev, bcast_b ? 1 : 0);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  // the staging buffer is reused by the next call
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int unpack(i2c_handle_t h, const double* rec, const FieldMap& f, int t0, int nt, double* host) {
+  size_t per = (size_t)f.rows * f.cols;
+  size_t total = (size_t)h->B * nt * per;
+  REQUIRE(total <= h->scratch_elems, "internal: staging buffer too small");
+  unpack_kernel<<<nblocks(total), 256, 0, h->stream>>>(rec, f, t0, nt, h->T, f.per_cell ? h->cell_head : 0, h->B, h->ntiles,
+                                                       h->scratch);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(host, h->scratch, total * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static double* rec_prior(i2c_handle_t h) { return h->prior_is_A ? h->recA : h->recB; }
+static double* rec_post(i2c_handle_t h) { return h->prior_is_A ? h->recB : h->recA; }
+static double* rec_latest(i2c_handle_t h) { return h->latest_is_A ? h->recA : h->recB; }
+
+static int field_map(i2c_handle_t h, int field, FieldMap* f, double** base) {
+  const int dx = h->d.dx, du = h->d.du, n = dx + du, dz = h->d.dz, dzt = h->d.dzt;
+  const RecDims& r = h->r;
+  const int P_SIG = n, P_K = n + tri(n), P_KK = P_K + du * dx, P_SIGK = P_KK + du;
+  const int F_SIG1 = n, F_MU3 = n + tri(n), F_SIG3 = F_MU3 + dx, F_J = F_SIG3 + tri(dx);
+  FieldMap m{0, 0, 0, 1, 1, 0, 0, 1};
+  switch (field) {
+    case I2C_F_MU_XU0_M: m = {r.e_post(), 0, 0, n, 1, 0, 0, 1}; *base = rec_latest(h); break;
+    case I2C_F_SIG_XU0_M: m = {r.e_post(), P_SIG, 1, n, n, 0, 0, 1}; *base = rec_latest(h); break;
+    case I2C_F_K: m = {r.e_post(), P_K, 0, du, dx, 0, 0, 1}; *base = rec_latest(h); break;
+    case I2C_F_KK: m = {r.e_post(), P_KK, 0, du, 1, 0, 0, 1}; *base = rec_latest(h); break;
+    case I2C_F_SIGK: m = {r.e_post(), P_SIGK, 1, du, du, 0, 0, 1}; *base = rec_latest(h); break;
+    case I2C_F_PRIOR_MU: m = {r.e_post(), 0, 0, n, 1, 0, 0, 1}; *base = rec_prior(h); break;
+    case I2C_F_PRIOR_SIG: m = {r.e_post(), P_SIG, 1, n, n, 0, 0, 1}; *base = rec_prior(h); break;
+    case I2C_F_PRIOR_K: m = {r.e_post(), P_K, 0, du, dx, 0, 0, 1}; *base = rec_prior(h); break;
+    case I2C_F_MU_XU1_F: m = {r.e_filt(), 0, 0, n, 1, 0, 0, 1}; *base = h->filt; break;
+    case I2C_F_SIG_XU1_F: m = {r.e_filt(), F_SIG1, 1, n, n, 0, 0, 1}; *base = h->filt; break;
+    case I2C_F_MU_X3_F: m = {r.e_filt(), F_MU3, 0, dx, 1, 0, 0, 1}; *base = h->filt; break;
+    case I2C_F_SIG_X3_F: m = {r.e_filt(), F_SIG3, 1, dx, dx, 0, 0, 1}; *base = h->filt; break;
+    case I2C_F_J_DYN: m = {r.e_filt(), F_J, 0, n, dx, 0, 0, 1}; *base = h->filt; break;
+    case I2C_F_MU_XU0_F: m = {r.e_auxf(), 0, 0, n, 1, 0, 0, 1}; *base = h->auxf; break;
+    case I2C_F_SIG_XU0_F: m = {r.e_auxf(), n, 1, n, n, 0, 0, 1}; *base = h->auxf; break;
+    case I2C_F_MU_Z0_F: m = {r.e_auxf(), n + tri(n), 0, dz, 1, 0, 0, 1}; *base = h->auxf; break;
+    case I2C_F_SIG_Z0_F: m = {r.e_auxf(), n + tri(n) + dz, 1, dz, dz, 0, 0, 1}; *base = h->auxf; break;
+    case I2C_F_MU_Z0_M: m = {r.e_auxb(), 0, 0, dz, 1, 0, 0, 1}; *base = h->auxb; break;
+    case I2C_F_SIG_Z0_M: m = {r.e_auxb(), dz, 1, dz, dz, 0, 0, 1}; *base = h->auxb; break;
+    case I2C_F_MU_X3_M: m = {r.e_auxb(), dz + tri(dz), 0, dx, 1, 0, 0, 1}; *base = h->auxb; break;
+    case I2C_F_SIG_X3_M: m = {r.e_auxb(), dz + tri(dz) + dx, 1, dx, dx, 0, 0, 1}; *base = h->auxb; break;
+    case I2C_F_MU_XU0_PF: m = {r.e_pf(), 0, 0, n, 1, 0, 0, 1}; *base = h->pf; break;
+    case I2C_F_SIG_XU0_PF: m = {r.e_pf(), n, 1, n, n, 0, 0, 1}; *base = h->pf; break;
+    case I2C_F_MU_Z0_PF: m = {r.e_pf(), n + tri(n), 0, dz, 1, 0, 0, 1}; *base = h->pf; break;
+    case I2C_F_SIG_Z0_PF: m = {r.e_pf(), n + tri(n) + dz, 1, dz, dz, 0, 0, 1}; *base = h->pf; break;
+    case I2C_F_MU_X3_PF: m = {r.e_pf(), n + tri(n) + dz + tri(dz), 0, dx, 1, 0, 0, 1}; *base = h->pf; break;
+    case I2C_F_SIG_X3_PF: m = {r.e_pf(), n + tri(n) + dz + tri(dz) + dx, 1, dx, dx, 0, 0, 1}; *base = h->pf; break;
+    case I2C_F_MU_Z3_M: m = {r.e_term(), 0, 0, dzt, 1, 0, 0, 0}; *base = h->term; break;
+    case I2C_F_SIG_Z3_M: m = {r.e_term(), dzt, 1, dzt, dzt, 0, 0, 0}; *base = h->term; break;
+    default: return set_err(-1, "unknown field id");
+  }
+  if (*base == nullptr) return set_err(-1, "field needs a handle created with enable_aux=1");
+  *f = m;
+  return 0;
+}
+
+static void full_to_tri(const double* full, int n, double* packed) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) packed[i * (i + 1) / 2 + j] = full[i * n + j];
+}
+
+// dense SPD helpers for the handful of host-side constants (sizes <= 9)
+static bool host_chol(std::vector<double>& A, int n) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[j * n + j];
+    for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
+    if (!(d > 0.0)) return false;
+    A[j * n + j] = sqrt(d);
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[i * n + j];
+      for (int k = 0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = s / A[j * n + j];
+    }
+  }
+  return true;
+}
+static bool host_spd_inverse(const double* M, int n, double* out, double* logdet) {
+  std::vector<double> L(M, M + n * n);
+  if (!host_chol(L, n)) return false;
+  double ld = 0.0;
+  for (int i = 0; i < n; ++i) ld += 2.0 * log(L[i * n + i]);
+  if (logdet) *logdet = ld;
+  for (int c = 0; c < n; ++c) {
+    std::vector<double> y(n, 0.0);
+    for (int i = 0; i < n; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s -= L[i * n + k] * y[k];
+      y[i] = s / L[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double s = y[i];
+      for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * out[k * n + c];
+      out[i * n + c] = s / L[i * n + i];
+    }
+  }
+  return true;
+}
+
+static void cubature_rule(double a, double b, double k, int dim, double* sf, double* w0, double* wi) {
+  // CubatureQuadrature.weights (exp_types.py:40-49); the mean uses weights_sig as well (quirk A.6.1)
+  double lam = a * a * (dim + k) - dim;
+  *sf = sqrt(dim + lam);
+  *wi = 1.0 / (2.0 * (dim + lam));
+  *w0 = 2.0 * lam * (*wi) + (1.0 - a * a + b);
+}
+
+static int upload_flags(i2c_handle_t h) {
+  CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(h->cell_index_dev, h->index.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" {
+
+int i2c_set_initial_state(i2c_handle_t h, const double* x0, const double* sig_x0) {
+  REQUIRE(h && x0 && sig_x0, "NULL argument");
+  FieldMap fx{h->d.dx, 0, 0, h->d.dx, 1, 0, 0, 0};
+  int rc = pack(h, h->x0, fx, 0, 1, x0, false);
+  if (rc) return rc;
+  FieldMap fs{tri(h->d.dx), 0, 1, h->d.dx, h->d.dx, 0, 0, 0};
+  return pack(h, h->sig_x0, fs, 0, 1, sig_x0, false);
+}
+
+int i2c_set_initial_state_dev(i2c_handle_t h, const double* x0_dev, const double* sig_x0_dev) {
+  REQUIRE(h && x0_dev && sig_x0_dev, "NULL argument");
+  FieldMap fx{h->d.dx, 0, 0, h->d.dx, 1, 0, 0, 0};
+  size_t total = (size_t)h->Bpad * h->d.dx;
+  pack_kernel<<<nblocks(total), 256, 0, h->stream>>>(h->x0, fx, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles, x0_dev, 0);
+  FieldMap fs{tri(h->d.dx), 0, 1, h->d.dx, h->d.dx, 0, 0, 0};
+  total = (size_t)h->Bpad * h->d.dx * h->d.dx;
+  pack_kernel<<<nblocks(total), 256, 0, h->stream>>>(h->sig_x0, fs, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles, sig_x0_dev, 0);
+  h->launches += 2;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int i2c_get_initial_state(i2c_handle_t h, double* x0, double* sig_x0) {
+  REQUIRE(h, "NULL handle");
+  int rc = 0;
+  if (x0) {
+    FieldMap fx{h->d.dx, 0, 0, h->d.dx, 1, 0, 0, 0};
+    rc = unpack(h, h->x0, fx, 0, 1, x0);
+    if (rc) return rc;
+  }
+  if (sig_x0) {
+    FieldMap fs{tri(h->d.dx), 0, 1, h->d.dx, h->d.dx, 0, 0, 0};
+    rc = unpack(h, h->sig_x0, fs, 0, 1, sig_x0);
+  }
+  return rc;
+}
+
+int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, const double* sig_eta, const double* mu_u,
+                    const double* sig_u, const double* QR, const double* Qf, const double* z, const double* z_graph,
+                    const double* z_term, const double* alpha0, double alpha_update_tol, const double* mu_x_term,
+                    const double* sig_x_term, double dtemp, const double* env_par) {
+  REQUIRE(h && x0 && sig_x0 && sig_eta && mu_u && sig_u && QR && z && z_graph && alpha0, "NULL argument");
+  const int dx = h->d.dx, du = h->d.du, n = dx + du, dz = h->d.dz, dzt = h->d.dzt, T = h->T;
+  REQUIRE(h->d.np == 0 || env_par != nullptr, "this env needs per-problem parameters (env_par)");
+  REQUIRE((mu_x_term == nullptr) == (sig_x_term == nullptr), "covariance control needs both mu_x_term and sig_x_term");
+  KParams& kp = h->kp;
+  memset(&kp, 0, sizeof(kp));
+  // ---- constants
+  kp.qr_diag = 1;
+  for (int a = 0; a < dz; ++a)
+    for (int b = 0; b < dz; ++b) {
+      kp.QR[a * dz + b] = QR[a * dz + b];
+      if (a != b && QR[a * dz + b] != 0.0) kp.qr_diag = 0;
+    }
+  REQUIRE(host_spd_inverse(QR, dz, kp.QRinv, nullptr), "QR (block_diag(Q, R)) must be positive definite");
+  kp.has_qf = (Qf != nullptr && kHasTerm[h->cfg.env]) ? 1 : 0;
+  if (Qf != nullptr) {
+    REQUIRE(z_term != nullptr, "Qf given without z_term");
+    for (int a = 0; a < dzt * dzt; ++a) kp.Qf[a] = Qf[a];
+    REQUIRE(host_spd_inverse(Qf, dzt, kp.Qfinv, nullptr), "Qf must be positive definite");
+    for (int a = 0; a < dzt; ++a) kp.z_term[a] = z_term[a];
+  }
+  full_to_tri(sig_eta, dx, kp.sig_eta);
+  for (int a = 0; a < dz; ++a) kp.z_graph[a] = z_graph[a];
+  kp.cov_ctrl = sig_x_term != nullptr;
+  if (kp.cov_ctrl) {
+    full_to_tri(sig_x_term, dx, kp.sxt);
+    std::vector<double> inv(dx * dx);
+    REQUIRE(host_spd_inverse(sig_x_term, dx, inv.data(), &kp.sxt_logdet), "sig_x_terminal must be positive definite");
+    for (int i = 0; i < dx; ++i) {
+      kp.mu_xt[i] = mu_x_term[i];
+      double s = 0.0;
+      for (int k = 0; k < dx; ++k) s += inv[i * dx + k] * mu_x_term[k];
+      kp.sxt_inv_mu[i] = s;
+    }
+  }
+  kp.alpha_tol = alpha_update_tol;
+  cubature_rule(h->cfg.quad_alpha, h->cfg.quad_beta, h->cfg.quad_kappa, n, &kp.sf_n, &kp.w0_n, &kp.wi_n);
+  cubature_rule(h->cfg.quad_alpha, h->cfg.quad_beta, h->cfg.quad_kappa, dx, &kp.sf_x, &kp.w0_x, &kp.wi_x);
+  // ---- graph state
+  h->cell_head = 0;
+  h->flags.assign(T, I2C_CELL_INDEPENDENT | I2C_CELL_EXPERT);
+  h->flags[T - 1] |= I2C_CELL_TERMINAL;
+  h->index.resize(T);
+  for (int t = 0; t < T; ++t) h->index[t] = t;
+  h->tau = T - 1;
+  h->temp = 1.0;
+  h->dtemp = dtemp;
+  h->prior_is_A = 1;
+  h->latest_is_A = 0;
+  int rc = upload_flags(h);
+  if (rc) return rc;
+  // ---- per-problem data
+  rc = i2c_set_initial_state(h, x0, sig_x0);
+  if (rc) return rc;
+  {
+    FieldMap fa{1, 0, 0, 1, 1, 0, 0, 0};
+    // alpha is [Bpad] flat == tiles of 32 with E = 1
+    rc = pack(h, h->alpha, fa, 0, 1, alpha0, false);
+    if (rc) return rc;
+  }
+  if (h->d.np > 0) {
+    FieldMap fp{h->d.np, 0, 0, h->d.np, 1, 0, 0, 0};
+    rc = pack(h, h->envpar, fp, 0, 1, env_par, false);
+    if (rc) return rc;
+  }
+  if (h->cfg.z_per_problem) {
+    FieldMap fz{dz, 0, 0, dz, 1, 0, 0, 1};
+    rc = pack(h, h->z_cell, fz, 0, T, z, false);
+    if (rc) return rc;
+  } else {
+    CUDA_OK(cudaMemcpyAsync(h->z_cell, z, (size_t)T * dz * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
+  // ---- cells: constructor state
+  {
+    double* dev;
+    rc = stage_in(h, mu_u, (size_t)h->B * T * du, &dev);
+    if (rc) return rc;
+    InitArgs ia{dx, du, n, h->r.e_post(), T, 0, h->Bpad, h->ntiles, 0, {0, 0, 0}};
+    full_to_tri(sig_u, du, ia.sig_u);
+    h->sig_u_host.assign(ia.sig_u, ia.sig_u + tri(du));
+    init_cells_kernel<<<nblocks((size_t)h->Bpad * T), 256, 0, h->stream>>>(h->recA, h->recB, ia, 0, T, h->x0, h->sig_x0, dev,
+                                                                          h->B);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemsetAsync(h->status, 0, (size_t)h->Bpad * 4, h->stream));
+    CUDA_OK(cudaMemsetAsync(h->info, 0, (size_t)h->Bpad * 4, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
+  h->problem_set = true;
+  return 0;
+}
+
+int i2c_set_cell_flags(i2c_handle_t h, const int32_t* flags) {
+  REQUIRE(h && flags, "NULL argument");
+  for (int t = 0; t < h->T; ++t) h->flags[(t + h->cell_head) % h->T] = flags[t];
+  return upload_flags(h);
+}
+int i2c_get_cell_flags(i2c_handle_t h, int32_t* flags) {
+  REQUIRE(h && flags, "NULL argument");
+  for (int t = 0; t < h->T; ++t) flags[t] = h->flags[(t + h->cell_head) % h->T];
+  return 0;
+}
+int i2c_set_cell_index(i2c_handle_t h, const int32_t* index) {
+  REQUIRE(h && index, "NULL argument");
+  for (int t = 0; t < h->T; ++t) h->index[(t + h->cell_head) % h->T] = index[t];
+  return upload_flags(h);
+}
+int i2c_set_tau(i2c_handle_t h, int32_t tau) {
+  REQUIRE(h, "NULL handle");
+  h->tau = tau;
+  return 0;
+}
+int i2c_set_alpha(i2c_handle_t h, const double* alpha) {
+  REQUIRE(h && alpha, "NULL argument");
+  FieldMap fa{1, 0, 0, 1, 1, 0, 0, 0};
+  int rc = pack(h, h->alpha, fa, 0, 1, alpha, false);
+  if (rc) return rc;
+  for (auto& f : h->flags) f &= ~I2C_CELL_OWN_ALPHA;  // update_xi pushes sig_xi to all current cells
+  return upload_flags(h);
+}
+int i2c_get_alpha(i2c_handle_t h, double* alpha) {
+  REQUIRE(h && alpha, "NULL argument");
+  CUDA_OK(cudaMemcpyAsync(alpha, h->alpha, (size_t)h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int i2c_set_temp(i2c_handle_t h, double temp) {
+  REQUIRE(h, "NULL handle");
+  h->temp = temp;
+  return 0;
+}
+int i2c_get_temp(i2c_handle_t h, double* temp) {
+  REQUIRE(h && temp, "NULL argument");
+  *temp = h->temp;
+  return 0;
+}
+
+int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
+  REQUIRE(h, "NULL handle");
+  REQUIRE(h->problem_set, "i2c_set_problem has not been called");
+  REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "n_iter must be in [1, max_iters]");
+  REQUIRE(!(phases & I2C_PH_STORE_AUX) || h->cfg.enable_aux, "I2C_PH_STORE_AUX needs enable_aux=1");
+  REQUIRE(!(phases & I2C_PH_CALIBRATE) || (phases & I2C_PH_PROPAGATE), "CALIBRATE needs PROPAGATE");
+  KParams kp = h->kp;
+  kp.prior = rec_prior(h);
+  kp.post = rec_post(h);
+  kp.latest = rec_latest(h);
+  kp.filt = h->filt;
+  kp.auxf = h->auxf;
+  kp.auxb = h->auxb;
+  kp.pf = h->pf;
+  kp.term = h->term;
+  kp.x0 = h->x0;
+  kp.sig_x0 = h->sig_x0;
+  kp.alpha = h->alpha;
+  kp.alpha_cell = h->alpha_cell;
+  kp.z_cell = h->z_cell;
+  kp.envpar = h->envpar;
+  kp.cell_flags = h->cell_flags_dev;
+  kp.cell_index = h->cell_index_dev;
+  kp.metrics = h->metrics;
+  kp.status = h->status;
+  kp.info = h->info;
+  kp.B = h->B;
+  kp.Bpad = h->Bpad;
+  kp.ntiles = h->ntiles;
+  kp.T = h->T;
+  kp.n_iter = n_iter;
+  kp.phases = phases;
+  kp.tau = h->tau;
+  kp.max_iters = h->cfg.max_iters;
+  kp.cell_head = h->cell_head;
+  kp.z_per_problem = h->cfg.z_per_problem;
+  kp.temp0 = h->temp;
+  kp.dtemp = h->dtemp;
+  CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  int rc = launch_em(h->cfg.env, kp, (void*)h->stream);
+  if (rc != 0) return set_err(-100 - rc, std::string("EM kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+  CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+  h->launches++;
+  h->last_n_iter = n_iter;
+  // ---- mirror the state machine the kernel just executed
+  bool flip = false, alpha_pushed = false;
+  for (int it = 0; it < n_iter; ++it) {
+    if (phases & I2C_PH_BACKWARD) {
+      h->latest_is_A = h->prior_is_A ? 0 : 1;  // backward wrote `post`
+      if (h->kp.cov_ctrl) h->temp += h->dtemp;
+    }
+    if (phases & I2C_PH_UPDATE_PRIORS) {
+      if (h->latest_is_A != h->prior_is_A) h->prior_is_A = h->latest_is_A;  // swap prior/post
+      flip = true;
+    }
+    if (phases & (I2C_PH_MSTEP | I2C_PH_CALIBRATE)) alpha_pushed = true;
+  }
+  if (flip || alpha_pushed) {
+    for (int s = 0; s < h->T; ++s) {
+      if (flip && h->tau > 0 && h->index[s] <= h->tau) h->flags[s] &= ~I2C_CELL_INDEPENDENT;
+      if (alpha_pushed) h->flags[s] &= ~I2C_CELL_OWN_ALPHA;
+    }
+    CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  return 0;
+}
+
+int i2c_synchronize(i2c_handle_t h) {
+  REQUIRE(h, "NULL handle");
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int i2c_get_metric(i2c_handle_t h, int32_t metric, double* out, int32_t n_iter) {
+  REQUIRE(h && out, "NULL argument");
+  REQUIRE(metric >= 0 && metric < I2C_M_COUNT, "unknown metric id");
+  REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "bad n_iter");
+  const double* src = h->metrics + (size_t)metric * h->cfg.max_iters * h->Bpad;
+  CUDA_OK(cudaMemcpy2DAsync(out, (size_t)h->B * 8, src, (size_t)h->Bpad * 8, (size_t)h->B * 8, n_iter, cudaMemcpyDeviceToHost,
+                            h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int i2c_get_status(i2c_handle_t h, int32_t* status, int32_t* info) {
+  REQUIRE(h, "NULL handle");
+  if (status) CUDA_OK(cudaMemcpyAsync(status, h->status, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (info) CUDA_OK(cudaMemcpyAsync(info, h->info, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int i2c_field_shape(i2c_handle_t h, int32_t field, int32_t* rows, int32_t* cols) {
+  REQUIRE(h, "NULL handle");
+  FieldMap f;
+  double* base = nullptr;
+  // shape queries must work without aux buffers
+  bool had = h->cfg.enable_aux;
+  double* dummy = (double*)1;
+  double *a0 = h->auxf, *a1 = h->auxb, *a2 = h->pf;
+  if (!had) h->auxf = h->auxb = h->pf = dummy;
+  int rc = field_map(h, field, &f, &base);
+  h->auxf = a0, h->auxb = a1, h->pf = a2;
+  if (rc) return rc;
+  if (rows) *rows = f.rows;
+  if (cols) *cols = f.cols;
+  return 0;
+}
+
+int i2c_get_field(i2c_handle_t h, int32_t field, int32_t t0, int32_t t1, double* out) {
+  REQUIRE(h && out, "NULL argument");
+  FieldMap f;
+  double* base;
+  int rc = field_map(h, field, &f, &base);
+  if (rc) return rc;
+  if (!f.per_cell) {
+    t0 = 0;
+    t1 = 1;
+  }
+  REQUIRE(t0 >= 0 && t1 <= h->T && t0 < t1, "bad cell range");
+  return unpack(h, base, f, t0, t1 - t0, out);
+}
+
+int i2c_set_field(i2c_handle_t h, int32_t field, int32_t t0, int32_t t1, const double* in) {
+  REQUIRE(h && in, "NULL argument");
+  FieldMap f;
+  double* base;
+  int rc = field_map(h, field, &f, &base);
+  if (rc) return rc;
+  if (!f.per_cell) {
+    t0 = 0;
+    t1 = 1;
+  }
+  REQUIRE(t0 >= 0 && t1 <= h->T && t0 < t1, "bad cell range");
+  return pack(h, base, f, t0, t1 - t0, in, false);
+}
+
+int i2c_get_policy(i2c_handle_t h, double* K, double* k, double* sigK) {
+  REQUIRE(h, "NULL handle");
+  int rc = 0;
+  if (K && (rc = i2c_get_field(h, I2C_F_K, 0, h->T, K))) return rc;
+  if (k && (rc = i2c_get_field(h, I2C_F_KK, 0, h->T, k))) return rc;
+  if (sigK && (rc = i2c_get_field(h, I2C_F_SIGK, 0, h->T, sigK))) return rc;
+  return 0;
+}
+
+int i2c_get_policy_dev(i2c_handle_t h, double* K_dev, double* k_dev, double* sigK_dev) {
+  REQUIRE(h, "NULL handle");
+  const int fields[3] = {I2C_F_K, I2C_F_KK, I2C_F_SIGK};
+  double* outs[3] = {K_dev, k_dev, sigK_dev};
+  for (int i = 0; i < 3; ++i) {
+    if (!outs[i]) continue;
+    FieldMap f;
+    double* base;
+    int rc = field_map(h, fields[i], &f, &base);
+    if (rc) return rc;
+    size_t total = (size_t)h->B * h->T * f.rows * f.cols;
+    unpack_kernel<<<nblocks(total), 256, 0, h->stream>>>(base, f, 0, h->T, h->T, h->cell_head, h->B, h->ntiles, outs[i]);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int i2c_get_first_action(i2c_handle_t h, double* mu_u, double* sig_u) {
+  REQUIRE(h, "NULL handle");
+  const int dx = h->d.dx, du = h->d.du, n = dx + du;
+  int rc = 0;
+  if (mu_u) {
+    FieldMap f{h->r.e_post(), dx, 0, du, 1, 0, 0, 1};
+    rc = unpack(h, rec_latest(h), f, 0, 1, mu_u);
+    if (rc) return rc;
+  }
+  if (sig_u) {
+    FieldMap f{h->r.e_post(), n, 2, du, du, dx, dx, 1};
+    rc = unpack(h, rec_latest(h), f, 0, 1, sig_u);
+  }
+  return rc;
+}
+
+int i2c_shift_horizon(i2c_handle_t h, const double* z_new, const double* mu_u_init, double alpha_init) {
+  REQUIRE(h && z_new && mu_u_init, "NULL argument");
+  const int dx = h->d.dx, du = h->d.du, n = dx + du, dz = h->d.dz, T = h->T;
+  // cells.pop(0): advance the ring; the freed slot becomes the new last cell
+  h->cell_head = (h->cell_head + 1) % T;
+  const int slot = (T - 1 + h->cell_head) % T;
+  h->flags[slot] = I2C_CELL_INDEPENDENT | I2C_CELL_EXPERT | I2C_CELL_OWN_ALPHA;
+  h->index[slot] = 0;
+  int rc = upload_flags(h);
+  if (rc) return rc;
+  // deepcopy(cell_init): constructor-state records (policy/mpc.py:174-176)
+  double* dev;
+  rc = stage_in(h, mu_u_init, du, &dev);
+  if (rc) return rc;
+  InitArgs ia{dx, du, n, h->r.e_post(), T, h->cell_head, h->Bpad, h->ntiles, 1, {0, 0, 0}};
+  for (int i = 0; i < tri(du); ++i) ia.sig_u[i] = h->sig_u_host[i];
+  init_cells_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->recA, h->recB, ia, T - 1, 1, h->x0, h->sig_x0, dev, h->B);
+  fill_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->alpha_cell + (size_t)slot * h->Bpad, (size_t)h->Bpad, alpha_init);
+  h->launches += 2;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (h->cfg.z_per_problem) {
+    FieldMap fz{dz, 0, 0, dz, 1, 0, 0, 1};
+    rc = pack(h, h->z_cell, fz, T - 1, 1, z_new, false);
+  } else {
+    CUDA_OK(cudaMemcpyAsync(h->z_cell + (size_t)slot * dz, z_new, (size_t)dz * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
+  return rc;
+}
+
+int i2c_ckf_step(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta) {
+  REQUIRE(h && y && u && sig_zeta, "NULL argument");
+  REQUIRE(h->d.dy > 0, "this env defines no measurement map (only the quadrotor does)");
+  const int dx = h->d.dx, du = h->d.du, dy = h->d.dy;
+  // stage y and u (tiled) in the scratch buffer: [ntiles][dy][32] then [ntiles][du][32]
+  size_t ny = (size_t)h->ntiles * dy * TILE, nu = (size_t)h->ntiles * du * TILE;
+  REQUIRE(2 * (ny + nu) <= h->scratch_elems, "internal: staging buffer too small");
+  double* ty = h->scratch + (size_t)h->B * (dy + du);
+  double* tu = ty + ny;
+  CUDA_OK(cudaMemcpyAsync(h->scratch, y, (size_t)h->B * dy * 8, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(h->scratch + (size_t)h->B * dy, u, (size_t)h->B * du * 8, cudaMemcpyHostToDevice, h->stream));
+  FieldMap fy{dy, 0, 0, dy, 1, 0, 0, 0}, fu{du, 0, 0, du, 1, 0, 0, 0};
+  pack_kernel<<<nblocks((size_t)h->Bpad * dy), 256, 0, h->stream>>>(ty, fy, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles, h->scratch, 0);
+  pack_kernel<<<nblocks((size_t)h->Bpad * du), 256, 0, h->stream>>>(tu, fu, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles,
+                                                                    h->scratch + (size_t)h->B * dy, 0);
+  CkfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x0 = h->x0;
+  a.sig_x0 = h->sig_x0;
+  a.y = ty;
+  a.u = tu;
+  a.envpar = h->envpar;
+  a.status = h->status;
+  a.B = h->B;
+  a.ntiles = h->ntiles;
+  cubature_rule(1.0, 0.0, 0.0, dx, &a.sf, &a.w0, &a.wi);  // policy/mpc.py:121: CubatureQuadrature(1, 0, 0)
+  for (int i = 0; i < tri(dx); ++i) a.sig_eta[i] = h->kp.sig_eta[i];
+  full_to_tri(sig_zeta, dy, a.sig_zeta);
+  int rc = launch_ckf(h->cfg.env, a, (void*)h->stream);
+  h->launches += 3;
+  if (rc != 0) return set_err(-100 - rc, "CKF kernel launch failed");
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int i2c_quadrature(int32_t env, int32_t fn, int32_t n_problems, const double* m, const double* S, double quad_alpha,
+                   double quad_beta, double quad_kappa, const double* env_par, double* m_y, double* S_y, double* S_xy,
+                   int32_t* status, int32_t device) {
+  REQUIRE(env >= 0 && env < I2C_ENV_COUNT, "unknown env id (no CPU fallback for unregistered callables)");
+  REQUIRE(fn >= 0 && fn <= 3 && n_problems >= 1 && m && S && m_y && S_y && S_xy, "bad argument");
+  const EnvDims& d = kEnv[env];
+  REQUIRE(d.np == 0 || env_par, "this env needs env_par");
+  REQUIRE(fn != 3 || d.dy > 0, "this env defines no measurement map");
+  REQUIRE(fn != 1 || kHasTerm[env], "this env defines no terminal cost features");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_err(-2, "no CUDA device available: the i2c hot path has no CPU fallback");
+  CUDA_OK(cudaSetDevice(device));
+  const int n = d.dx + d.du;
+  const int D = (fn == 0 || fn == 2) ? n : d.dx;
+  const int DY = fn == 0 ? d.dz : (fn == 1 ? d.dzt : (fn == 2 ? d.dx : d.dy));
+  const int B = n_problems, Bpad = (int)align_up((size_t)B, TILE), nt = Bpad / TILE;
+  const int np = d.np > 0 ? d.np : 1;
+  size_t canon = (size_t)B * (D + D * D + DY + DY * DY + D * DY + np);
+  size_t tiled = (size_t)Bpad * (D + tri(D) + DY + tri(DY) + D * DY + np);
+  double* buf = nullptr;
+  int32_t* st = nullptr;
+  CUDA_OK(cudaMalloc((void**)&buf, (canon + tiled) * 8));
+  CUDA_OK(cudaMalloc((void**)&st, (size_t)Bpad * 4));
+  double *c_m = buf, *c_S = c_m + (size_t)B * D, *c_my = c_S + (size_t)B * D * D, *c_Sy = c_my + (size_t)B * DY,
+         *c_Sxy = c_Sy + (size_t)B * DY * DY, *c_par = c_Sxy + (size_t)B * D * DY;
+  double *t_m = buf + canon, *t_S = t_m + (size_t)Bpad * D, *t_my = t_S + (size_t)Bpad * tri(D),
+         *t_Sy = t_my + (size_t)Bpad * DY, *t_Sxy = t_Sy + (size_t)Bpad * tri(DY), *t_par = t_Sxy + (size_t)Bpad * D * DY;
+  cudaStream_t s = 0;
+  int rc = 0;
+  do {
+    if (cudaMemcpyAsync(c_m, m, (size_t)B * D * 8, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(c_S, S, (size_t)B * D * D * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+      rc = set_err(-3, "H2D copy failed");
+      break;
+    }
+    FieldMap fm{D, 0, 0, D, 1, 0, 0, 0}, fS{tri(D), 0, 1, D, D, 0, 0, 0};
+    pack_kernel<<<nblocks((size_t)Bpad * D), 256, 0, s>>>(t_m, fm, 0, 1, 1, 0, B, Bpad, nt, c_m, 0);
+    pack_kernel<<<nblocks((size_t)Bpad * D * D), 256, 0, s>>>(t_S, fS, 0, 1, 1, 0, B, Bpad, nt, c_S, 0);
+    if (d.np > 0) {
+      cudaMemcpyAsync(c_par, env_par, (size_t)B * np * 8, cudaMemcpyHostToDevice, s);
+      FieldMap fp{np, 0, 0, np, 1, 0, 0, 0};
+      pack_kernel<<<nblocks((size_t)Bpad * np), 256, 0, s>>>(t_par, fp, 0, 1, 1, 0, B, Bpad, nt, c_par, 0);
+    }
+    QuadArgs a;
+    a.m = t_m, a.S = t_S, a.envpar = t_par, a.my = t_my, a.Sy = t_Sy, a.Sxy = t_Sxy, a.status = st;
+    a.B = B, a.ntiles = nt;
+    cubature_rule(quad_alpha, quad_beta, quad_kappa, D, &a.sf, &a.w0, &a.wi);
+    int lrc = launch_quadrature(env, fn, a, (void*)s);
+    if (lrc != 0) {
+      rc = set_err(-100 - lrc, "quadrature kernel launch failed");
+      break;
+    }
+    FieldMap fy{DY, 0, 0, DY, 1, 0, 0, 0}, fSy{tri(DY), 0, 1, DY, DY, 0, 0, 0}, fxy{D * DY, 0, 0, D, DY, 0, 0, 0};
+    unpack_kernel<<<nblocks((size_t)B * DY), 256, 0, s>>>(t_my, fy, 0, 1, 1, 0, B, nt, c_my);
+    unpack_kernel<<<nblocks((size_t)B * DY * DY), 256, 0, s>>>(t_Sy, fSy, 0, 1, 1, 0, B, nt, c_Sy);
+    unpack_kernel<<<nblocks((size_t)B * D * DY), 256, 0, s>>>(t_Sxy, fxy, 0, 1, 1, 0, B, nt, c_Sxy);
+    cudaMemcpyAsync(m_y, c_my, (size_t)B * DY * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(S_y, c_Sy, (size_t)B * DY * DY * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(S_xy, c_Sxy, (size_t)B * D * DY * 8, cudaMemcpyDeviceToHost, s);
+    if (status) cudaMemcpyAsync(status, st, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = set_err(-100 - (int)e, std::string("quadrature: ") + cudaGetErrorString(e));
+  } while (0);
+  cudaFree(buf);
+  cudaFree(st);
+  return rc;
+}
+
+// ---- snapshot / restore: [host state blob][workspace bytes]
+struct SnapHeader {
+  uint64_t magic, ws_bytes;
+  int32_t prior_is_A, latest_is_A, cell_head, tau, last_n_iter, problem_set, T, pad;
+  double temp, dtemp;
+  KParams kp;
+};
+
+int i2c_snapshot_bytes(i2c_handle_t h, size_t* bytes) {
+  REQUIRE(h && bytes, "NULL argument");
+  *bytes = sizeof(SnapHeader) + (size_t)h->T * 8 + 3 * 8 + h->ws_bytes;
+  return 0;
+}
+
+int i2c_snapshot(i2c_handle_t h, void* host_buf, size_t bytes) {
+  REQUIRE(h && host_buf, "NULL argument");
+  size_t need;
+  i2c_snapshot_bytes(h, &need);
+  REQUIRE(bytes >= need, "snapshot buffer too small");
+  SnapHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.magic = 0x6932635f62323030ull;
+  hd.ws_bytes = h->ws_bytes;
+  hd.prior_is_A = h->prior_is_A, hd.latest_is_A = h->latest_is_A, hd.cell_head = h->cell_head, hd.tau = h->tau;
+  hd.last_n_iter = h->last_n_iter, hd.problem_set = h->problem_set, hd.T = h->T;
+  hd.temp = h->temp, hd.dtemp = h->dtemp;
+  hd.kp = h->kp;
+  char* p = (char*)host_buf;
+  memcpy(p, &hd, sizeof(hd));
+  p += sizeof(hd);
+  memcpy(p, h->flags.data(), (size_t)h->T * 4);
+  p += (size_t)h->T * 4;
+  memcpy(p, h->index.data(), (size_t)h->T * 4);
+  p += (size_t)h->T * 4;
+  double su[3] = {0, 0, 0};
+  for (size_t i = 0; i < h->sig_u_host.size() && i < 3; ++i) su[i] = h->sig_u_host[i];
+  memcpy(p, su, 24);
+  p += 24;
+  CUDA_OK(cudaMemcpyAsync(p, h->ws, h->ws_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int i2c_restore(i2c_handle_t h, const void* host_buf, size_t bytes) {
+  REQUIRE(h && host_buf, "NULL argument");
+  REQUIRE(bytes >= sizeof(SnapHeader), "snapshot too small");
+  SnapHeader hd;
+  const char* p = (const char*)host_buf;
+  memcpy(&hd, p, sizeof(hd));
+  REQUIRE(hd.magic == 0x6932635f62323030ull && hd.ws_bytes == h->ws_bytes && hd.T == h->T,
+          "snapshot does not match this handle's configuration");
+  p += sizeof(hd);
+  h->prior_is_A = hd.prior_is_A, h->latest_is_A = hd.latest_is_A, h->cell_head = hd.cell_head, h->tau = hd.tau;
+  h->last_n_iter = hd.last_n_iter, h->problem_set = hd.problem_set != 0;
+  h->temp = hd.temp, h->dtemp = hd.dtemp;
+  h->kp = hd.kp;
+  h->flags.resize(h->T);
+  h->index.resize(h->T);
+  memcpy(h->flags.data(), p, (size_t)h->T * 4);
+  p += (size_t)h->T * 4;
+  memcpy(h->index.data(), p, (size_t)h->T * 4);
+  p += (size_t)h->T * 4;
+  double su[3];
+  memcpy(su, p, 24);
+  p += 24;
+  h->sig_u_host.assign(su, su + tri(h->d.du));
+  CUDA_OK(cudaMemcpyAsync(h->ws, p, h->ws_bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int i2c_dfma_peak(int32_t device, double* tflops) {
+  REQUIRE(tflops != nullptr, "NULL argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(-2, "no CUDA device available");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 14;
+  double* out = nullptr;
+  CUDA_OK(cudaMalloc((void**)&out, (size_t)threads * blocks * 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0, 0);
+    dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  CUDA_OK(cudaGetLastError());
+  *tflops = best;
+  return 0;
+}
+
+int i2c_kernel_launches(i2c_handle_t h, int64_t* n) {
+  REQUIRE(h && n, "NULL argument");
+  *n = h->launches;
+  return 0;
+}
+
+int i2c_last_run_ms(i2c_handle_t h, float* ms) {
+  REQUIRE(h && ms, "NULL argument");
+  CUDA_OK(cudaEventSynchronize(h->ev1));
+  CUDA_OK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return 0;
+}
+
+}  // extern "C"

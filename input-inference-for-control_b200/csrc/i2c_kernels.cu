@@ -1,0 +1,1170 @@
+// Persistent fp64 kernels of the Gaussian i2c EM sweep for sm_100a.
+//
+// One thread owns one problem for the whole launch: it runs the forward filter over the horizon, the
+// backward smoother (with the M-step statistics fused in), optionally the closed-loop propagate sweep,
+// then the alpha update -- for all requested EM iterations -- without leaving the kernel.  Problems are
+// independent, so no inter-thread synchronisation is needed; the recursion state (mean / covariance /
+// Cholesky factor of the dx-dimensional message) is carried in registers between timesteps and all
+// small dense algebra (Cholesky, triangular solves, Gaussian conditioning) is fully unrolled over
+// packed-lower-triangular register arrays.  Per-cell records live in HBM in the tiled layout described
+// in i2c_types.h: every global access of a warp is a 256-byte coalesced segment.
+//
+// Reference arithmetic restated here (paths relative to the reference root):
+//   forward cell  i2c/i2c.py:350-447     backward cell  i2c/i2c.py:544-610
+//   propagate     i2c/i2c.py:150-199     M-step         i2c/i2c.py:1004-1065, 913-981
+//   quadrature    i2c/inference/quadrature.py:15-58, i2c/exp_types.py:36-49
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "envs.cuh"
+#include "i2c_types.h"
+
+namespace i2c {
+
+template <class Env>
+struct Lay {
+  static constexpr int DX = Env::DX, DU = Env::DU, N = DX + DU, DZ = Env::DZ, DZT = Env::DZT;
+  // posterior / prior record
+  static constexpr int P_MU = 0, P_SIG = N, P_K = P_SIG + TRI(N), P_KK = P_K + DU * DX, P_SIGK = P_KK + DU;
+  static constexpr int E_POST = P_SIGK + TRI(DU);
+  // filtered record
+  static constexpr int F_MU1 = 0, F_SIG1 = N, F_MU3 = F_SIG1 + TRI(N), F_SIG3 = F_MU3 + DX, F_J = F_SIG3 + TRI(DX);
+  static constexpr int E_FILT = F_J + N * DX;
+  static constexpr int AF_MU0 = 0, AF_SIG0 = N, AF_MUZ = AF_SIG0 + TRI(N), AF_SIGZ = AF_MUZ + DZ;
+  static constexpr int E_AUXF = AF_SIGZ + TRI(DZ);
+  static constexpr int AB_MUZ = 0, AB_SIGZ = DZ, AB_MU3M = AB_SIGZ + TRI(DZ), AB_SIG3M = AB_MU3M + DX;
+  static constexpr int E_AUXB = AB_SIG3M + TRI(DX);
+  static constexpr int PF_MU = 0, PF_SIG = N, PF_MUZ = PF_SIG + TRI(N), PF_SIGZ = PF_MUZ + DZ, PF_MU3 = PF_SIGZ + TRI(DZ),
+                       PF_SIG3 = PF_MU3 + DX;
+  static constexpr int E_PF = PF_SIG3 + TRI(DX);
+  static constexpr int TM_MU = 0, TM_SIG = DZT, E_TERM = DZT + TRI(DZT);
+};
+
+// ------------------------------------------------------------------------------------------------
+// Sigma-point transform (inference/quadrature.py:15-58) around (m, chol L) in dimension D.
+//   my  = sum_p w_p y_p                        (mean uses weights_sig: quirk A.6.1)
+//   Syy = sum_p w_p y_p y_p^T - my my^T        (packed lower, no noise added)
+//   Dm[j][:] = w * sf * (y_{+j} - y_{-j})      so that  S_xy = L * Dm  (exact rewrite of
+//              sum_p w_p x_p y_p^T - m my^T for the symmetric point set m +- sf L[:,j])
+template <int D, int DY, class Eval>
+__device__ __forceinline__ void sigma_transform(const double* m, const double* L, double sf, double w0, double wi,
+                                                Eval&& eval, double* my, double* Syy, double* Dm) {
+  double sy[DY], syy[TRI(DY)];
+#pragma unroll
+  for (int a = 0; a < DY; ++a) sy[a] = 0.0;
+#pragma unroll
+  for (int a = 0; a < TRI(DY); ++a) syy[a] = 0.0;
+  const double wsf = wi * sf;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double xp[D], xm[D], yp[DY], ym[DY];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (i >= j) {
+        double d = sf * L[tix(i, j)];
+        xp[i] = m[i] + d;
+        xm[i] = m[i] - d;
+      } else {
+        xp[i] = m[i];
+        xm[i] = m[i];
+      }
+    }
+    eval(xp, j, yp);
+    eval(xm, j, ym);
+#pragma unroll
+    for (int a = 0; a < DY; ++a) {
+      sy[a] += yp[a] + ym[a];
+      Dm[j * DY + a] = wsf * (yp[a] - ym[a]);
+#pragma unroll
+      for (int b = 0; b <= a; ++b) syy[tix(a, b)] = fma(yp[a], yp[b], fma(ym[a], ym[b], syy[tix(a, b)]));
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < DY; ++a) my[a] = wi * sy[a];
+#pragma unroll
+  for (int a = 0; a < TRI(DY); ++a) Syy[a] = wi * syy[a];
+  if (w0 != 0.0) {  // centre point only contributes for alpha != 1 or beta != 0 (exp_types.py:40-49)
+    double y0[DY];
+    eval(m, -1, y0);
+#pragma unroll
+    for (int a = 0; a < DY; ++a) {
+      my[a] = fma(w0, y0[a], my[a]);
+#pragma unroll
+      for (int b = 0; b <= a; ++b) Syy[tix(a, b)] = fma(w0 * y0[a], y0[b], Syy[tix(a, b)]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < DY; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) Syy[tix(a, b)] = fma(-my[a], my[b], Syy[tix(a, b)]);
+}
+
+// S_xy[i][a] = sum_{j<=i} L[i][j] Dm[j][a]
+template <int D, int DY>
+__device__ __forceinline__ void cross_cov(const double* L, const double* Dm, double* Sxy) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int a = 0; a < DY; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j <= i; ++j) s = fma(L[tix(i, j)], Dm[j * DY + a], s);
+      Sxy[i * DY + a] = s;
+    }
+}
+
+// Gaussian conditioning on an observation with moments (my, Sy incl. noise, Sxy) and target z:
+//   G = Sxy Sy^{-1};  mu += G (z - my);  Sig -= G Sxy^T      (i2c.py:398-403 / :438-443)
+// done through the Cholesky factor of Sy: W_i = Ly^{-1} Sxy[i,:]^T, r = Ly^{-1}(z - my).
+template <int D, int DY>
+__device__ __forceinline__ bool condition(double* mu, double* Sig, double* Sy, const double* Sxy, const double* my,
+                                          const double* z) {
+  double invd[DY];
+  bool ok = chol_rows<DY>(Sy, invd);
+  double r[DY];
+#pragma unroll
+  for (int a = 0; a < DY; ++a) r[a] = z[a] - my[a];
+  fwd_subst<DY>(Sy, invd, r);
+  double W[D * DY];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double w[DY];
+#pragma unroll
+    for (int a = 0; a < DY; ++a) w[a] = Sxy[i * DY + a];
+    fwd_subst<DY>(Sy, invd, w);
+    double dm = 0.0;
+#pragma unroll
+    for (int a = 0; a < DY; ++a) {
+      W[i * DY + a] = w[a];
+      dm = fma(w[a], r[a], dm);
+    }
+    mu[i] += dm;
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double s = Sig[tix(i, j)];
+#pragma unroll
+      for (int a = 0; a < DY; ++a) s = fma(-W[i * DY + a], W[j * DY + a], s);
+      Sig[tix(i, j)] = s;
+    }
+  return ok;
+}
+
+// quadratic-cost statistics of a Gaussian cost feature (i2c.py:1034-1043 and :680-683, :913-919)
+//   mean = e^T QR e + tr(Sz QR),  var = 2 tr((Sz QR)^2) + 4 e^T QR Sz QR e,   e = mz - zref
+template <int DZ>
+__device__ __forceinline__ void cost_stats(const KParams& p, const double* mz, const double* Sz, const double* zref,
+                                           double& mean, double& var) {
+  double e[DZ], v[DZ];
+#pragma unroll
+  for (int a = 0; a < DZ; ++a) e[a] = mz[a] - zref[a];
+  if (p.qr_diag) {
+    double m = 0.0, t2 = 0.0, q4 = 0.0;
+#pragma unroll
+    for (int a = 0; a < DZ; ++a) v[a] = p.QR[a * DZ + a] * e[a];
+#pragma unroll
+    for (int a = 0; a < DZ; ++a) {
+      m = fma(e[a], v[a], m);
+      m = fma(Sz[tix(a, a)], p.QR[a * DZ + a], m);
+    }
+#pragma unroll
+    for (int a = 0; a < DZ; ++a)
+#pragma unroll
+      for (int b = 0; b < DZ; ++b) {
+        double s = Sz[six(a, b)];
+        t2 = fma(s * s, p.QR[a * DZ + a] * p.QR[b * DZ + b], t2);
+        q4 = fma(v[a] * s, v[b], q4);
+      }
+    mean = m;
+    var = 2.0 * t2 + 4.0 * q4;
+  } else {
+    double P[DZ * DZ];  // Sz QR
+#pragma unroll
+    for (int a = 0; a < DZ; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < DZ; ++b) s = fma(p.QR[a * DZ + b], e[b], s);
+      v[a] = s;
+    }
+#pragma unroll
+    for (int a = 0; a < DZ; ++a)
+#pragma unroll
+      for (int b = 0; b < DZ; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < DZ; ++c) s = fma(Sz[six(a, c)], p.QR[c * DZ + b], s);
+        P[a * DZ + b] = s;
+      }
+    double m = 0.0, t2 = 0.0, q4 = 0.0;
+#pragma unroll
+    for (int a = 0; a < DZ; ++a) {
+      m = fma(e[a], v[a], m);
+      m += P[a * DZ + a];
+#pragma unroll
+      for (int b = 0; b < DZ; ++b) {
+        t2 = fma(P[a * DZ + b], P[b * DZ + a], t2);
+        q4 = fma(v[a] * Sz[six(a, b)], v[b], q4);
+      }
+    }
+    mean = m;
+    var = 2.0 * t2 + 4.0 * q4;
+  }
+}
+
+// tr(QR (d d^T + Sz)),  d = z - mz     (expected_observation_covar + calculate_alpha numerator)
+template <int DZ>
+__device__ __forceinline__ double alpha_trace(const double* Q, int qr_diag, const double* mz, const double* Sz,
+                                              const double* z) {
+  double d[DZ];
+#pragma unroll
+  for (int a = 0; a < DZ; ++a) d[a] = z[a] - mz[a];
+  double tr = 0.0;
+  if (qr_diag) {
+#pragma unroll
+    for (int a = 0; a < DZ; ++a) tr = fma(Q[a * DZ + a], fma(d[a], d[a], Sz[tix(a, a)]), tr);
+  } else {
+#pragma unroll
+    for (int a = 0; a < DZ; ++a)
+#pragma unroll
+      for (int b = 0; b < DZ; ++b) tr = fma(Q[a * DZ + b], fma(d[b], d[a], Sz[six(b, a)]), tr);
+  }
+  return tr;
+}
+
+// message carried between cells: dx-dimensional Gaussian + its Cholesky factor
+template <int DX>
+struct Carry {
+  double m[DX], S[TRI(DX)], L[TRI(DX)], invd[DX];
+};
+
+template <class Env>
+struct Worker {
+  using LY = Lay<Env>;
+  static constexpr int DX = LY::DX, DU = LY::DU, N = LY::N, DZ = LY::DZ, DZT = LY::DZT;
+  using TrigT = typename Env::TrigT;
+
+  const KParams& p;
+  const int tile, lane, b;
+  double par[Env::NP > 0 ? Env::NP : 1];
+  int status, info;
+  // record views: the forward sweep reads `prior`, the backward sweep writes `post`, propagate reads the
+  // most recently written posterior `latest`; _update_priors swaps prior/post instead of copying.
+  double *prior, *post, *latest;
+  bool own_alpha_valid;
+
+  __device__ Worker(const KParams& p_, int tile_, int lane_) : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_) {
+    status = I2C_OK;
+    info = 0;
+    prior = p.prior;
+    post = p.post;
+    latest = p.latest;
+    own_alpha_valid = true;
+#pragma unroll
+    for (int i = 0; i < Env::NP; ++i) par[i] = p.envpar[((size_t)tile * Env::NP + i) * TILE + lane];
+  }
+
+  __device__ __forceinline__ int slot(int t) const {
+    int s = t + p.cell_head;
+    return s >= p.T ? s - p.T : s;
+  }
+  __device__ __forceinline__ double* rec(double* base, int t, int E) const {
+    return base + ((size_t)slot(t) * p.ntiles + tile) * (size_t)E * TILE + lane;
+  }
+  __device__ __forceinline__ void fail(int code, int it, int t) {
+    if (status == I2C_OK) {
+      status = code;
+      info = (it << 16) | (t & 0xffff);
+    }
+  }
+  __device__ __forceinline__ void load_z(int t, double* z) const {
+    if (p.z_per_problem) {
+      const double* q = p.z_cell + ((size_t)slot(t) * p.ntiles + tile) * DZ * TILE + lane;
+#pragma unroll
+      for (int a = 0; a < DZ; ++a) z[a] = q[a * TILE];
+    } else {
+#pragma unroll
+      for (int a = 0; a < DZ; ++a) z[a] = p.z_cell[slot(t) * DZ + a];
+    }
+  }
+  __device__ __forceinline__ double cell_alpha(int t, int flags, double alpha) const {
+    return ((flags & I2C_CELL_OWN_ALPHA) && own_alpha_valid) ? p.alpha_cell[(size_t)slot(t) * p.Bpad + b] : alpha;
+  }
+
+  // exp(-1/2 d^T C^-1 d): the pdf ratio w/Z of i2c.py:369-374 (scipy multivariate_normal)
+  __device__ __forceinline__ bool pdf_ratio(const double* C_in, const double* d_in, double& rho) {
+    double C[TRI(DX)], invd[DX], d[DX];
+#pragma unroll
+    for (int i = 0; i < TRI(DX); ++i) C[i] = C_in[i];
+#pragma unroll
+    for (int i = 0; i < DX; ++i) d[i] = d_in[i];
+    bool ok = chol_rows<DX>(C, invd);
+    fwd_subst<DX>(C, invd, d);
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < DX; ++i) q = fma(d[i], d[i], q);
+    rho = exp(-0.5 * q);
+    return ok;
+  }
+
+  // Joint (x,u) Gaussian under a linear-Gaussian controller around the incoming state message:
+  //   mu = [m0; mu_u + Kt (m0 - mu_x_ref)],  Sigma = [[S0, S0 Kt^T],[Kt S0, Su]]
+  // Writes mu[N], Sig[TRI N] and the Cholesky factor L[TRI N] (rows < DX reuse the carried factor).
+  __device__ __forceinline__ bool build_joint(const Carry<DX>& c, const double* Kt, const double* mu_u, const double* Suu,
+                                              bool coupled, double* mu, double* Sig, double* L, double* invd) {
+#pragma unroll
+    for (int i = 0; i < DX; ++i) mu[i] = c.m[i];
+#pragma unroll
+    for (int i = 0; i < TRI(DX); ++i) {
+      Sig[i] = c.S[i];
+      L[i] = c.L[i];
+    }
+#pragma unroll
+    for (int i = 0; i < DX; ++i) invd[i] = c.invd[i];
+#pragma unroll
+    for (int r = 0; r < DU; ++r) {
+      mu[DX + r] = mu_u[r];
+#pragma unroll
+      for (int j = 0; j < DX; ++j) {
+        double s = 0.0;
+        if (coupled) {
+#pragma unroll
+          for (int k = 0; k < DX; ++k) s = fma(Kt[r * DX + k], c.S[six(k, j)], s);
+        }
+        Sig[tix(DX + r, j)] = s;
+        L[tix(DX + r, j)] = s;
+      }
+#pragma unroll
+      for (int q = 0; q <= r; ++q) {
+        Sig[tix(DX + r, DX + q)] = Suu[tix(r, q)];
+        L[tix(DX + r, DX + q)] = Suu[tix(r, q)];
+      }
+    }
+    return chol_rows<N, DX>(L, invd);
+  }
+
+  // ---------------------------------------------------------------------------------- forward cell
+  // I2cCell._forward_msgs_quadrature (i2c.py:350-447).  c: (mu_x0_f, sig_x0_f) in, (mu_x3_f, sig_x3_f) out.
+  __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, Carry<DX>& c,
+                                               LogAcc& ent_x) {
+    const double* pr = rec(prior, t, LY::E_POST);
+    double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
+    {
+      double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];
+#pragma unroll
+      for (int r = 0; r < DU; ++r) mu_u[r] = pr[(LY::P_MU + DX + r) * TILE];
+#pragma unroll
+      for (int r = 0; r < DU; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) Suu[tix(r, q)] = pr[(LY::P_SIG + tix(DX + r, DX + q)) * TILE];
+      const bool indep = flags & I2C_CELL_INDEPENDENT;
+      if (!indep) {
+        // feedback prior (i2c.py:361-387): K <- K * N(mu_x0_f; mu_prev, C)/N(mu_prev; mu_prev, C), C = Sig_xx + sig_x0_f
+        double mx[DX], Sxx[TRI(DX)], Sux[DU * DX], C[TRI(DX)], d[DX];
+#pragma unroll
+        for (int i = 0; i < DX; ++i) mx[i] = pr[(LY::P_MU + i) * TILE];
+#pragma unroll
+        for (int i = 0; i < TRI(DX); ++i) Sxx[i] = pr[(LY::P_SIG + i) * TILE];
+#pragma unroll
+        for (int r = 0; r < DU; ++r)
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            Sux[r * DX + j] = pr[(LY::P_SIG + tix(DX + r, j)) * TILE];
+            Kt[r * DX + j] = pr[(LY::P_K + r * DX + j) * TILE];
+          }
+#pragma unroll
+        for (int i = 0; i < TRI(DX); ++i) C[i] = Sxx[i] + c.S[i];
+#pragma unroll
+        for (int i = 0; i < DX; ++i) d[i] = c.m[i] - mx[i];
+        double rho;
+        if (!pdf_ratio(C, d, rho)) fail(I2C_FAIL_MVN, it, t);
+#pragma unroll
+        for (int i = 0; i < DU * DX; ++i) Kt[i] *= rho;
+        // mu_u0_f = mu_u0_m + K (mu_x0_f - mu_x0_m);  sig_u0_f = sig_u0_m - K sig_ux^T + K sig_x0_f K^T
+        double KS[DU * DX];
+#pragma unroll
+        for (int r = 0; r < DU; ++r)
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < DX; ++k) s = fma(Kt[r * DX + k], c.S[six(k, j)], s);
+            KS[r * DX + j] = s;
+          }
+#pragma unroll
+        for (int r = 0; r < DU; ++r) {
+          double s = mu_u[r];
+#pragma unroll
+          for (int k = 0; k < DX; ++k) s = fma(Kt[r * DX + k], d[k], s);
+          mu_u[r] = s;
+#pragma unroll
+          for (int q = 0; q <= r; ++q) {
+            double v = Suu[tix(r, q)];
+#pragma unroll
+            for (int k = 0; k < DX; ++k) v = fma(-Kt[r * DX + k], Sux[q * DX + k], v);
+#pragma unroll
+            for (int k = 0; k < DX; ++k) v = fma(KS[r * DX + k], Kt[q * DX + k], v);
+            Suu[tix(r, q)] = v;
+          }
+        }
+      }
+      if (!build_joint(c, Kt, mu_u, Suu, !indep, mu, Sig, L, invd)) fail(I2C_FAIL_CHOL_PRIOR, it, t);
+    }
+    double* af = aux ? rec(p.auxf, t, LY::E_AUXF) : nullptr;
+    if (aux) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) af[(LY::AF_MU0 + i) * TILE] = mu[i];
+#pragma unroll
+      for (int i = 0; i < TRI(N); ++i) af[(LY::AF_SIG0 + i) * TILE] = Sig[i];
+    }
+
+    // ---- cost observation update (i2c.py:390-404)
+    {
+      double mz[DZ], Sz[TRI(DZ)], Dm[N * DZ], Sxy[N * DZ], z[DZ];
+      TrigT ctx;
+      Env::center(mu, ctx);
+      sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                             [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
+      cross_cov<N, DZ>(L, Dm, Sxy);
+      const double a_cell = cell_alpha(t, flags, alpha);
+#pragma unroll
+      for (int a = 0; a < DZ; ++a)
+#pragma unroll
+        for (int bb = 0; bb <= a; ++bb) Sz[tix(a, bb)] = fma(a_cell, p.QRinv[a * DZ + bb], Sz[tix(a, bb)]);
+      if (aux) {
+#pragma unroll
+        for (int i = 0; i < DZ; ++i) af[(LY::AF_MUZ + i) * TILE] = mz[i];
+#pragma unroll
+        for (int i = 0; i < TRI(DZ); ++i) af[(LY::AF_SIGZ + i) * TILE] = Sz[i];
+      }
+      load_z(t, z);
+      if (!condition<N, DZ>(mu, Sig, Sz, Sxy, mz, z)) fail(I2C_FAIL_CHOL_OBS, it, t);
+    }
+    double* fr = rec(p.filt, t, LY::E_FILT);
+#pragma unroll
+    for (int i = 0; i < N; ++i) fr[(LY::F_MU1 + i) * TILE] = mu[i];
+#pragma unroll
+    for (int i = 0; i < TRI(N); ++i) fr[(LY::F_SIG1 + i) * TILE] = Sig[i];
+
+    // ---- dynamics moment matching (i2c.py:415-428)
+#pragma unroll
+    for (int i = 0; i < TRI(N); ++i) L[i] = Sig[i];
+    if (!chol_rows<N>(L, invd)) fail(I2C_FAIL_CHOL_FILTERED, it, t);
+    {
+      double Dm[N * DX], Sxy[N * DX];
+      TrigT ctx;
+      Env::center(mu, ctx);
+      sigma_transform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                             [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Dm);
+      cross_cov<N, DX>(L, Dm, Sxy);
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) {
+        c.S[i] += p.sig_eta[i];
+        c.L[i] = c.S[i];
+      }
+      if (!chol_rows<DX>(c.L, c.invd)) fail(I2C_FAIL_CHOL_X3, it, t);
+      // J_dyn = Sxy Sig_x3^{-1}  (n x dx)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double w[DX];
+#pragma unroll
+        for (int a = 0; a < DX; ++a) w[a] = Sxy[i * DX + a];
+        fwd_subst<DX>(c.L, c.invd, w);
+        bwd_subst<DX>(c.L, c.invd, w);
+#pragma unroll
+        for (int a = 0; a < DX; ++a) fr[(LY::F_J + i * DX + a) * TILE] = w[a];
+      }
+    }
+    // ---- terminal cost update on the outgoing message (i2c.py:430-443)
+    if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf) {
+      double mz[DZT], Sz[TRI(DZT)], Dm[DX * DZT], Sxy[DX * DZT];
+      TrigT ctx;
+      Env::center(c.m, ctx);
+      sigma_transform<DX, DZT>(c.m, c.L, p.sf_x, p.w0_x, p.wi_x,
+                               [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Dm);
+      cross_cov<DX, DZT>(c.L, Dm, Sxy);
+      const double a_cell = cell_alpha(t, flags, alpha);
+#pragma unroll
+      for (int a = 0; a < DZT; ++a)
+#pragma unroll
+        for (int bb = 0; bb <= a; ++bb) Sz[tix(a, bb)] = fma(a_cell, p.Qfinv[a * DZT + bb], Sz[tix(a, bb)]);
+      if (!condition<DX, DZT>(c.m, c.S, Sz, Sxy, mz, p.z_term)) fail(I2C_FAIL_CHOL_TERMINAL, it, t);
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) c.L[i] = c.S[i];
+      if (!chol_rows<DX>(c.L, c.invd)) fail(I2C_FAIL_CHOL_TERMINAL, it, t);
+    }
+#pragma unroll
+    for (int i = 0; i < DX; ++i) {
+      fr[(LY::F_MU3 + i) * TILE] = c.m[i];
+      ent_x.mul(c.L[tix(i, i)]);
+    }
+#pragma unroll
+    for (int i = 0; i < TRI(DX); ++i) fr[(LY::F_SIG3 + i) * TILE] = c.S[i];
+  }
+
+  // ---------------------------------------------------------------------------------- backward cell
+  // I2cCell._backward_msgs_quadrature (i2c.py:544-610) for a non-final cell, with the per-cell M-step
+  // statistics fused in.  (m3m, S3m) in: next cell's (mu_x0_m, sig_x0_m); out: this cell's.
+  struct Stats {
+    double cost, cost_var, tr;
+    LogAcc ent_u;
+  };
+  __device__ __forceinline__ void backward_cell(int it, int t, int flags, bool aux, double* m3m, double* S3m, Stats& st) {
+    const double* fr = rec(p.filt, t, LY::E_FILT);
+    double mu[N], Sig[TRI(N)], J[N * DX];
+    {
+      double dm[DX], dS[TRI(DX)];
+#pragma unroll
+      for (int i = 0; i < DX; ++i) dm[i] = m3m[i] - fr[(LY::F_MU3 + i) * TILE];
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) dS[i] = S3m[i] - fr[(LY::F_SIG3 + i) * TILE];
+#pragma unroll
+      for (int i = 0; i < N * DX; ++i) J[i] = fr[(LY::F_J + i) * TILE];
+      if (aux) {
+        double* ab = rec(p.auxb, t, LY::E_AUXB);
+#pragma unroll
+        for (int i = 0; i < DX; ++i) ab[(LY::AB_MU3M + i) * TILE] = m3m[i];
+#pragma unroll
+        for (int i = 0; i < TRI(DX); ++i) ab[(LY::AB_SIG3M + i) * TILE] = S3m[i];
+      }
+      // mu_xu1_m = mu_xu1_f + J (mu_x3_m - mu_x3_f);  sig_xu1_m = sig_xu1_f + J (sig_x3_m - sig_x3_f) J^T
+      double JD[N * DX];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double s = fr[(LY::F_MU1 + i) * TILE];
+#pragma unroll
+        for (int k = 0; k < DX; ++k) s = fma(J[i * DX + k], dm[k], s);
+        mu[i] = s;
+#pragma unroll
+        for (int k = 0; k < DX; ++k) {
+          double v = 0.0;
+#pragma unroll
+          for (int l = 0; l < DX; ++l) v = fma(J[i * DX + l], dS[six(l, k)], v);
+          JD[i * DX + k] = v;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          double s = fr[(LY::F_SIG1 + tix(i, j)) * TILE];
+#pragma unroll
+          for (int k = 0; k < DX; ++k) s = fma(JD[i * DX + k], J[j * DX + k], s);
+          Sig[tix(i, j)] = s;
+        }
+    }
+    double* po = rec(post, t, LY::E_POST);
+#pragma unroll
+    for (int i = 0; i < N; ++i) po[(LY::P_MU + i) * TILE] = mu[i];
+#pragma unroll
+    for (int i = 0; i < TRI(N); ++i) po[(LY::P_SIG + i) * TILE] = Sig[i];
+#pragma unroll
+    for (int i = 0; i < DX; ++i) m3m[i] = mu[i];
+#pragma unroll
+    for (int i = 0; i < TRI(DX); ++i) S3m[i] = Sig[i];
+
+    double L[TRI(N)], invd[N];
+#pragma unroll
+    for (int i = 0; i < TRI(N); ++i) L[i] = Sig[i];
+    if (!chol_rows<N>(L, invd)) fail(I2C_FAIL_CHOL_POSTERIOR, it, t);
+
+    // controller (i2c.py:598-608): K = sig_ux sig_xx^{-1} = L_ux L_xx^{-1}; sigK = sig_uu - K sig_ux^T = L_uu L_uu^T
+#pragma unroll
+    for (int r = 0; r < DU; ++r) {
+      double w[DX];
+#pragma unroll
+      for (int j = 0; j < DX; ++j) w[j] = L[tix(DX + r, j)];
+      bwd_subst<DX>(L, invd, w);  // solves L_xx^T k^T = l^T  <=>  k L_xx = l
+      double kk = mu[DX + r];
+#pragma unroll
+      for (int j = 0; j < DX; ++j) {
+        po[(LY::P_K + r * DX + j) * TILE] = w[j];
+        kk = fma(-w[j], mu[j], kk);
+      }
+      po[(LY::P_KK + r) * TILE] = kk;
+#pragma unroll
+      for (int q = 0; q <= r; ++q) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k <= q; ++k) s = fma(L[tix(DX + r, DX + k)], L[tix(DX + q, DX + k)], s);
+        po[(LY::P_SIGK + tix(r, q)) * TILE] = s;
+      }
+    }
+    // policy entropy needs det(sig_u0_m) (i2c.py:1072-1081)
+    {
+      double Su[TRI(DU)], iu[DU];
+#pragma unroll
+      for (int r = 0; r < DU; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) Su[tix(r, q)] = Sig[tix(DX + r, DX + q)];
+      if (!chol_rows<DU>(Su, iu)) fail(I2C_FAIL_POLICY_DET, it, t);
+#pragma unroll
+      for (int r = 0; r < DU; ++r) st.ent_u.mul(Su[tix(r, r)]);
+    }
+    // marginal cost-feature moments (i2c.py:594-596) -> alpha / cost statistics
+    {
+      double mz[DZ], Sz[TRI(DZ)], Dm[N * DZ], z[DZ];
+      TrigT ctx;
+      Env::center(mu, ctx);
+      sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                             [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
+      if (aux) {
+        double* ab = rec(p.auxb, t, LY::E_AUXB);
+#pragma unroll
+        for (int i = 0; i < DZ; ++i) ab[(LY::AB_MUZ + i) * TILE] = mz[i];
+#pragma unroll
+        for (int i = 0; i < TRI(DZ); ++i) ab[(LY::AB_SIGZ + i) * TILE] = Sz[i];
+      }
+      double cm, cv;
+      cost_stats<DZ>(p, mz, Sz, p.z_graph, cm, cv);
+      st.cost += cm;
+      st.cost_var += cv;
+      load_z(t, z);
+      st.tr += alpha_trace<DZ>(p.QR, p.qr_diag, mz, Sz, z);
+    }
+  }
+
+  // end-of-chain handling of the last cell (i2c.py:546-572): covariance control or plain hand-over, and
+  // the terminal cost-feature moments for the alpha update.  c holds (mu_x3_f, sig_x3_f, chol).
+  __device__ __forceinline__ void backward_terminal(int it, int t, double temp, const Carry<DX>& c, double* m3m,
+                                                    double* S3m, double& tr_term) {
+    double Lm[TRI(DX)], invm[DX];
+    if (p.cov_ctrl) {
+      // sig_x3_m = S - S (Sig_T + S)^{-1} S,  mu_x3_m = sig_x3_m (S^{-1} mu_x3_f + Sig_T^{-1} mu_T),  S = temp * sig_x3_f
+      double S[TRI(DX)], A[TRI(DX)], ia[DX];
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) {
+        S[i] = temp * c.S[i];
+        A[i] = p.sxt[i] + S[i];
+      }
+      if (!chol_rows<DX>(A, ia)) fail(I2C_FAIL_COV_CONTROL, it, t);
+      double W[DX * DX];  // W[:, j] = La^{-1} S[:, j]
+#pragma unroll
+      for (int j = 0; j < DX; ++j) {
+        double w[DX];
+#pragma unroll
+        for (int i = 0; i < DX; ++i) w[i] = S[six(i, j)];
+        fwd_subst<DX>(A, ia, w);
+#pragma unroll
+        for (int i = 0; i < DX; ++i) W[i * DX + j] = w[i];
+      }
+#pragma unroll
+      for (int i = 0; i < DX; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          double s = S[tix(i, j)];
+#pragma unroll
+          for (int k = 0; k < DX; ++k) s = fma(-W[k * DX + i], W[k * DX + j], s);
+          S3m[tix(i, j)] = s;
+        }
+      // S^{-1} mu_x3_f = (1/temp) sig_x3_f^{-1} mu_x3_f via the carried factor
+      double v[DX];
+#pragma unroll
+      for (int i = 0; i < DX; ++i) v[i] = c.m[i];
+      fwd_subst<DX>(c.L, c.invd, v);
+      bwd_subst<DX>(c.L, c.invd, v);
+      const double it_ = 1.0 / temp;
+#pragma unroll
+      for (int i = 0; i < DX; ++i) v[i] = fma(v[i], it_, p.sxt_inv_mu[i]);
+#pragma unroll
+      for (int i = 0; i < DX; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < DX; ++k) s = fma(S3m[six(i, k)], v[k], s);
+        m3m[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) Lm[i] = S3m[i];
+      if (Env::HAS_TERM && p.has_qf) {
+        if (!chol_rows<DX>(Lm, invm)) fail(I2C_FAIL_COV_CONTROL, it, t);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < DX; ++i) m3m[i] = c.m[i];
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) {
+        S3m[i] = c.S[i];
+        Lm[i] = c.L[i];
+      }
+    }
+    tr_term = 0.0;
+    if (Env::HAS_TERM && p.has_qf) {
+      double mz[DZT], Sz[TRI(DZT)], Dm[DX * DZT];
+      TrigT ctx;
+      Env::center(m3m, ctx);
+      sigma_transform<DX, DZT>(m3m, Lm, p.sf_x, p.w0_x, p.wi_x,
+                               [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Dm);
+      double* tm = p.term + ((size_t)tile * LY::E_TERM) * TILE + lane;
+#pragma unroll
+      for (int i = 0; i < DZT; ++i) tm[(LY::TM_MU + i) * TILE] = mz[i];
+#pragma unroll
+      for (int i = 0; i < TRI(DZT); ++i) tm[(LY::TM_SIG + i) * TILE] = Sz[i];
+      tr_term = alpha_trace<DZT>(p.Qf, 0, mz, Sz, p.z_term);
+    }
+  }
+
+  // ---------------------------------------------------------------------------------- propagate cell
+  // I2cCell._propagate_forward_quadrature (i2c.py:150-199).
+  struct PStats {
+    double cost, cost_var, cost_min, tr;
+    LogAcc ent;
+  };
+  __device__ __forceinline__ void propagate_cell(int it, int t, int flags, bool aux, Carry<DX>& c, PStats& st) {
+    const double* po = rec(post, t, LY::E_POST);
+    double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
+    {
+      double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];
+#pragma unroll
+      for (int r = 0; r < DU; ++r) mu_u[r] = po[(LY::P_MU + DX + r) * TILE];
+#pragma unroll
+      for (int r = 0; r < DU; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) Suu[tix(r, q)] = po[(LY::P_SIG + tix(DX + r, DX + q)) * TILE];
+#pragma unroll
+      for (int i = 0; i < DU * DX; ++i) Kt[i] = po[(LY::P_K + i) * TILE];
+      if (!(flags & I2C_CELL_INDEPENDENT)) {
+        double mx[DX], Sxx[TRI(DX)], d[DX];
+#pragma unroll
+        for (int i = 0; i < DX; ++i) mx[i] = po[(LY::P_MU + i) * TILE];
+#pragma unroll
+        for (int i = 0; i < TRI(DX); ++i) Sxx[i] = po[(LY::P_SIG + i) * TILE];
+#pragma unroll
+        for (int i = 0; i < DX; ++i) d[i] = c.m[i] - mx[i];
+        if (flags & I2C_CELL_EXPERT) {
+          double C[TRI(DX)], rho;
+#pragma unroll
+          for (int i = 0; i < TRI(DX); ++i) C[i] = Sxx[i] + c.S[i];
+          // the reference swallows exceptions here (try/except + logging.error, i2c.py:161-167): K unchanged
+          if (pdf_ratio(C, d, rho)) {
+#pragma unroll
+            for (int i = 0; i < DU * DX; ++i) Kt[i] *= rho;
+          }
+        }
+        // mu_u0_pf = mu_u0_m + K (mu_x0_pf - mu_x0_m); sig_u0_pf = K sig_x0_pf K^T + sig_u0_m - K sig_x0_m K^T
+#pragma unroll
+        for (int r = 0; r < DU; ++r) {
+          double s = mu_u[r];
+#pragma unroll
+          for (int k = 0; k < DX; ++k) s = fma(Kt[r * DX + k], d[k], s);
+          mu_u[r] = s;
+        }
+        double KD[DU * DX];  // K (sig_x0_pf - sig_x0_m)
+#pragma unroll
+        for (int r = 0; r < DU; ++r)
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < DX; ++k) s = fma(Kt[r * DX + k], c.S[six(k, j)] - Sxx[six(k, j)], s);
+            KD[r * DX + j] = s;
+          }
+#pragma unroll
+        for (int r = 0; r < DU; ++r)
+#pragma unroll
+          for (int q = 0; q <= r; ++q) {
+            double v = Suu[tix(r, q)];
+#pragma unroll
+            for (int k = 0; k < DX; ++k) v = fma(KD[r * DX + k], Kt[q * DX + k], v);
+            Suu[tix(r, q)] = v;
+          }
+      }
+      // NOTE: even for independent cells the joint carries the cross-covariance K sig_x (i2c.py:173-179)
+      if (!build_joint(c, Kt, mu_u, Suu, true, mu, Sig, L, invd)) fail(I2C_FAIL_CHOL_PROPAGATE, it, t);
+    }
+    double* pf = aux ? rec(p.pf, t, LY::E_PF) : nullptr;
+    if (aux) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) pf[(LY::PF_MU + i) * TILE] = mu[i];
+#pragma unroll
+      for (int i = 0; i < TRI(N); ++i) pf[(LY::PF_SIG + i) * TILE] = Sig[i];
+    }
+    {
+      double mz[DZ], Sz[TRI(DZ)], Dm[N * DZ], z[DZ];
+      TrigT ctx;
+      Env::center(mu, ctx);
+      sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                             [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
+      if (aux) {
+#pragma unroll
+        for (int i = 0; i < DZ; ++i) pf[(LY::PF_MUZ + i) * TILE] = mz[i];
+#pragma unroll
+        for (int i = 0; i < TRI(DZ); ++i) pf[(LY::PF_SIGZ + i) * TILE] = Sz[i];
+      }
+      double cm, cv;
+      cost_stats<DZ>(p, mz, Sz, p.z_graph, cm, cv);
+      st.cost += cm;
+      st.cost_var += cv;
+      st.cost_min = fmin(st.cost_min, cm);
+      load_z(t, z);
+      st.tr += alpha_trace<DZ>(p.QR, p.qr_diag, mz, Sz, z);
+    }
+    {
+      double Dm[N * DX];
+      TrigT ctx;
+      Env::center(mu, ctx);
+      sigma_transform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                             [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Dm);
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) {
+        c.S[i] += p.sig_eta[i];
+        c.L[i] = c.S[i];
+      }
+      if (!chol_rows<DX>(c.L, c.invd)) fail(I2C_FAIL_CHOL_PROPAGATE, it, t);
+#pragma unroll
+      for (int i = 0; i < DX; ++i) st.ent.mul(c.L[tix(i, i)]);
+    }
+    if (aux) {
+#pragma unroll
+      for (int i = 0; i < DX; ++i) pf[(LY::PF_MU3 + i) * TILE] = c.m[i];
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) pf[(LY::PF_SIG3 + i) * TILE] = c.S[i];
+    }
+  }
+
+  __device__ __forceinline__ bool load_x0(Carry<DX>& c) {
+    const double* q = p.x0 + ((size_t)tile * DX) * TILE + lane;
+#pragma unroll
+    for (int i = 0; i < DX; ++i) c.m[i] = q[i * TILE];
+    q = p.sig_x0 + ((size_t)tile * TRI(DX)) * TILE + lane;
+#pragma unroll
+    for (int i = 0; i < TRI(DX); ++i) {
+      c.S[i] = q[i * TILE];
+      c.L[i] = c.S[i];
+    }
+    return chol_rows<DX>(c.L, c.invd);
+  }
+
+  __device__ __forceinline__ void metric(int m, int it, double v) const {
+    p.metrics[((size_t)m * p.max_iters + it) * p.Bpad + b] = v;
+  }
+
+  // ---------------------------------------------------------------------------------- the EM loop
+  __device__ void run() {
+    const double HALF_LOG_2PIE = 1.4189385332046727;  // 0.5 * log(2 pi e)
+    double alpha = p.alpha[b];
+    const bool aux = p.phases & I2C_PH_STORE_AUX;
+    bool flipped = false;  // _update_priors has cleared state_action_independence for index <= tau
+    double temp = p.temp0;
+    const int T = p.T;
+    for (int it = 0; it < p.n_iter; ++it) {
+      Carry<DX> c;
+      LogAcc ent_x;
+      ent_x.reset();
+      Stats st;
+      st.cost = st.cost_var = st.tr = 0.0;
+      st.ent_u.reset();
+      double tr_term = 0.0;
+      if (p.phases & I2C_PH_FORWARD) {
+        if (!load_x0(c)) fail(I2C_FAIL_CHOL_PRIOR, it, 0);
+        for (int t = 0; t < T; ++t) {
+          int flags = p.cell_flags[slot(t)];
+          if (flipped && p.tau > 0 && p.cell_index[slot(t)] <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
+          forward_cell(it, t, flags, alpha, aux, c, ent_x);
+        }
+      }
+      if (p.phases & I2C_PH_BACKWARD) {
+        if (!(p.phases & I2C_PH_FORWARD)) {
+          // resume from the stored filtered message of the last cell
+          const double* fr = rec(p.filt, T - 1, LY::E_FILT);
+#pragma unroll
+          for (int i = 0; i < DX; ++i) c.m[i] = fr[(LY::F_MU3 + i) * TILE];
+#pragma unroll
+          for (int i = 0; i < TRI(DX); ++i) {
+            c.S[i] = fr[(LY::F_SIG3 + i) * TILE];
+            c.L[i] = c.S[i];
+          }
+          chol_rows<DX>(c.L, c.invd);
+        }
+        double m3m[DX], S3m[TRI(DX)];
+        backward_terminal(it, T - 1, temp, c, m3m, S3m, tr_term);
+        if (p.cov_ctrl) temp += p.dtemp;
+        for (int t = T - 1; t >= 0; --t) backward_cell(it, t, p.cell_flags[slot(t)], aux, m3m, S3m, st);
+        latest = post;
+      }
+      PStats ps;
+      ps.cost = ps.cost_var = ps.tr = 0.0;
+      ps.cost_min = INFINITY;
+      ps.ent.reset();
+      if (p.phases & I2C_PH_PROPAGATE) {
+        Carry<DX> cp;
+        if (!load_x0(cp)) fail(I2C_FAIL_CHOL_PROPAGATE, it, 0);
+        for (int t = 0; t < T; ++t) {
+          int flags = p.cell_flags[slot(t)];
+          if (flipped && p.tau > 0 && p.cell_index[slot(t)] <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
+          propagate_cell(it, t, flags, aux, cp, ps);
+        }
+        if (p.cov_ctrl) {
+          // KL(N(mu_x3_pf, sig_x3_pf) || N(mu_xT, sig_xT)) of the last cell (i2c.py:1012-1019, 1223-1229)
+          double A[TRI(DX)], ia[DX], d[DX];
+#pragma unroll
+          for (int i = 0; i < TRI(DX); ++i) A[i] = p.sxt[i];
+          chol_rows<DX>(A, ia);
+#pragma unroll
+          for (int i = 0; i < DX; ++i) d[i] = p.mu_xt[i] - cp.m[i];
+          fwd_subst<DX>(A, ia, d);
+          double dist = 0.0, tr = 0.0, ld1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < DX; ++i) dist = fma(d[i], d[i], dist);
+          // tr(SigT^{-1} Sig1) = || La^{-1} L1 ||_F^2
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double w[DX];
+#pragma unroll
+            for (int i = 0; i < DX; ++i) w[i] = (i >= j) ? cp.L[tix(i, j)] : 0.0;
+            fwd_subst<DX>(A, ia, w);
+#pragma unroll
+            for (int i = 0; i < DX; ++i) tr = fma(w[i], w[i], tr);
+            ld1 += log(cp.L[tix(j, j)]);
+          }
+          metric(I2C_M_KL_TERM, it, 0.5 * (p.sxt_logdet - 2.0 * ld1 + tr + dist - (double)DX));
+        }
+      }
+      if (p.phases & I2C_PH_MSTEP) {
+        metric(I2C_M_COST_M, it, st.cost);
+        metric(I2C_M_COST_M_VAR, it, st.cost_var);
+        if (p.phases & I2C_PH_PROPAGATE) {
+          metric(I2C_M_COST_PF, it, ps.cost);
+          metric(I2C_M_COST_PF_VAR, it, ps.cost_var);
+          metric(I2C_M_COST_PF_MIN, it, ps.cost_min);
+          metric(I2C_M_ALPHA_PF, it, ps.tr / (double)(DZ * T));
+          metric(I2C_M_PROPAGATE_ENTROPY, it, (double)(T * DX) * HALF_LOG_2PIE + ps.ent.value());
+        } else {
+          metric(I2C_M_COST_PF, it, -1.0);
+        }
+        metric(I2C_M_POLICY_ENTROPY, it, (double)(T * DU) * HALF_LOG_2PIE + st.ent_u.value());
+        metric(I2C_M_X_PRIOR_ENTROPY, it, (double)(T * DX) * HALF_LOG_2PIE + ent_x.value());
+      }
+      if (p.phases & I2C_PH_UPDATE_PRIORS) {
+        // _update_priors (i2c.py:1210-1221): prior <- posterior (record swap), independence cleared for index <= tau
+        if (latest == post) {
+          double* tmp = prior;
+          prior = post;
+          post = tmp;
+        }
+        flipped = true;
+      }
+      if (p.phases & I2C_PH_MSTEP) {
+        // compute_update_alpha(update_alpha=True) (i2c.py:921-963)
+        double sf = (double)(DZ * T);
+        double tr = st.tr;
+        if (Env::HAS_TERM && p.has_qf) {
+          tr += tr_term;
+          sf += (double)DZT;
+        }
+        double a_new = tr / sf;
+        metric(I2C_M_ALPHA_DESIRED, it, a_new);
+        if (a_new != a_new) {
+          fail(I2C_FAIL_NAN_ALPHA, it, 0);
+          a_new = alpha;
+        } else if (p.alpha_tol >= 0.0) {
+          const double ratio = a_new / alpha;
+          const double upper = 2.0 - p.alpha_tol;
+          double upd = a_new;
+          if (ratio < p.alpha_tol) upd = p.alpha_tol * alpha;
+          if (ratio > upper) upd = upper * alpha;
+          a_new = upd;
+        } else {
+          a_new = alpha;
+        }
+        alpha = a_new;
+        own_alpha_valid = false;  // update_xi pushes the new sig_xi to every cell (i2c.py:976-981)
+        metric(I2C_M_ALPHA, it, alpha);
+      }
+      if (p.phases & I2C_PH_CALIBRATE) {
+        // calibrate_alpha (i2c.py:895-911): alpha from the propagated cost features, no terminal term
+        double a_pf = ps.tr / (double)(DZ * T);
+        bool upd = (p.phases & I2C_PH_ONLY_DECREASE) ? (a_pf < alpha) : true;
+        if (upd) {
+          alpha = a_pf;
+          own_alpha_valid = false;
+        }
+        metric(I2C_M_ALPHA, it, alpha);
+      }
+    }
+    p.alpha[b] = alpha;
+    if (status != I2C_OK && p.status[b] == I2C_OK) {
+      p.status[b] = status;
+      p.info[b] = info;
+    }
+  }
+};
+
+template <class Env>
+__global__ void __launch_bounds__(128) em_kernel(const __grid_constant__ KParams pin) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / TILE;
+  const int lane = threadIdx.x % TILE;
+  if (warp >= pin.ntiles) return;
+  Worker<Env> w(pin, warp, lane);
+  w.run();
+}
+
+template <class Env>
+static int launch_em_t(const KParams& p, cudaStream_t s) {
+  // one warp per tile of 32 problems; small blocks spread the warps over all SMs / sub-partitions
+  int threads = 32;
+  if (p.ntiles >= 148 * 8) threads = 64;
+  if (p.ntiles >= 148 * 32) threads = 128;
+  int wpb = threads / TILE;
+  int blocks = (p.ntiles + wpb - 1) / wpb;
+  em_kernel<Env><<<blocks, threads, 0, s>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int launch_em(int env, const KParams& p, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (env) {
+    case I2C_ENV_LINEAR: return launch_em_t<EnvLinear>(p, s);
+    case I2C_ENV_LINEAR_MIN_ENERGY: return launch_em_t<EnvLinearMinEnergy>(p, s);
+    case I2C_ENV_PENDULUM: return launch_em_t<EnvPendulum>(p, s);
+    case I2C_ENV_PENDULUM_ACT_REG: return launch_em_t<EnvPendulumActReg>(p, s);
+    case I2C_ENV_CARTPOLE: return launch_em_t<EnvCartpole>(p, s);
+    case I2C_ENV_DOUBLE_CARTPOLE: return launch_em_t<EnvDoubleCartpole>(p, s);
+    case I2C_ENV_QUADROTOR: return launch_em_t<EnvQuadrotor>(p, s);
+  }
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone sigma-point transform: QuadratureInference.forward / forward_gaussian
+// (inference/quadrature.py:27-58) for the registered env maps.
+template <class Env, int FN>
+struct QuadDims {
+  static constexpr int N = Env::DX + Env::DU;
+  static constexpr int D = (FN == 0 || FN == 2) ? N : Env::DX;
+  static constexpr int DY = FN == 0 ? Env::DZ : (FN == 1 ? Env::DZT : (FN == 2 ? Env::DX : (Env::DY > 0 ? Env::DY : 1)));
+};
+
+template <class Env, int FN>
+__global__ void __launch_bounds__(64) quad_kernel(const __grid_constant__ QuadArgs a) {
+  using QD = QuadDims<Env, FN>;
+  constexpr int D = QD::D, DY = QD::DY;
+  const int tile = (blockIdx.x * blockDim.x + threadIdx.x) / TILE, lane = threadIdx.x % TILE;
+  if (tile >= a.ntiles) return;
+  double par[Env::NP > 0 ? Env::NP : 1];
+#pragma unroll
+  for (int i = 0; i < Env::NP; ++i) par[i] = a.envpar[((size_t)tile * Env::NP + i) * TILE + lane];
+  double m[D], L[TRI(D)], invd[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) m[i] = a.m[((size_t)tile * D + i) * TILE + lane];
+#pragma unroll
+  for (int i = 0; i < TRI(D); ++i) L[i] = a.S[((size_t)tile * TRI(D) + i) * TILE + lane];
+  bool ok = chol_rows<D>(L, invd);
+  double my[DY], Sy[TRI(DY)], Dm[D * DY], Sxy[D * DY];
+  typename Env::TrigT ctx;
+  Env::center(m, ctx);
+  sigma_transform<D, DY>(m, L, a.sf, a.w0, a.wi,
+                         [&](const double* x, int j, double* y) {
+                           if (FN == 0) Env::obs(x, j, ctx, y);
+                           else if (FN == 1) Env::obs_term(x, j, ctx, y);
+                           else if (FN == 2) Env::dyn(x, j, ctx, par, y);
+                           else Env::measure(x, j, ctx, y);
+                         },
+                         my, Sy, Dm);
+  cross_cov<D, DY>(L, Dm, Sxy);
+#pragma unroll
+  for (int i = 0; i < DY; ++i) a.my[((size_t)tile * DY + i) * TILE + lane] = my[i];
+#pragma unroll
+  for (int i = 0; i < TRI(DY); ++i) a.Sy[((size_t)tile * TRI(DY) + i) * TILE + lane] = Sy[i];
+#pragma unroll
+  for (int i = 0; i < D * DY; ++i) a.Sxy[((size_t)tile * D * DY + i) * TILE + lane] = Sxy[i];
+  if (a.status) a.status[tile * TILE + lane] = ok ? I2C_OK : I2C_FAIL_CHOL_PRIOR;
+}
+
+template <class Env>
+static int launch_quad_t(int fn, const QuadArgs& a, cudaStream_t s) {
+  int threads = 64, blocks = (a.ntiles * TILE + threads - 1) / threads;
+  switch (fn) {
+    case 0: quad_kernel<Env, 0><<<blocks, threads, 0, s>>>(a); break;
+    case 1: quad_kernel<Env, 1><<<blocks, threads, 0, s>>>(a); break;
+    case 2: quad_kernel<Env, 2><<<blocks, threads, 0, s>>>(a); break;
+    case 3:
+      if (Env::DY == 0) return -2;
+      quad_kernel<Env, 3><<<blocks, threads, 0, s>>>(a);
+      break;
+    default: return -1;
+  }
+  return (int)cudaGetLastError();
+}
+
+int launch_quadrature(int env, int fn, const QuadArgs& a, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (env) {
+    case I2C_ENV_LINEAR: return launch_quad_t<EnvLinear>(fn, a, s);
+    case I2C_ENV_LINEAR_MIN_ENERGY: return launch_quad_t<EnvLinearMinEnergy>(fn, a, s);
+    case I2C_ENV_PENDULUM: return launch_quad_t<EnvPendulum>(fn, a, s);
+    case I2C_ENV_PENDULUM_ACT_REG: return launch_quad_t<EnvPendulumActReg>(fn, a, s);
+    case I2C_ENV_CARTPOLE: return launch_quad_t<EnvCartpole>(fn, a, s);
+    case I2C_ENV_DOUBLE_CARTPOLE: return launch_quad_t<EnvDoubleCartpole>(fn, a, s);
+    case I2C_ENV_QUADROTOR: return launch_quad_t<EnvQuadrotor>(fn, a, s);
+  }
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cubature Kalman filter step: PartiallyObservedMpcPolicy.filter (policy/mpc.py:125-145).
+template <class Env>
+__global__ void __launch_bounds__(64) ckf_kernel(const __grid_constant__ CkfArgs a) {
+  constexpr int DX = Env::DX, DU = Env::DU, N = DX + DU, DY = Env::DY > 0 ? Env::DY : 1;
+  const int tile = (blockIdx.x * blockDim.x + threadIdx.x) / TILE, lane = threadIdx.x % TILE;
+  if (tile >= a.ntiles) return;
+  double par[Env::NP > 0 ? Env::NP : 1];
+#pragma unroll
+  for (int i = 0; i < Env::NP; ++i) par[i] = a.envpar[((size_t)tile * Env::NP + i) * TILE + lane];
+  double m[DX], S[TRI(DX)], L[TRI(DX)], invd[DX], u[DU];
+#pragma unroll
+  for (int i = 0; i < DX; ++i) m[i] = a.x0[((size_t)tile * DX + i) * TILE + lane];
+#pragma unroll
+  for (int i = 0; i < TRI(DX); ++i) L[i] = a.sig_x0[((size_t)tile * TRI(DX) + i) * TILE + lane];
+#pragma unroll
+  for (int i = 0; i < DU; ++i) u[i] = a.u[((size_t)tile * DU + i) * TILE + lane];
+  bool ok = chol_rows<DX>(L, invd);
+  typename Env::TrigT ctx;
+  // predict: pass the belief through the dynamics with the applied control appended to every point
+  double mf[DX], Dm0[DX * DX];
+  Env::center(m, ctx);
+  sigma_transform<DX, DX>(m, L, a.sf, a.w0, a.wi,
+                          [&](const double* x, int j, double* y) {
+                            double xu[N];
+#pragma unroll
+                            for (int i = 0; i < DX; ++i) xu[i] = x[i];
+#pragma unroll
+                            for (int i = 0; i < DU; ++i) xu[DX + i] = u[i];
+                            Env::dyn(xu, j, ctx, par, y);
+                          },
+                          mf, S, Dm0);
+#pragma unroll
+  for (int i = 0; i < TRI(DX); ++i) {
+    S[i] += a.sig_eta[i];
+    L[i] = S[i];
+  }
+  ok = chol_rows<DX>(L, invd) && ok;
+  // update on the measurement
+  double my[DY], Sy[TRI(DY)], Dm[DX * DY], Sxy[DX * DY], yv[DY];
+  Env::center(mf, ctx);
+  sigma_transform<DX, DY>(mf, L, a.sf, a.w0, a.wi,
+                          [&](const double* x, int j, double* y) { Env::measure(x, j, ctx, y); }, my, Sy, Dm);
+  cross_cov<DX, DY>(L, Dm, Sxy);
+#pragma unroll
+  for (int i = 0; i < TRI(DY); ++i) Sy[i] += a.sig_zeta[i];
+#pragma unroll
+  for (int i = 0; i < DY; ++i) yv[i] = a.y[((size_t)tile * DY + i) * TILE + lane];
+  ok = condition<DX, DY>(mf, S, Sy, Sxy, my, yv) && ok;
+#pragma unroll
+  for (int i = 0; i < DX; ++i) a.x0[((size_t)tile * DX + i) * TILE + lane] = mf[i];
+#pragma unroll
+  for (int i = 0; i < TRI(DX); ++i) a.sig_x0[((size_t)tile * TRI(DX) + i) * TILE + lane] = S[i];
+  if (!ok && a.status[tile * TILE + lane] == I2C_OK) a.status[tile * TILE + lane] = I2C_FAIL_CKF;
+}
+
+int launch_ckf(int env, const CkfArgs& a, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int threads = 64, blocks = (a.ntiles * TILE + threads - 1) / threads;
+  switch (env) {
+    case I2C_ENV_QUADROTOR: ckf_kernel<EnvQuadrotor><<<blocks, threads, 0, s>>>(a); break;
+    default: return -2;  // only the quadrotor defines measure() (mpc_quad.py:371-383)
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace i2c

@@ -1,0 +1,100 @@
+// Internal types shared by the kernels and the C-ABI implementation (not part of the public header).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/i2c_b200.h"
+
+namespace i2c {
+
+constexpr int TILE = 32;       // problems per tile == one warp; innermost (contiguous) axis of every record
+constexpr int MAX_DX = 6, MAX_DU = 2, MAX_N = 8, MAX_DZ = 9, MAX_DZT = 8, MAX_DY = 8;
+
+// Device layout ("AoSoA"): a per-cell record with E fp64 elements per problem is stored as
+//   buf[cell][tile][e][lane],  lane = problem % 32, tile = problem / 32
+// so that (a) the 32 threads of a warp read element e of their 32 problems as one 256-byte
+// coalesced segment and (b) the record of one (cell, tile) is a single contiguous E*256-byte
+// block (bulk-copy friendly).
+struct KParams {
+  // ---- per-cell records
+  double* prior;  // [T][ntiles][E_POST][32]  read by the forward sweep
+  double* post;   // [T][ntiles][E_POST][32]  written by the backward sweep
+  double* latest; // == prior or post: the record the most recent backward sweep wrote (propagate / getters)
+  double* filt;   // [T][ntiles][E_FILT][32]  forward -> backward
+  double* auxf;   // [T][ntiles][E_AUXF][32]  optional
+  double* auxb;   // [T][ntiles][E_AUXB][32]  optional
+  double* pf;     // [T][ntiles][E_PF][32]    optional (propagate messages)
+  double* term;   // [ntiles][E_TERM][32]     terminal cost-feature moments of the last cell
+  // ---- per-problem
+  double* x0;      // [ntiles][DX][32]
+  double* sig_x0;  // [ntiles][TRI(DX)][32]
+  double* alpha;   // [Bpad]
+  double* alpha_cell;   // [T][Bpad]   (cells flagged OWN_ALPHA)
+  const double* z_cell; // [T][DZ] or [T][ntiles][DZ][32]
+  const double* envpar; // [ntiles][NP][32]
+  int32_t* cell_flags;  // [T]
+  const int32_t* cell_index;  // [T]
+  double* metrics;      // [I2C_M_COUNT][max_iters][Bpad]
+  int32_t* status;      // [Bpad]
+  int32_t* info;        // [Bpad]
+  // ---- scalars
+  int32_t B, Bpad, ntiles, T;
+  int32_t n_iter, phases, tau, max_iters;
+  int32_t cell_head;  // ring offset: logical cell t lives in slot (t + cell_head) % T (O(1) MPC horizon shift)
+  int32_t z_per_problem, qr_diag, has_qf, cov_ctrl;
+  double alpha_tol, temp0, dtemp;
+  double sf_n, w0_n, wi_n;  // cubature rule in dim n = dx+du (exp_types.py:36-49)
+  double sf_x, w0_x, wi_x;  // cubature rule in dim dx
+  // ---- shared constants (row-major full matrices; packed lower where noted)
+  double QR[MAX_DZ * MAX_DZ], QRinv[MAX_DZ * MAX_DZ];
+  double Qf[MAX_DZT * MAX_DZT], Qfinv[MAX_DZT * MAX_DZT];
+  double sig_eta[MAX_DX * (MAX_DX + 1) / 2];     // packed lower
+  double z_graph[MAX_DZ], z_term[MAX_DZT];
+  double sxt[MAX_DX * (MAX_DX + 1) / 2];         // sig_x_terminal, packed lower
+  double sxt_inv_mu[MAX_DX];                     // sig_x_terminal^{-1} mu_x_terminal
+  double mu_xt[MAX_DX];
+  double sxt_logdet;                             // log det sig_x_terminal (KL term)
+};
+
+// element counts of the records for given dims
+struct RecDims {
+  int dx, du, n, dz, dzt;
+  __host__ __device__ static constexpr int tri(int k) { return k * (k + 1) / 2; }
+  __host__ __device__ constexpr int e_post() const { return n + tri(n) + du * dx + du + tri(du); }
+  __host__ __device__ constexpr int e_filt() const { return n + tri(n) + dx + tri(dx) + n * dx; }
+  __host__ __device__ constexpr int e_auxf() const { return n + tri(n) + dz + tri(dz); }
+  __host__ __device__ constexpr int e_auxb() const { return dz + tri(dz) + dx + tri(dx); }
+  __host__ __device__ constexpr int e_pf() const { return n + tri(n) + dz + tri(dz) + dx + tri(dx); }
+  __host__ __device__ constexpr int e_term() const { return dzt + tri(dzt); }
+};
+
+// launchers implemented in i2c_kernels.cu
+int launch_em(int env, const KParams& p, void* stream);
+
+struct QuadArgs {
+  const double* m;   // [ntiles][D][32]
+  const double* S;   // [ntiles][TRI(D)][32]
+  const double* envpar;
+  double* my;        // [ntiles][DY][32]
+  double* Sy;        // [ntiles][TRI(DY)][32]
+  double* Sxy;       // [ntiles][D*DY][32]
+  int32_t* status;   // [Bpad]
+  int32_t B, ntiles;
+  double sf, w0, wi;
+};
+int launch_quadrature(int env, int fn, const QuadArgs& a, void* stream);
+
+struct CkfArgs {
+  double* x0;        // [ntiles][DX][32]   belief mean, updated in place
+  double* sig_x0;    // [ntiles][TRI DX][32]
+  const double* y;   // [ntiles][DY][32]
+  const double* u;   // [ntiles][DU][32]
+  const double* envpar;
+  int32_t* status;
+  int32_t B, ntiles;
+  double sf, w0, wi;
+  double sig_eta[MAX_DX * (MAX_DX + 1) / 2];
+  double sig_zeta[MAX_DY * (MAX_DY + 1) / 2];
+};
+int launch_ckf(int env, const CkfArgs& a, void* stream);
+
+}  // namespace i2c

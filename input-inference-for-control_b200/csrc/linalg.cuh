@@ -1,0 +1,77 @@
+// Small dense fp64 linear algebra held entirely in registers (one problem per thread).
+// Symmetric matrices are stored as packed lower triangles, row-major: (i,j), i>=j -> i(i+1)/2 + j.
+// Every loop has compile-time bounds and is fully unrolled so that the arrays stay in registers.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace i2c {
+
+__host__ __device__ constexpr int TRI(int n) { return n * (n + 1) / 2; }
+__host__ __device__ constexpr int tix(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+__host__ __device__ constexpr int six(int i, int j) { return i >= j ? tix(i, j) : tix(j, i); }
+
+// Cholesky factorisation rows [START, N) of a packed lower matrix, in place (rows < START already hold L
+// and invd[] their reciprocal pivots).  Returns false when a pivot is not strictly positive (or NaN) --
+// the LAPACK potrf failure the reference turns into LinAlgError (inference/quadrature.py:17-24).
+template <int N, int START = 0>
+__device__ __forceinline__ bool chol_rows(double* A, double* invd) {
+  bool ok = true;
+#pragma unroll
+  for (int i = START; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      double s = A[tix(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s = fma(-A[tix(i, k)], A[tix(j, k)], s);
+      A[tix(i, j)] = s * invd[j];
+    }
+    double d = A[tix(i, i)];
+#pragma unroll
+    for (int k = 0; k < i; ++k) d = fma(-A[tix(i, k)], A[tix(i, k)], d);
+    ok = ok && (d > 0.0) && (d < 1.0e300);
+    double r = rsqrt(d);
+    invd[i] = r;
+    A[tix(i, i)] = d * r;
+  }
+  return ok;
+}
+
+// y <- L^{-1} y  (forward substitution), L packed lower with reciprocal pivots invd.
+template <int N>
+__device__ __forceinline__ void fwd_subst(const double* L, const double* invd, double* y) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = y[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s = fma(-L[tix(i, k)], y[k], s);
+    y[i] = s * invd[i];
+  }
+}
+
+// y <- L^{-T} y  (backward substitution).
+template <int N>
+__device__ __forceinline__ void bwd_subst(const double* L, const double* invd, double* y) {
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) s = fma(-L[tix(k, i)], y[k], s);
+    y[i] = s * invd[i];
+  }
+}
+
+// Running log-determinant accumulator that avoids one fp64 log() per pivot: keeps a renormalised
+// mantissa product and an integer exponent; value() = log(product).
+struct LogAcc {
+  double m;
+  int e;
+  __device__ __forceinline__ void reset() { m = 1.0; e = 0; }
+  __device__ __forceinline__ void mul(double x) {
+    int ex;
+    m = frexp(m * x, &ex);
+    e += ex;
+  }
+  __device__ __forceinline__ double value() const { return log(m) + 0.6931471805599453 * (double)e; }
+};
+
+}  // namespace i2c

@@ -1,0 +1,7 @@
+"""i2c_b200 -- B200-native batched Gaussian input inference for control (host side of the C-ABI)."""
+from . import _capi as capi
+from ._capi import I2cError, lib
+from .batched import BatchedI2c, quadrature
+from . import envs
+
+__all__ = ["BatchedI2c", "quadrature", "I2cError", "lib", "capi", "envs"]

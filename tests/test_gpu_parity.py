@@ -1,0 +1,186 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs
+and against the committed golden vectors of the unmodified reference."""
+import numpy as np
+import pytest
+
+from conftest import GAINS, golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def i2c_b200():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import i2c_b200 as m
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return m
+
+
+ENVS = ["LinearKnown", "LinearKnownMinimumEnergy", "PendulumKnown", "PendulumKnownActReg", "CartpoleKnown",
+        "DoubleCartpoleKnown"]
+
+
+@pytest.mark.parametrize("env", ENVS)
+def test_quadrature_kats(i2c_b200, env):
+    """Stand-alone sigma-point kernel vs the reference's QuadratureInference outputs (golden) for every env map."""
+    g = golden("quadrature_kat")
+    m = np.stack([g[f"{env}/{r}/m_in"] for r in range(3)])
+    S = np.stack([g[f"{env}/{r}/S_in"] for r in range(3)])
+    dx = {"LinearKnown": 2, "LinearKnownMinimumEnergy": 2, "PendulumKnown": 2, "PendulumKnownActReg": 2,
+          "CartpoleKnown": 4, "DoubleCartpoleKnown": 6}[env]
+    my, Sy, Sxy, st = i2c_b200.quadrature(env, "observe", m, S)
+    assert np.all(st == 0)
+    for r in range(3):
+        assert relerr(my[r], g[f"{env}/{r}/obs_m"]) < 1e-13
+        assert relerr(Sy[r], g[f"{env}/{r}/obs_S"]) < 1e-11
+        assert relerr(Sxy[r], g[f"{env}/{r}/obs_Sxy"]) < 1e-11
+    my, Sy, Sxy, st = i2c_b200.quadrature(env, "forward", m, S)
+    for r in range(3):
+        assert relerr(my[r], g[f"{env}/{r}/dyn_m"]) < 1e-13
+        assert relerr(Sy[r], g[f"{env}/{r}/dyn_S"]) < 1e-10
+        assert relerr(Sxy[r], g[f"{env}/{r}/dyn_Sxy"]) < 1e-10
+    if env != "PendulumKnownActReg":
+        my, Sy, Sxy, st = i2c_b200.quadrature(env, "observe_terminal", m[:, :dx], S[:, :dx, :dx])
+        for r in range(3):
+            assert relerr(my[r], g[f"{env}/{r}/term_m"]) < 1e-13
+            assert relerr(Sy[r], g[f"{env}/{r}/term_S"]) < 1e-11
+
+
+def test_quadrature_general_weights_and_failure(i2c_b200):
+    from oracle import i2c_oracle as O
+    from oracle import envs as E
+
+    rng = np.random.default_rng(3)
+    B = 37
+    A = rng.normal(size=(B, 5, 5))
+    S = 0.02 * A @ A.transpose(0, 2, 1) + 1e-3 * np.eye(5)
+    m = rng.normal(size=(B, 5))
+    sys_ = E.Cartpole()
+    for abk in [(1.0, 0.0, 0.0), (0.5, 2.0, 1.0), (1.0, 2.0, 0.5)]:
+        q = O.Quad(O.Cubature(*abk), 5)
+        mz, Sz = q.forward(sys_.observe, m, S)
+        my, Sy, Sxy, st = i2c_b200.quadrature("CartpoleKnown", "observe", m, S, quad=abk)
+        assert np.all(st == 0)
+        assert relerr(my, mz) < 1e-12 and relerr(Sy, Sz) < 1e-9 and relerr(Sxy, q.sig_xy) < 1e-9, abk
+    S[5] = -S[5]  # not PD -> per-problem status, neighbours unaffected
+    my, Sy, Sxy, st = i2c_b200.quadrature("CartpoleKnown", "observe", m, S)
+    assert st[5] != 0 and np.all(np.delete(st, 5) == 0)
+
+
+def make_pair(i2c_b200, env, B, T, Q, R, Qf, alpha, tol, seed, x0_scale, sig_u, mu_x_term=None, sig_x_term=None,
+              enable_aux=True):
+    from oracle import i2c_oracle as O
+
+    rng = np.random.default_rng(seed)
+    e = i2c_b200.envs.make(env)
+    x0 = e.x0 + x0_scale * rng.normal(size=(B, e.dim_x))
+    mu_u = 1e-2 * rng.normal(size=(B, T, e.dim_u))
+    G = i2c_b200.BatchedI2c(env, B, T, Q, R, Qf, alpha, tol, mu_u, sig_u, mu_x_term, sig_x_term, x0=x0,
+                            enable_aux=enable_aux)
+    ref = O.make_graph(env, T, Q, R, Qf, alpha, tol, mu_u, sig_u, mu_x_term, sig_x_term, B=B, x0=x0)
+    return G, ref
+
+
+# NOTE: after learn_msgs the reference's cell.mu_xu0_f holds the NEW prior (= posterior, _update_priors i2c.py:1220);
+# the joint prior the forward pass built is kept as mu_xu0_f_prev.  Device fields: "mu_xu0_f" = built joint,
+# "prior_mu" = prior record.
+FIELDS_F = ["mu_z0_f", "sig_z0_f", "mu_xu1_f", "sig_xu1_f", "mu_x3_f", "sig_x3_f", "J_dyn"]
+FIELDS_B = ["mu_x3_m", "sig_x3_m", "mu_xu0_m", "sig_xu0_m", "mu_z0_m", "sig_z0_m", "K", "k", "sigK"]
+FIELDS_P = ["mu_xu0_pf", "sig_xu0_pf", "mu_z0_pf", "sig_z0_pf", "mu_x3_pf", "sig_x3_pf"]
+
+
+ALIAS = {"mu_xu0_f_prev": "mu_xu0_f", "sig_xu0_f_prev": "sig_xu0_f", "mu_xu0_f": "prior_mu", "sig_xu0_f": "prior_sig"}
+
+
+def compare_cells(G, ref, names, tol_s, tol_g, tag=""):
+    for a in names:
+        mine = G.field(ALIAS.get(a, a))
+        theirs = ref.stack(a)
+        e = relerr(mine, theirs, floor=1e-6 if a in GAINS else 0.0)
+        assert e < (tol_g if a in GAINS else tol_s), (tag, a, e)
+
+
+CASES = [
+    # env, B, T, Q, R, alpha, tol, x0 scale, sig_u, iters, tol_state, tol_gain
+    ("PendulumKnown", 96, 60, np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), 100.0, 0.0, [0.3, 0.5], 2.0, 4, 1e-9, 1e-7),
+    ("CartpoleKnown", 64, 50, np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0]), 80.0, 0.0, 0.05, 1.0, 3, 1e-9, 1e-6),
+    ("DoubleCartpoleKnown", 40, 40, 1e-3 * np.diag([1.0, 1.0, 100.0, 1.0, 100.0, 10.0, 1.0, 1.0]), 1e-3 * np.diag([0.1]),
+     0.05, 0.99, 0.02, 1.0, 3, 1e-8, 1e-5),
+    ("LinearKnownMinimumEnergy", 33, 30, None, np.diag([1.0]), 10.0, 0.5, 0.3, 10.0, 3, 1e-10, 1e-7),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_em_batched_vs_oracle(i2c_b200, case):
+    env, B, T, Q, R, alpha, tol, xs, su, iters, tol_s, tol_g = case
+    e = i2c_b200.envs.make(env)
+    Qf = Q if e.has_term else None
+    G, ref = make_pair(i2c_b200, env, B, T, Q, R, Qf, alpha, tol, 42, np.asarray(xs), su * np.eye(e.dim_u))
+    for it in range(iters):
+        G.learn(1)
+        ref.learn_msgs()
+        st, info = G.status()
+        assert np.all(st == 0), (it, st, info)
+        compare_cells(G, ref, FIELDS_F + FIELDS_B + ["mu_xu0_f_prev", "sig_xu0_f_prev", "mu_xu0_f", "sig_xu0_f"], tol_s,
+                      tol_g, tag=f"it{it}")
+        assert relerr(G.alpha, ref.alpha) < 1e-10
+    for name, lst in [("alpha", ref.alphas[1:]), ("alpha_desired", ref.alphas_desired[1:]), ("cost_m", ref.costs_m),
+                      ("cost_m_var", ref.costs_m_var), ("policy_entropy", ref.policy_entropy),
+                      ("x_prior_entropy", ref.x_prior_entropy)]:
+        assert relerr(np.array(G.metrics[name]), np.array(lst)) < 1e-9, name
+    K, k, sk = G.get_local_linear_policy()
+    Kr, kr, skr = ref.get_local_linear_policy()
+    assert relerr(K, Kr, 1e-6) < tol_g and relerr(k, kr, 1e-6) < tol_g and relerr(sk, skr) < tol_s
+    if e.has_term and Qf is not None:
+        assert relerr(G.field("mu_z3_m")[:, 0], ref.cells[-1].mu_z3_m) < tol_s
+        assert relerr(G.field("sig_z3_m")[:, 0], ref.cells[-1].sig_z3_m) < tol_s
+
+
+def test_fused_iterations_equal_single_steps(i2c_b200):
+    """Running n EM iterations inside one persistent launch == n launches of one iteration (bitwise)."""
+    Q, R = np.diag([1.0, 100.0, 1.0]), np.diag([2.0])
+    G1, _ = make_pair(i2c_b200, "PendulumKnown", 64, 50, Q, R, Q, 100.0, 0.0, 1, np.array([0.3, 0.5]), 2.0 * np.eye(1),
+                      enable_aux=False)
+    G2, _ = make_pair(i2c_b200, "PendulumKnown", 64, 50, Q, R, Q, 100.0, 0.0, 1, np.array([0.3, 0.5]), 2.0 * np.eye(1),
+                      enable_aux=False)
+    G1.learn(5)
+    for _ in range(5):
+        G2.learn(1)
+    for a in ["mu_xu0_m", "sig_xu0_m", "K", "k", "sigK", "mu_xu1_f", "J_dyn"]:
+        assert np.array_equal(G1.field(a), G2.field(a)), a
+    assert np.array_equal(np.array(G1.metrics["alpha"]), np.array(G2.metrics["alpha"]))
+    assert np.array_equal(np.array(G1.metrics["cost_m"]), np.array(G2.metrics["cost_m"]))
+
+
+@pytest.mark.parametrize("name,tol_s,tol_g", [("pendulum_known_quad_seed0", 1e-9, 1e-7), ("pendulum_T200_x0pert", 1e-9, 1e-7),
+                                              ("cartpole_T120", 1e-9, 1e-6), ("double_cartpole_T80", 1e-8, 1e-5)])
+def test_em_against_reference_golden(i2c_b200, name, tol_s, tol_g):
+    """B = 1 CUDA run against per-cell dumps of the unmodified reference."""
+    g = golden(name)
+
+    def opt(a):
+        return None if a.size == 0 else a
+
+    G = i2c_b200.BatchedI2c(str(g["env"]), 1, int(g["T"]), opt(g["Q"]), g["R"], opt(g["Qf"]), float(g["alpha0"]),
+                            float(g["tol"]), g["mu_u"], g["sig_u"], x0=g["x0"], enable_aux=True)
+    n_dump, n_total = int(g["n_dump"]), int(g["n_total"])
+    for it in range(1, n_dump + 1):
+        G.learn(1)
+        for a in FIELDS_F + FIELDS_B + ["mu_xu0_f", "sig_xu0_f"]:
+            e = relerr(G.field(ALIAS.get(a, a))[0], g[f"it{it}/{a}"], floor=1e-6 if a in GAINS else 0.0)
+            assert e < (tol_g if a in GAINS else tol_s), (it, a, e)
+    G.learn(n_total - n_dump)
+    assert np.all(G.status()[0] == 0)
+    al = np.array([a[0] for a in G.alphas])
+    # alpha schedule: bitwise where the ratio clip binds, else to round-off amplification
+    assert relerr(al, g["alphas"]) < 1e-8
+    assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-8
+    K, k, sk = G.get_local_linear_policy()
+    assert relerr(K[0], g["final/K"], 1e-6) < 10 * tol_g
+    assert relerr(k[0], g["final/k"], 1e-6) < 10 * tol_g
+    assert relerr(sk[0], g["final/sigK"]) < 10 * tol_s
+    assert relerr(G.field("mu_xu0_m")[0], g["final/mu_xu0_m"]) < 100 * tol_s
