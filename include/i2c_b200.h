@@ -165,6 +165,8 @@ int i2c_set_cell_flags(i2c_handle_t h, const int32_t* flags /*[H]*/);
 int i2c_get_cell_flags(i2c_handle_t h, int32_t* flags /*[H]*/);
 int i2c_set_cell_index(i2c_handle_t h, const int32_t* index /*[H]*/);
 int i2c_set_tau(i2c_handle_t h, int32_t tau);
+/* Per-cell targets: `c.z = z_traj[i]` (policy/mpc.py:30-31).  z[H][dz] (or [B][H][dz] when z_per_problem). */
+int i2c_set_cell_targets(i2c_handle_t h, const double* z);
 int i2c_set_alpha(i2c_handle_t h, const double* alpha /*[B]*/); /* _override_alpha / update_xi on all cells */
 int i2c_get_alpha(i2c_handle_t h, double* alpha /*[B]*/);
 int i2c_set_temp(i2c_handle_t h, double temp);

@@ -628,6 +628,21 @@ int i2c_set_tau(i2c_handle_t h, int32_t tau) {
   h->tau = tau;
   return 0;
 }
+int i2c_set_cell_targets(i2c_handle_t h, const double* z) {
+  REQUIRE(h && z, "NULL argument");
+  const int dz = h->d.dz, T = h->T;
+  if (h->cfg.z_per_problem) {
+    FieldMap fz{dz, 0, 0, dz, 1, 0, 0, 1};
+    return pack(h, h->z_cell, fz, 0, T, z, false);
+  }
+  for (int t = 0; t < T; ++t) {
+    int slot = (t + h->cell_head) % T;
+    CUDA_OK(cudaMemcpyAsync(h->z_cell + (size_t)slot * dz, z + (size_t)t * dz, (size_t)dz * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int i2c_set_alpha(i2c_handle_t h, const double* alpha) {
   REQUIRE(h && alpha, "NULL argument");
   FieldMap fa{1, 0, 0, 1, 1, 0, 0, 0};

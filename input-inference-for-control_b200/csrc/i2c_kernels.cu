@@ -711,7 +711,7 @@ struct Worker {
     LogAcc ent;
   };
   __device__ __forceinline__ void propagate_cell(int it, int t, int flags, bool aux, Carry<DX>& c, PStats& st) {
-    const double* po = rec(post, t, LY::E_POST);
+    const double* po = rec(latest, t, LY::E_POST);
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
     {
       double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];

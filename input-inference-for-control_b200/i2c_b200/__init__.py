@@ -3,5 +3,6 @@ from . import _capi as capi
 from ._capi import I2cError, lib
 from .batched import BatchedI2c, quadrature
 from . import envs
+from .mpc import BatchedPartiallyObservedMpc
 
-__all__ = ["BatchedI2c", "quadrature", "I2cError", "lib", "capi", "envs"]
+__all__ = ["BatchedI2c", "BatchedPartiallyObservedMpc", "quadrature", "I2cError", "lib", "capi", "envs"]

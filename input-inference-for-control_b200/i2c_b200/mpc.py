@@ -1,0 +1,74 @@
+"""Batched receding-horizon i2c controllers on the GPU.
+
+``BatchedPartiallyObservedMpc`` is the batched counterpart of the reference's
+``PartiallyObservedMpcPolicy`` (i2c/policy/mpc.py:115-182): B closed-loop roll-outs share one device-resident
+planning graph (``BatchedI2c`` with horizon T_plan); every control step runs the cubature Kalman filter
+(i2c_ckf_step), ``n_iter`` x (forward + backward sweep, _update_priors) in one persistent kernel launch, reads the
+first action, and shifts the horizon in O(1) (ring buffer of cells, i2c_shift_horizon).
+"""
+import numpy as np
+
+from . import _capi as capi
+
+
+class BatchedPartiallyObservedMpc:
+    def __init__(self, i2c, n_iter, sig_u, z_traj=None, sig_zeta=None):
+        self.i2c = i2c
+        self.dim_u, self.dim_x = i2c.dims[1], i2c.dims[0]
+        self.n_iter = int(n_iter)
+        self.sig_u = np.asarray(sig_u, float)
+        self.sig_zeta = sig_zeta
+        # MpcPolicy.__init__ (policy/mpc.py:16-33): tau = 0; cell_init = deepcopy(cells[0]) BEFORE the targets are
+        # assigned: the appended cells carry the initial action prior of cell 0 and the initial alpha (quirk A.6.6)
+        i2c.tau = 0
+        self._mu_u_init = i2c.mu_u_init[0, 0].copy()
+        self._alpha_init = float(i2c.alpha0[0])
+        self.z_traj = None if z_traj is None else np.asarray(z_traj, float)
+        if self.z_traj is not None:
+            self._set_targets(self.z_traj[: i2c.H])
+        self._z_last = None if self.z_traj is None else self.z_traj[i2c.H - 1].copy()
+
+    def _set_targets(self, z):
+        import ctypes as C
+
+        g = self.i2c
+        assert not g.z_per_problem
+        g.z = capi.f64(z, (g.H, g.dims[2]))
+        # cell targets live in one small device array; re-upload through the problem setter's z path
+        capi.check(g.lib.i2c_set_cell_targets(g._h, capi.ptr(g.z)))
+
+    def set_control(self, feedforward):
+        """policy/mpc.py:35-41 (tau = 0: cells stay independent; tau = H: feedback after the first _update_priors)."""
+        self.i2c.tau = 0 if feedforward else self.i2c.H
+
+    def filter(self, y, u):
+        """PartiallyObservedMpcPolicy.filter (policy/mpc.py:125-145)."""
+        self.i2c.ckf_step(y, u, self.sig_zeta)
+
+    def optimize(self, n_iter, mu=None, covar=None):
+        """policy/mpc.py:147-154: n_iter x (_forward_backward_msgs; _update_priors) from the current belief."""
+        if mu is not None:
+            self.i2c.set_initial_state(mu, covar)
+        self.i2c.forward_backward(n_iter, update_priors=True)
+
+    @property
+    def belief(self):
+        return self.i2c.get_initial_state()
+
+    def __call__(self, i, y, u):
+        """policy/mpc.py:156-182 with deterministic=True: returns the first planned action [B, du]."""
+        if i > 0:
+            self.filter(y, u)
+        self.optimize(self.n_iter)
+        ctrl, _ = self.i2c.first_action()
+        g = self.i2c
+        if self.z_traj is not None:
+            if (i + g.H) < self.z_traj.shape[0]:
+                z_new = self.z_traj[i + g.H]
+            else:
+                z_new = self._z_last
+            self._z_last = np.array(z_new, float)
+        else:
+            z_new = g.z_graph
+        g.shift_horizon(z_new, self._mu_u_init, self._alpha_init)
+        return ctrl
