@@ -47,9 +47,9 @@ struct EnvPendulum {
   static constexpr int DX = 2, DU = 1, DZ = 4, DZT = 3, NP = 0, DY = 0, NA = 1;
   static constexpr bool HAS_TERM = true;
   using TrigT = Trig<NA>;
-  __device__ static void center(const double* m, TrigT& t) { sincos(m[0], &t.s[0], &t.c[0]); }
+  __device__ static void center(const double* m, TrigT& t) { fast_sincos(m[0], &t.s[0], &t.c[0]); }
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j != 0) { s = c.s[0]; co = c.c[0]; } else { sincos(x[0], &s, &co); }
+    if (j != 0) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[0], &s, &co); }
   }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
     const double dt = 0.05, d = 1e-2, g = 9.80665;
@@ -90,9 +90,9 @@ struct EnvCartpole {
   static constexpr int DX = 4, DU = 1, DZ = 6, DZT = 5, NP = 0, DY = 0, NA = 1;
   static constexpr bool HAS_TERM = true;
   using TrigT = Trig<NA>;
-  __device__ static void center(const double* m, TrigT& t) { sincos(m[1], &t.s[0], &t.c[0]); }
+  __device__ static void center(const double* m, TrigT& t) { fast_sincos(m[1], &t.s[0], &t.c[0]); }
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { sincos(x[1], &s, &co); }
+    if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[1], &s, &co); }
   }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
     const double g = 9.81, Mc = 0.37, Mp = 0.127, Mt = Mc + Mp, l = 0.3365, dt = 1.0 / 250.0;
@@ -102,8 +102,8 @@ struct EnvCartpole {
     double dth2 = xu[3] * xu[3];
     double num = -Mp * l * sth * cth * dth2 + Mt * g * sth - u * cth;
     double den = l * ((4.0 / 3.0) * Mt - Mp * cth * cth);
-    double th_acc = num / den;
-    double x_acc = (Mp * l * sth * dth2 - Mp * l * th_acc * cth + u) / Mt;
+    double th_acc = num * fast_rcp(den);
+    double x_acc = (Mp * l * sth * dth2 - Mp * l * th_acc * cth + u) * (1.0 / Mt);
     y[0] = fma(dt, xu[2], xu[0]);
     y[1] = fma(dt, xu[3], xu[1]);
     y[2] = fma(dt, x_acc, xu[2]);
@@ -130,14 +130,14 @@ struct EnvDoubleCartpole {
   static constexpr bool HAS_TERM = true;
   using TrigT = Trig<NA>;
   __device__ static void center(const double* m, TrigT& t) {
-    sincos(m[1], &t.s[0], &t.c[0]);
-    sincos(m[2], &t.s[1], &t.c[1]);
+    fast_sincos(m[1], &t.s[0], &t.c[0]);
+    fast_sincos(m[2], &t.s[1], &t.c[1]);
   }
   __device__ static void trig1(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { sincos(x[1], &s, &co); }
+    if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[1], &s, &co); }
   }
   __device__ static void trig2(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j < 0 || j > 2) { s = c.s[1]; co = c.c[1]; } else { sincos(x[2], &s, &co); }
+    if (j < 0 || j > 2) { s = c.s[1]; co = c.c[1]; } else { fast_sincos(x[2], &s, &co); }
   }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
     const double dt = 1.0 / 125.0, g = 9.81, Mc = 0.37, Mp1 = 0.127, Mp2 = 0.127, Mt = Mc + Mp1 + Mp2;
@@ -147,7 +147,7 @@ struct EnvDoubleCartpole {
     double s1, c1, s2, c2, sd, cd;
     trig1(xu, j, c, s1, c1);
     trig2(xu, j, c, s2, c2);
-    sincos(xu[1] - xu[2], &sd, &cd);
+    fast_sincos(xu[1] - xu[2], &sd, &cd);
     double M12 = a12 * c1, M13 = a13 * c2, M23 = a23 * cd;
     double qd = xu[3], td1 = xu[4], td2 = xu[5];
     double C12 = -a12 * td1 * s1, C13 = -a13 * td2 * s2, C23 = a23 * td2 * sd, C32 = -a23 * td1 * sd;
@@ -158,11 +158,11 @@ struct EnvDoubleCartpole {
     double r2 = -(C23 * td2) - G2;
     double r3 = -(C32 * td1) - G3;
     // solve the SPD 3x3 system M qdd = r by Cholesky (the reference forms inv(M) @ r)
-    double l11 = sqrt(M11), i11 = 1.0 / l11;
+    const double i11 = 1.2659242088545832;  // 1/sqrt(Mt), Mt = 0.624
     double l21 = M12 * i11, l31 = M13 * i11;
-    double l22 = sqrt(M22 - l21 * l21), i22 = 1.0 / l22;
+    double i22 = fast_rsqrt(M22 - l21 * l21);
     double l32 = (M23 - l31 * l21) * i22;
-    double l33 = sqrt(M33 - l31 * l31 - l32 * l32), i33 = 1.0 / l33;
+    double i33 = fast_rsqrt(M33 - l31 * l31 - l32 * l32);
     double y1 = r1 * i11;
     double y2 = (r2 - l21 * y1) * i22;
     double y3 = (r3 - l31 * y1 - l32 * y2) * i33;
@@ -201,9 +201,9 @@ struct EnvQuadrotor {
   static constexpr double VDX = 0.8;                                      // W/25
   static constexpr double MASS = 5.0 * (2 * 0.8) * (2 * (400.0 / 30.0 / 100.0));
   static constexpr double INERTIA = MASS * ((2 * 0.8) * (2 * 0.8) + (2 * (400.0 / 30.0 / 100.0)) * (2 * (400.0 / 30.0 / 100.0))) / 12.0;
-  __device__ static void center(const double* m, TrigT& t) { sincos(m[2], &t.s[0], &t.c[0]); }
+  __device__ static void center(const double* m, TrigT& t) { fast_sincos(m[2], &t.s[0], &t.c[0]); }
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j < 0 || j > 2) { s = c.s[0]; co = c.c[0]; } else { sincos(x[2], &s, &co); }
+    if (j < 0 || j > 2) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[2], &s, &co); }
   }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
     const double h = 0.1;
@@ -211,9 +211,9 @@ struct EnvQuadrotor {
     double s, co;
     trig(xu, j, c, s, co);
     double f = u1 + u2;
-    double vx = xu[3] + h * ((-s * f) / MASS);
-    double vy = xu[4] + h * (-9.81 + (co * f) / MASS);
-    double w = xu[5] + h * (VDX * (u2 - u1)) / INERTIA;
+    double vx = xu[3] + h * ((-s * f) * (1.0 / MASS));
+    double vy = xu[4] + h * (-9.81 + (co * f) * (1.0 / MASS));
+    double w = xu[5] + h * (VDX * (u2 - u1)) * (1.0 / INERTIA);
     w = w * (1.0 / (1.0 + h * 0.5));
     y[0] = xu[0] + h * vx;
     y[1] = xu[1] + h * vy;

@@ -38,7 +38,27 @@ struct Lay {
                        PF_SIG3 = PF_MU3 + DX;
   static constexpr int E_PF = PF_SIG3 + TRI(DX);
   static constexpr int TM_MU = 0, TM_SIG = DZT, E_TERM = DZT + TRI(DZT);
+  // staged (prefetched) parts of the records: the prior / posterior without k, sigK; the whole filtered record
+  static constexpr int E_STAGE_POST = P_KK, E_STAGE = E_FILT > P_KK ? E_FILT : P_KK;
 };
+
+// ------------------------------------------------------------------------------------------------
+// cp.async staging of the next cell's record: every thread copies ITS OWN E elements (8 B each, one coalesced
+// 256-byte segment per warp instruction) into thread-private shared-memory slots while the current cell is being
+// computed, then waits on its own async group -- no block / warp synchronisation is needed because no slot is
+// shared between threads.  Layout of the staging buffer mirrors the global record: smem[e][lane].
+template <int E>
+__device__ __forceinline__ void stage_record(double* sdst, const double* gsrc) {
+  const unsigned s0 = (unsigned)__cvta_generic_to_shared(sdst);
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s0 + e * TILE * 8), "l"(gsrc + (size_t)e * TILE) : "memory");
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // Sigma-point transform (inference/quadrature.py:15-58) around (m, chol L) in dimension D.
@@ -253,8 +273,10 @@ struct Worker {
   // most recently written posterior `latest`; _update_priors swaps prior/post instead of copying.
   double *prior, *post, *latest;
   bool own_alpha_valid;
+  double* stage;  // this warp's double buffer: [2][E_STAGE][32], already offset by lane
 
-  __device__ Worker(const KParams& p_, int tile_, int lane_) : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_) {
+  __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_)
+      : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_) {
     status = I2C_OK;
     info = 0;
     prior = p.prior;
@@ -346,9 +368,8 @@ struct Worker {
 
   // ---------------------------------------------------------------------------------- forward cell
   // I2cCell._forward_msgs_quadrature (i2c.py:350-447).  c: (mu_x0_f, sig_x0_f) in, (mu_x3_f, sig_x3_f) out.
-  __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, Carry<DX>& c,
-                                               LogAcc& ent_x) {
-    const double* pr = rec(prior, t, LY::E_POST);
+  __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, const double* pr,
+                                               Carry<DX>& c, LogAcc& ent_x) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
     {
       double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];
@@ -510,8 +531,8 @@ struct Worker {
     double cost, cost_var, tr;
     LogAcc ent_u;
   };
-  __device__ __forceinline__ void backward_cell(int it, int t, int flags, bool aux, double* m3m, double* S3m, Stats& st) {
-    const double* fr = rec(p.filt, t, LY::E_FILT);
+  __device__ __forceinline__ void backward_cell(int it, int t, int flags, bool aux, const double* fr, double* m3m,
+                                                double* S3m, Stats& st) {
     double mu[N], Sig[TRI(N)], J[N * DX];
     {
       double dm[DX], dS[TRI(DX)];
@@ -710,8 +731,8 @@ struct Worker {
     double cost, cost_var, cost_min, tr;
     LogAcc ent;
   };
-  __device__ __forceinline__ void propagate_cell(int it, int t, int flags, bool aux, Carry<DX>& c, PStats& st) {
-    const double* po = rec(latest, t, LY::E_POST);
+  __device__ __forceinline__ void propagate_cell(int it, int t, int flags, bool aux, const double* po, Carry<DX>& c,
+                                                 PStats& st) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
     {
       double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];
@@ -857,11 +878,19 @@ struct Worker {
       double tr_term = 0.0;
       if (p.phases & I2C_PH_FORWARD) {
         if (!load_x0(c)) fail(I2C_FAIL_CHOL_PRIOR, it, 0);
+        __threadfence();  // records written by earlier sweeps of this thread are read back through cp.async
+        stage_record<LY::E_STAGE_POST>(stage, rec(prior, 0, LY::E_POST));
+        stage_commit();
         for (int t = 0; t < T; ++t) {
+          double* cur = stage + (t & 1) * (LY::E_STAGE * TILE);
+          if (t + 1 < T) stage_record<LY::E_STAGE_POST>(stage + ((t + 1) & 1) * (LY::E_STAGE * TILE), rec(prior, t + 1, LY::E_POST));
+          stage_commit();
           int flags = p.cell_flags[slot(t)];
           if (flipped && p.tau > 0 && p.cell_index[slot(t)] <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
-          forward_cell(it, t, flags, alpha, aux, c, ent_x);
+          stage_wait<1>();
+          forward_cell(it, t, flags, alpha, aux, cur, c, ent_x);
         }
+        stage_wait<0>();
       }
       if (p.phases & I2C_PH_BACKWARD) {
         if (!(p.phases & I2C_PH_FORWARD)) {
@@ -879,7 +908,17 @@ struct Worker {
         double m3m[DX], S3m[TRI(DX)];
         backward_terminal(it, T - 1, temp, c, m3m, S3m, tr_term);
         if (p.cov_ctrl) temp += p.dtemp;
-        for (int t = T - 1; t >= 0; --t) backward_cell(it, t, p.cell_flags[slot(t)], aux, m3m, S3m, st);
+        __threadfence();
+        stage_record<LY::E_FILT>(stage + ((T - 1) & 1) * (LY::E_STAGE * TILE), rec(p.filt, T - 1, LY::E_FILT));
+        stage_commit();
+        for (int t = T - 1; t >= 0; --t) {
+          double* cur = stage + (t & 1) * (LY::E_STAGE * TILE);
+          if (t > 0) stage_record<LY::E_FILT>(stage + ((t - 1) & 1) * (LY::E_STAGE * TILE), rec(p.filt, t - 1, LY::E_FILT));
+          stage_commit();
+          stage_wait<1>();
+          backward_cell(it, t, p.cell_flags[slot(t)], aux, cur, m3m, S3m, st);
+        }
+        stage_wait<0>();
         latest = post;
       }
       PStats ps;
@@ -889,11 +928,19 @@ struct Worker {
       if (p.phases & I2C_PH_PROPAGATE) {
         Carry<DX> cp;
         if (!load_x0(cp)) fail(I2C_FAIL_CHOL_PROPAGATE, it, 0);
+        __threadfence();
+        stage_record<LY::E_STAGE_POST>(stage, rec(latest, 0, LY::E_POST));
+        stage_commit();
         for (int t = 0; t < T; ++t) {
+          double* cur = stage + (t & 1) * (LY::E_STAGE * TILE);
+          if (t + 1 < T) stage_record<LY::E_STAGE_POST>(stage + ((t + 1) & 1) * (LY::E_STAGE * TILE), rec(latest, t + 1, LY::E_POST));
+          stage_commit();
           int flags = p.cell_flags[slot(t)];
           if (flipped && p.tau > 0 && p.cell_index[slot(t)] <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
-          propagate_cell(it, t, flags, aux, cp, ps);
+          stage_wait<1>();
+          propagate_cell(it, t, flags, aux, cur, cp, ps);
         }
+        stage_wait<0>();
         if (p.cov_ctrl) {
           // KL(N(mu_x3_pf, sig_x3_pf) || N(mu_xT, sig_xT)) of the last cell (i2c.py:1012-1019, 1223-1229)
           double A[TRI(DX)], ia[DX], d[DX];
@@ -995,7 +1042,9 @@ __global__ void __launch_bounds__(128) em_kernel(const __grid_constant__ KParams
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / TILE;
   const int lane = threadIdx.x % TILE;
   if (warp >= pin.ntiles) return;
-  Worker<Env> w(pin, warp, lane);
+  extern __shared__ __align__(16) double stage_smem[];
+  double* stage = stage_smem + (size_t)(threadIdx.x / TILE) * (2 * Lay<Env>::E_STAGE * TILE) + lane;
+  Worker<Env> w(pin, warp, lane, stage);
   w.run();
 }
 
@@ -1007,7 +1056,14 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   if (p.ntiles >= 148 * 32) threads = 128;
   int wpb = threads / TILE;
   int blocks = (p.ntiles + wpb - 1) / wpb;
-  em_kernel<Env><<<blocks, threads, 0, s>>>(p);
+  const size_t smem = (size_t)wpb * 2 * Lay<Env>::E_STAGE * TILE * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  em_kernel<Env><<<blocks, threads, smem, s>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "fastmath.cuh"
+
 namespace i2c {
 
 __host__ __device__ constexpr int TRI(int n) { return n * (n + 1) / 2; }
@@ -29,7 +31,7 @@ __device__ __forceinline__ bool chol_rows(double* A, double* invd) {
 #pragma unroll
     for (int k = 0; k < i; ++k) d = fma(-A[tix(i, k)], A[tix(i, k)], d);
     ok = ok && (d > 0.0) && (d < 1.0e300);
-    double r = rsqrt(d);
+    double r = fast_rsqrt(d);
     invd[i] = r;
     A[tix(i, i)] = d * r;
   }
