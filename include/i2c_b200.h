@@ -73,7 +73,9 @@ enum i2c_phase {
   I2C_PH_UPDATE_PRIORS = 16, /* I2cGraph._update_priors       i2c.py:1210-1221 */
   I2C_PH_CALIBRATE = 32,     /* calibrate_alpha (after PROPAGATE)  i2c.py:895-911 */
   I2C_PH_ONLY_DECREASE = 64, /* calibrate_alpha(only_decrease=True) */
-  I2C_PH_STORE_AUX = 128     /* also write the per-cell auxiliary messages (mu_z0_f, sig_z0_f, prior joint, ...) */
+  I2C_PH_STORE_AUX = 128,    /* also write the per-cell auxiliary messages (mu_z0_f, sig_z0_f, prior joint, ...) */
+  I2C_PH_RICCATI = 256       /* I2cGraph._backward_ricatti_msgs (i2c.py:888-893, cells :612-678); Linearize, linear envs,
+                                needs the aux records of the preceding forward/backward pass */
 };
 /* I2cGraph.learn_msgs (i2c.py:1238-1245) without / with propagate */
 #define I2C_PH_LEARN (I2C_PH_FORWARD | I2C_PH_BACKWARD | I2C_PH_MSTEP | I2C_PH_UPDATE_PRIORS)
@@ -104,7 +106,9 @@ enum i2c_field {
   I2C_F_MU_X3_PF = 25, I2C_F_SIG_X3_PF = 26,
   /* terminal cost-feature moments of the last cell: shape [B][1][...] */
   I2C_F_MU_Z3_M = 27, I2C_F_SIG_Z3_M = 28,
-  I2C_F_COUNT = 29
+  /* Riccati messages (after I2C_PH_RICCATI): full [dx][dx] matrices / [dx] vectors */
+  I2C_F_LAMBDA_X3_B = 29, I2C_F_NU_X3_B = 30, I2C_F_LAMBDA_X0_B = 31, I2C_F_NU_X0_B = 32,
+  I2C_F_COUNT = 33
 };
 
 /* Per-iteration, per-problem scalars (the Python lists on I2cGraph: i2c.py:1329-1372) */
@@ -146,7 +150,8 @@ int i2c_destroy(i2c_handle_t h);
  * constructor state (I2cCell.__init__, i2c.py:54-148): priors = (mu_u, sig_u), K = 0, all cells
  * independent, last cell terminal, tau = H-1, temp = 1.
  *   x0[B][dx], sig_x0[B][dx][dx], sig_eta[dx][dx], mu_u[B][H][du], sig_u[du][du],
- *   QR[dz][dz] (= block_diag(Q,R) or R), Qf[dzt][dzt] or NULL, z[H][dz] (or [B][H][dz]), z_term[dzt] or NULL,
+ *   QR[dz][dz] (= block_diag(Q,R) or R), Qf[dzt][dzt] or NULL, z[H][dz] (or [B][H][dz]), z_graph[dz] (the graph-level
+ *   target used by calc_cost), z_term[dzt] (or [B][dzt] when z_per_problem) or NULL,
  *   alpha0[B], mu_x_term[dx]/sig_x_term[dx][dx] or NULL (covariance control),
  *   env_par[B][n_par] or NULL (linear envs: A row-major, B, a). */
 int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, const double* sig_eta,

@@ -21,8 +21,11 @@ struct Trig {
 // par = [A00 A01 A10 A11 B0 B1 a0 a1].
 struct EnvLinear {
   static constexpr int DX = 2, DU = 1, DZ = 3, DZT = 2, NP = 8, DY = 0, NA = 0;
-  static constexpr bool HAS_TERM = true;
+  static constexpr bool HAS_TERM = true, LINEAR = true;
   using TrigT = Trig<NA>;
+  // z = E x + F u (+ e = 0): observe_linearize (env_def.py:171-181): E = [I2; 0], F = [0 0 1]^T
+  __host__ __device__ static constexpr double obsE(int a, int i) { return a == i ? 1.0 : 0.0; }
+  __host__ __device__ static constexpr double obsF(int a, int) { return a == 2 ? 1.0 : 0.0; }
   __device__ static void center(const double*, TrigT&) {}
   __device__ static void dyn(const double* xu, int, const TrigT&, const double* par, double* y) {
     y[0] = fma(par[0], xu[0], fma(par[1], xu[1], fma(par[4], xu[2], par[6])));
@@ -38,6 +41,9 @@ struct EnvLinear {
 // LinearMinimumEnergyDef: env_def.py:194-230 (cost on u only).
 struct EnvLinearMinEnergy : EnvLinear {
   static constexpr int DZ = 1;
+  // env_def.py:211-217: C = 0 (1x2), D = 1
+  __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
+  __host__ __device__ static constexpr double obsF(int, int) { return 1.0; }
   __device__ static void obs(const double* xu, int, const TrigT&, double* z) { z[0] = xu[2]; }
 };
 
@@ -45,7 +51,9 @@ struct EnvLinearMinEnergy : EnvLinear {
 // env_autograd.py:5-19 (dynamics), env_def.py:273-291 (features [sin th, cos th, thd, u]).
 struct EnvPendulum {
   static constexpr int DX = 2, DU = 1, DZ = 4, DZT = 3, NP = 0, DY = 0, NA = 1;
-  static constexpr bool HAS_TERM = true;
+  static constexpr bool HAS_TERM = true, LINEAR = false;
+  __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
+  __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
   using TrigT = Trig<NA>;
   __device__ static void center(const double* m, TrigT& t) { fast_sincos(m[0], &t.s[0], &t.c[0]); }
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
@@ -88,7 +96,9 @@ struct EnvPendulumActReg : EnvPendulum {
 // env_autograd.py:25-54, env_def.py:537-570 (features [x, sin th, cos th, xd, thd, u]).
 struct EnvCartpole {
   static constexpr int DX = 4, DU = 1, DZ = 6, DZT = 5, NP = 0, DY = 0, NA = 1;
-  static constexpr bool HAS_TERM = true;
+  static constexpr bool HAS_TERM = true, LINEAR = false;
+  __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
+  __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
   using TrigT = Trig<NA>;
   __device__ static void center(const double* m, TrigT& t) { fast_sincos(m[1], &t.s[0], &t.c[0]); }
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
@@ -127,7 +137,9 @@ struct EnvCartpole {
 // (features [x, sin th1, cos th1, sin th2, cos th2, xd, thd1, thd2, u]).
 struct EnvDoubleCartpole {
   static constexpr int DX = 6, DU = 1, DZ = 9, DZT = 8, NP = 0, DY = 0, NA = 2;
-  static constexpr bool HAS_TERM = true;
+  static constexpr bool HAS_TERM = true, LINEAR = false;
+  __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
+  __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
   using TrigT = Trig<NA>;
   __device__ static void center(const double* m, TrigT& t) {
     fast_sincos(m[1], &t.s[0], &t.c[0]);
@@ -196,7 +208,9 @@ struct EnvDoubleCartpole {
 // (typos in the right-rotor velocities reproduced).  observe is the identity.
 struct EnvQuadrotor {
   static constexpr int DX = 6, DU = 2, DZ = 8, DZT = 6, NP = 0, DY = 8, NA = 1;
-  static constexpr bool HAS_TERM = true;
+  static constexpr bool HAS_TERM = true, LINEAR = false;
+  __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
+  __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
   using TrigT = Trig<NA>;
   static constexpr double VDX = 0.8;                                      // W/25
   static constexpr double MASS = 5.0 * (2 * 0.8) * (2 * (400.0 / 30.0 / 100.0));

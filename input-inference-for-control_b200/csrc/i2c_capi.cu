@@ -50,7 +50,7 @@ struct i2c_handle_s {
   char* ws;
   size_t ws_bytes;
   // device buffers (inside ws)
-  double *recA, *recB, *filt, *auxf, *auxb, *pf, *term, *x0, *sig_x0, *alpha, *alpha_cell, *z_cell, *envpar, *metrics,
+  double *recA, *recB, *filt, *auxf, *auxb, *pf, *ric, *term, *x0, *sig_x0, *alpha, *alpha_cell, *z_cell, *z_term_pp, *envpar, *metrics,
       *scratch;
   int32_t *cell_flags_dev, *cell_index_dev, *status, *info;
   size_t scratch_elems;
@@ -66,6 +66,7 @@ struct i2c_handle_s {
   long long launches;
   cudaEvent_t ev0, ev1;
   bool problem_set;
+  bool has_z_term_pp;
   std::vector<double> mu_u_init_last, sig_u_host;
 };
 
@@ -175,7 +176,7 @@ static inline int nblocks(size_t total) {
 
 // ----------------------------------------------------------------------------------------- layout
 struct WsLayout {
-  size_t recA, recB, filt, auxf, auxb, pf, term, x0, sig_x0, alpha, alpha_cell, z_cell, envpar, metrics, scratch, flags,
+  size_t recA, recB, filt, auxf, auxb, pf, ric, term, x0, sig_x0, alpha, alpha_cell, z_cell, z_term_pp, envpar, metrics, scratch, flags,
       index, status, info, total, scratch_elems;
 };
 
@@ -195,12 +196,14 @@ static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
   w.auxf = take(c.enable_aux ? T * nt * r.e_auxf() * TILE : 0, 8);
   w.auxb = take(c.enable_aux ? T * nt * r.e_auxb() * TILE : 0, 8);
   w.pf = take(c.enable_aux ? T * nt * r.e_pf() * TILE : 0, 8);
+  w.ric = take((c.enable_aux && c.inference == I2C_INF_LINEARIZE) ? T * nt * r.e_ric() * TILE : 0, 8);
   w.term = take(nt * r.e_term() * TILE, 8);
   w.x0 = take(nt * d.dx * TILE, 8);
   w.sig_x0 = take(nt * tri(d.dx) * TILE, 8);
   w.alpha = take(Bpad, 8);
   w.alpha_cell = take(T * Bpad, 8);
   w.z_cell = take(c.z_per_problem ? T * nt * d.dz * TILE : T * d.dz, 8);
+  w.z_term_pp = take(c.z_per_problem ? nt * d.dzt * TILE : 0, 8);
   w.envpar = take(nt * (d.np > 0 ? d.np : 1) * TILE, 8);
   w.metrics = take((size_t)I2C_M_COUNT * c.max_iters * Bpad, 8);
   size_t n = d.dx + d.du;
@@ -220,7 +223,9 @@ static int check_cfg(const i2c_config_t* cfg) {
   REQUIRE(cfg != nullptr, "cfg is NULL");
   REQUIRE(cfg->abi_version == I2C_ABI_VERSION, "ABI version mismatch");
   REQUIRE(cfg->env >= 0 && cfg->env < I2C_ENV_COUNT, "unknown env id (no CPU fallback for unregistered envs)");
-  REQUIRE(cfg->inference == I2C_INF_CUBATURE, "only cubature inference runs through i2c_run");
+  REQUIRE(cfg->inference == I2C_INF_CUBATURE || cfg->inference == I2C_INF_LINEARIZE, "unknown inference kind");
+  REQUIRE(cfg->inference == I2C_INF_CUBATURE || cfg->env == I2C_ENV_LINEAR || cfg->env == I2C_ENV_LINEAR_MIN_ENERGY,
+          "Linearize inference is only available for the linear environments (nonlinear Jacobians: not built)");
   REQUIRE(cfg->n_problems >= 1 && cfg->horizon >= 1 && cfg->horizon < 65536, "bad B or H");
   REQUIRE(cfg->max_iters >= 1, "max_iters must be >= 1");
   REQUIRE(cfg->quad_alpha > 0.0, "cubature alpha must be > 0");
@@ -294,12 +299,14 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
   h->auxf = cfg->enable_aux ? (double*)(h->ws + w.auxf) : nullptr;
   h->auxb = cfg->enable_aux ? (double*)(h->ws + w.auxb) : nullptr;
   h->pf = cfg->enable_aux ? (double*)(h->ws + w.pf) : nullptr;
+  h->ric = (cfg->enable_aux && cfg->inference == I2C_INF_LINEARIZE) ? (double*)(h->ws + w.ric) : nullptr;
   h->term = (double*)(h->ws + w.term);
   h->x0 = (double*)(h->ws + w.x0);
   h->sig_x0 = (double*)(h->ws + w.sig_x0);
   h->alpha = (double*)(h->ws + w.alpha);
   h->alpha_cell = (double*)(h->ws + w.alpha_cell);
   h->z_cell = (double*)(h->ws + w.z_cell);
+  h->z_term_pp = cfg->z_per_problem ? (double*)(h->ws + w.z_term_pp) : nullptr;
   h->envpar = (double*)(h->ws + w.envpar);
   h->metrics = (double*)(h->ws + w.metrics);
   h->scratch = (double*)(h->ws + w.scratch);
@@ -408,6 +415,10 @@ static int field_map(i2c_handle_t h, int field, FieldMap* f, double** base) {
     case I2C_F_SIG_X3_PF: m = {r.e_pf(), n + tri(n) + dz + tri(dz) + dx, 1, dx, dx, 0, 0, 1}; *base = h->pf; break;
     case I2C_F_MU_Z3_M: m = {r.e_term(), 0, 0, dzt, 1, 0, 0, 0}; *base = h->term; break;
     case I2C_F_SIG_Z3_M: m = {r.e_term(), dzt, 1, dzt, dzt, 0, 0, 0}; *base = h->term; break;
+    case I2C_F_LAMBDA_X3_B: m = {r.e_ric(), 0, 0, dx, dx, 0, 0, 1}; *base = h->ric; break;
+    case I2C_F_NU_X3_B: m = {r.e_ric(), dx * dx, 0, dx, 1, 0, 0, 1}; *base = h->ric; break;
+    case I2C_F_LAMBDA_X0_B: m = {r.e_ric(), dx * dx + dx, 0, dx, dx, 0, 0, 1}; *base = h->ric; break;
+    case I2C_F_NU_X0_B: m = {r.e_ric(), 2 * dx * dx + dx, 0, dx, 1, 0, 0, 1}; *base = h->ric; break;
     default: return set_err(-1, "unknown field id");
   }
   if (*base == nullptr) return set_err(-1, "field needs a handle created with enable_aux=1");
@@ -536,6 +547,7 @@ int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, cons
     REQUIRE(host_spd_inverse(Qf, dzt, kp.Qfinv, nullptr), "Qf must be positive definite");
     for (int a = 0; a < dzt; ++a) kp.z_term[a] = z_term[a];
   }
+  h->has_z_term_pp = false;
   full_to_tri(sig_eta, dx, kp.sig_eta);
   for (int a = 0; a < dz; ++a) kp.z_graph[a] = z_graph[a];
   kp.cov_ctrl = sig_x_term != nullptr;
@@ -584,6 +596,12 @@ int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, cons
     FieldMap fz{dz, 0, 0, dz, 1, 0, 0, 1};
     rc = pack(h, h->z_cell, fz, 0, T, z, false);
     if (rc) return rc;
+    if (Qf != nullptr) {  // z_term is [B][dzt] when targets are per problem
+      FieldMap ft{dzt, 0, 0, dzt, 1, 0, 0, 0};
+      rc = pack(h, h->z_term_pp, ft, 0, 1, z_term, false);
+      if (rc) return rc;
+      h->has_z_term_pp = true;
+    }
   } else {
     CUDA_OK(cudaMemcpyAsync(h->z_cell, z, (size_t)T * dz * 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -674,6 +692,7 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "n_iter must be in [1, max_iters]");
   REQUIRE(!(phases & I2C_PH_STORE_AUX) || h->cfg.enable_aux, "I2C_PH_STORE_AUX needs enable_aux=1");
   REQUIRE(!(phases & I2C_PH_CALIBRATE) || (phases & I2C_PH_PROPAGATE), "CALIBRATE needs PROPAGATE");
+  REQUIRE(!(phases & I2C_PH_RICCATI) || (h->ric != nullptr), "RICCATI needs Linearize inference and enable_aux=1");
   KParams kp = h->kp;
   kp.prior = rec_prior(h);
   kp.post = rec_post(h);
@@ -682,12 +701,15 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   kp.auxf = h->auxf;
   kp.auxb = h->auxb;
   kp.pf = h->pf;
+  kp.ric = h->ric;
+  kp.linearize = h->cfg.inference == I2C_INF_LINEARIZE;
   kp.term = h->term;
   kp.x0 = h->x0;
   kp.sig_x0 = h->sig_x0;
   kp.alpha = h->alpha;
   kp.alpha_cell = h->alpha_cell;
   kp.z_cell = h->z_cell;
+  kp.z_term_pp = h->has_z_term_pp ? h->z_term_pp : nullptr;
   kp.envpar = h->envpar;
   kp.cell_flags = h->cell_flags_dev;
   kp.cell_index = h->cell_index_dev;
@@ -767,10 +789,11 @@ int i2c_field_shape(i2c_handle_t h, int32_t field, int32_t* rows, int32_t* cols)
   // shape queries must work without aux buffers
   bool had = h->cfg.enable_aux;
   double* dummy = (double*)1;
-  double *a0 = h->auxf, *a1 = h->auxb, *a2 = h->pf;
+  double *a0 = h->auxf, *a1 = h->auxb, *a2 = h->pf, *a3 = h->ric;
   if (!had) h->auxf = h->auxb = h->pf = dummy;
+  if (!h->ric) h->ric = dummy;
   int rc = field_map(h, field, &f, &base);
-  h->auxf = a0, h->auxb = a1, h->pf = a2;
+  h->auxf = a0, h->auxb = a1, h->pf = a2, h->ric = a3;
   if (rc) return rc;
   if (rows) *rows = f.rows;
   if (cols) *cols = f.cols;

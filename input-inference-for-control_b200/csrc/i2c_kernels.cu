@@ -38,6 +38,7 @@ struct Lay {
                        PF_SIG3 = PF_MU3 + DX;
   static constexpr int E_PF = PF_SIG3 + TRI(DX);
   static constexpr int TM_MU = 0, TM_SIG = DZT, E_TERM = DZT + TRI(DZT);
+  static constexpr int R_L3 = 0, R_N3 = DX * DX, R_L0 = R_N3 + DX, R_N0 = R_L0 + DX * DX, E_RIC = R_N0 + DX;
   // staged (prefetched) parts of the records: the prior / posterior without k, sigK; the whole filtered record
   static constexpr int E_STAGE_POST = P_KK, E_STAGE = E_FILT > P_KK ? E_FILT : P_KK;
 };
@@ -310,6 +311,16 @@ struct Worker {
       for (int a = 0; a < DZ; ++a) z[a] = p.z_cell[slot(t) * DZ + a];
     }
   }
+  __device__ __forceinline__ void load_zterm(double* zt) const {
+    if (p.z_term_pp) {
+      const double* q = p.z_term_pp + ((size_t)tile * DZT) * TILE + lane;
+#pragma unroll
+      for (int a = 0; a < DZT; ++a) zt[a] = q[a * TILE];
+    } else {
+#pragma unroll
+      for (int a = 0; a < DZT; ++a) zt[a] = p.z_term[a];
+    }
+  }
   __device__ __forceinline__ double cell_alpha(int t, int flags, double alpha) const {
     return ((flags & I2C_CELL_OWN_ALPHA) && own_alpha_valid) ? p.alpha_cell[(size_t)slot(t) * p.Bpad + b] : alpha;
   }
@@ -366,8 +377,70 @@ struct Worker {
     return chol_rows<N, DX>(L, invd);
   }
 
+  // ---------------------------------------------------------------------------------- Linearize moments
+  // Exact moments of the linear cost-feature map z = E x + F u (observe_linearize, env_def.py:171-181)
+  // and of the linear dynamics x' = A x + B u + a (LinearBase.forward_linearize, model.py:240-242):
+  // what _forward_msgs_linearize (i2c.py:297-306, 322-340) feeds its Kalman update / RTS gain.
+  __device__ __forceinline__ void lin_obs_moments(const double* mu, const double* Sig, double* mz, double* Sz, double* Sxy) {
+#pragma unroll
+    for (int a = 0; a < DZ; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) s = fma(i < DX ? Env::obsE(a, i) : Env::obsF(a, i - DX), mu[i], s);
+      mz[a] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int a = 0; a < DZ; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) s = fma(Sig[six(i, k)], k < DX ? Env::obsE(a, k) : Env::obsF(a, k - DX), s);
+        Sxy[i * DZ + a] = s;
+      }
+#pragma unroll
+    for (int a = 0; a < DZ; ++a)
+#pragma unroll
+      for (int bb = 0; bb <= a; ++bb) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s = fma(i < DX ? Env::obsE(a, i) : Env::obsF(a, i - DX), Sxy[i * DZ + bb], s);
+        Sz[tix(a, bb)] = s;
+      }
+  }
+  __device__ __forceinline__ double ABel(int r, int i) const { return i < DX ? par[r * DX + i] : par[DX * DX + r * DU + (i - DX)]; }
+  __device__ __forceinline__ void lin_dyn_moments(const double* mu, const double* Sig, double* m3, double* S3, double* Sxy) {
+#pragma unroll
+    for (int r = 0; r < DX; ++r) {
+      double s = par[DX * DX + DX * DU + r];
+#pragma unroll
+      for (int i = 0; i < N; ++i) s = fma(ABel(r, i), mu[i], s);
+      m3[r] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int r = 0; r < DX; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) s = fma(Sig[six(i, k)], ABel(r, k), s);
+        Sxy[i * DX + r] = s;
+      }
+#pragma unroll
+    for (int r = 0; r < DX; ++r)
+#pragma unroll
+      for (int q = 0; q <= r; ++q) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s = fma(ABel(r, i), Sxy[i * DX + q], s);
+        S3[tix(r, q)] = s;
+      }
+  }
+  __device__ __forceinline__ bool lin() const { return Env::LINEAR && p.linearize; }
+
   // ---------------------------------------------------------------------------------- forward cell
-  // I2cCell._forward_msgs_quadrature (i2c.py:350-447).  c: (mu_x0_f, sig_x0_f) in, (mu_x3_f, sig_x3_f) out.
+  // I2cCell._forward_msgs_quadrature (i2c.py:350-447); with p.linearize (linear envs) the same cell with exact
+  // linear moments = _forward_msgs_linearize (i2c.py:244-348; the terminal update then happens in the backward pass).  c: (mu_x0_f, sig_x0_f) in, (mu_x3_f, sig_x3_f) out.
   __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, const double* pr,
                                                Carry<DX>& c, LogAcc& ent_x) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
@@ -398,8 +471,11 @@ struct Worker {
         for (int i = 0; i < TRI(DX); ++i) C[i] = Sxx[i] + c.S[i];
 #pragma unroll
         for (int i = 0; i < DX; ++i) d[i] = c.m[i] - mx[i];
-        double rho;
-        if (!pdf_ratio(C, d, rho)) fail(I2C_FAIL_MVN, it, t);
+        double rho = 1.0;
+        // the quadrature cell always applies the ratio (quirk A.6.3); the linearize cell only for expert cells (:259)
+        if (!lin() || (flags & I2C_CELL_EXPERT)) {
+          if (!pdf_ratio(C, d, rho)) fail(I2C_FAIL_MVN, it, t);
+        }
 #pragma unroll
         for (int i = 0; i < DU * DX; ++i) Kt[i] *= rho;
         // mu_u0_f = mu_u0_m + K (mu_x0_f - mu_x0_m);  sig_u0_f = sig_u0_m - K sig_ux^T + K sig_x0_f K^T
@@ -442,12 +518,17 @@ struct Worker {
 
     // ---- cost observation update (i2c.py:390-404)
     {
-      double mz[DZ], Sz[TRI(DZ)], Dm[N * DZ], Sxy[N * DZ], z[DZ];
-      TrigT ctx;
-      Env::center(mu, ctx);
-      sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
-                             [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
-      cross_cov<N, DZ>(L, Dm, Sxy);
+      double mz[DZ], Sz[TRI(DZ)], Sxy[N * DZ], z[DZ];
+      if (lin()) {
+        lin_obs_moments(mu, Sig, mz, Sz, Sxy);
+      } else {
+        double Dm[N * DZ];
+        TrigT ctx;
+        Env::center(mu, ctx);
+        sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                               [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
+        cross_cov<N, DZ>(L, Dm, Sxy);
+      }
       const double a_cell = cell_alpha(t, flags, alpha);
 #pragma unroll
       for (int a = 0; a < DZ; ++a)
@@ -473,12 +554,17 @@ struct Worker {
     for (int i = 0; i < TRI(N); ++i) L[i] = Sig[i];
     if (!chol_rows<N>(L, invd)) fail(I2C_FAIL_CHOL_FILTERED, it, t);
     {
-      double Dm[N * DX], Sxy[N * DX];
-      TrigT ctx;
-      Env::center(mu, ctx);
-      sigma_transform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
-                             [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Dm);
-      cross_cov<N, DX>(L, Dm, Sxy);
+      double Sxy[N * DX];
+      if (lin()) {
+        lin_dyn_moments(mu, Sig, c.m, c.S, Sxy);
+      } else {
+        double Dm[N * DX];
+        TrigT ctx;
+        Env::center(mu, ctx);
+        sigma_transform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                               [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Dm);
+        cross_cov<N, DX>(L, Dm, Sxy);
+      }
 #pragma unroll
       for (int i = 0; i < TRI(DX); ++i) {
         c.S[i] += p.sig_eta[i];
@@ -498,7 +584,7 @@ struct Worker {
       }
     }
     // ---- terminal cost update on the outgoing message (i2c.py:430-443)
-    if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf) {
+    if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf && !lin()) {
       double mz[DZT], Sz[TRI(DZT)], Dm[DX * DZT], Sxy[DX * DZT];
       TrigT ctx;
       Env::center(c.m, ctx);
@@ -510,7 +596,9 @@ struct Worker {
       for (int a = 0; a < DZT; ++a)
 #pragma unroll
         for (int bb = 0; bb <= a; ++bb) Sz[tix(a, bb)] = fma(a_cell, p.Qfinv[a * DZT + bb], Sz[tix(a, bb)]);
-      if (!condition<DX, DZT>(c.m, c.S, Sz, Sxy, mz, p.z_term)) fail(I2C_FAIL_CHOL_TERMINAL, it, t);
+      double zt[DZT];
+      load_zterm(zt);
+      if (!condition<DX, DZT>(c.m, c.S, Sz, Sxy, mz, zt)) fail(I2C_FAIL_CHOL_TERMINAL, it, t);
 #pragma unroll
       for (int i = 0; i < TRI(DX); ++i) c.L[i] = c.S[i];
       if (!chol_rows<DX>(c.L, c.invd)) fail(I2C_FAIL_CHOL_TERMINAL, it, t);
@@ -625,11 +713,38 @@ struct Worker {
     }
     // marginal cost-feature moments (i2c.py:594-596) -> alpha / cost statistics
     {
-      double mz[DZ], Sz[TRI(DZ)], Dm[N * DZ], z[DZ];
-      TrigT ctx;
-      Env::center(mu, ctx);
-      sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
-                             [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
+      double mz[DZ], Sz[TRI(DZ)], z[DZ];
+      if (lin()) {
+        // mu_z0_m = observe(mu_xu0_m); sig_z0_m = C sig_x0_m C^T + D sig_u0_m D^T (no cross term, i2c.py:538-540)
+#pragma unroll
+        for (int a = 0; a < DZ; ++a) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) s = fma(i < DX ? Env::obsE(a, i) : Env::obsF(a, i - DX), mu[i], s);
+          mz[a] = s;
+        }
+#pragma unroll
+        for (int a = 0; a < DZ; ++a)
+#pragma unroll
+          for (int bb = 0; bb <= a; ++bb) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < DX; ++i)
+#pragma unroll
+              for (int k = 0; k < DX; ++k) s = fma(Env::obsE(a, i) * Env::obsE(bb, k), Sig[six(i, k)], s);
+#pragma unroll
+            for (int i = 0; i < DU; ++i)
+#pragma unroll
+              for (int k = 0; k < DU; ++k) s = fma(Env::obsF(a, i) * Env::obsF(bb, k), Sig[six(DX + i, DX + k)], s);
+            Sz[tix(a, bb)] = s;
+          }
+      } else {
+        double Dm[N * DZ];
+        TrigT ctx;
+        Env::center(mu, ctx);
+        sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                               [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
+      }
       if (aux) {
         double* ab = rec(p.auxb, t, LY::E_AUXB);
 #pragma unroll
@@ -638,7 +753,15 @@ struct Worker {
         for (int i = 0; i < TRI(DZ); ++i) ab[(LY::AB_SIGZ + i) * TILE] = Sz[i];
       }
       double cm, cv;
-      cost_stats<DZ>(p, mz, Sz, p.z_graph, cm, cv);
+      if (lin()) {
+        // calc_cost goes through the graph's cubature transform of the joint posterior (i2c.py:1034-1043), which
+        // is exact for a linear map: full E F Sigma (E F)^T including the x-u cross terms
+        double mzf[DZ], Szf[TRI(DZ)], Sxyf[N * DZ];
+        lin_obs_moments(mu, Sig, mzf, Szf, Sxyf);
+        cost_stats<DZ>(p, mzf, Szf, p.z_graph, cm, cv);
+      } else {
+        cost_stats<DZ>(p, mz, Sz, p.z_graph, cm, cv);
+      }
       st.cost += cm;
       st.cost_var += cv;
       load_z(t, z);
@@ -648,8 +771,54 @@ struct Worker {
 
   // end-of-chain handling of the last cell (i2c.py:546-572): covariance control or plain hand-over, and
   // the terminal cost-feature moments for the alpha update.  c holds (mu_x3_f, sig_x3_f, chol).
-  __device__ __forceinline__ void backward_terminal(int it, int t, double temp, const Carry<DX>& c, double* m3m,
-                                                    double* S3m, double& tr_term) {
+  __device__ __forceinline__ void backward_terminal(int it, int t, double temp, double a_cell, const Carry<DX>& c,
+                                                    double* m3m, double* S3m, double& tr_term) {
+    if constexpr (Env::LINEAR) {
+      if (p.linearize) {
+        // _backward_msgs_linearize, end of chain (i2c.py:450-501); observe_terminal is the identity for the linear envs
+        static_assert(!Env::LINEAR || Env::DZT == Env::DX, "linear envs observe the full state at the end");
+        tr_term = 0.0;
+#pragma unroll
+        for (int i = 0; i < DX; ++i) m3m[i] = c.m[i];
+#pragma unroll
+        for (int i = 0; i < TRI(DX); ++i) S3m[i] = c.S[i];
+        if (p.cov_ctrl) {
+#pragma unroll
+          for (int i = 0; i < DX; ++i) m3m[i] = p.mu_xt[i];
+#pragma unroll
+          for (int i = 0; i < TRI(DX); ++i) S3m[i] = p.sxt[i];
+        } else if (p.has_qf) {
+          double Sz[TRI(DX)], Sxy[DX * DX];
+#pragma unroll
+          for (int i = 0; i < DX; ++i)
+#pragma unroll
+            for (int j = 0; j < DX; ++j) Sxy[i * DX + j] = c.S[six(i, j)];
+#pragma unroll
+          for (int i = 0; i < DX; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) Sz[tix(i, j)] = fma(a_cell, p.Qfinv[i * DX + j], c.S[tix(i, j)]);
+          double zt[DZT];
+          load_zterm(zt);
+          if (!condition<DX, DX>(m3m, S3m, Sz, Sxy, c.m, zt)) fail(I2C_FAIL_CHOL_TERMINAL, it, t);
+        }
+        if (p.has_qf) {
+          double Sz3[TRI(DX)];
+#pragma unroll
+          for (int i = 0; i < DX; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) Sz3[tix(i, j)] = fma(a_cell, p.Qfinv[i * DX + j], S3m[tix(i, j)]);
+          double* tm = p.term + ((size_t)tile * LY::E_TERM) * TILE + lane;
+#pragma unroll
+          for (int i = 0; i < DX; ++i) tm[(LY::TM_MU + i) * TILE] = m3m[i];
+#pragma unroll
+          for (int i = 0; i < TRI(DX); ++i) tm[(LY::TM_SIG + i) * TILE] = Sz3[i];
+          double zt[DZT];
+          load_zterm(zt);
+          tr_term = alpha_trace<DX>(p.Qf, 0, m3m, Sz3, zt);
+        }
+        return;
+      }
+    }
     double Lm[TRI(DX)], invm[DX];
     if (p.cov_ctrl) {
       // sig_x3_m = S - S (Sig_T + S)^{-1} S,  mu_x3_m = sig_x3_m (S^{-1} mu_x3_f + Sig_T^{-1} mu_T),  S = temp * sig_x3_f
@@ -721,7 +890,9 @@ struct Worker {
       for (int i = 0; i < DZT; ++i) tm[(LY::TM_MU + i) * TILE] = mz[i];
 #pragma unroll
       for (int i = 0; i < TRI(DZT); ++i) tm[(LY::TM_SIG + i) * TILE] = Sz[i];
-      tr_term = alpha_trace<DZT>(p.Qf, 0, mz, Sz, p.z_term);
+      double zt[DZT];
+      load_zterm(zt);
+      tr_term = alpha_trace<DZT>(p.Qf, 0, mz, Sz, zt);
     }
   }
 
@@ -843,6 +1014,316 @@ struct Worker {
     }
   }
 
+  // ---------------------------------------------------------------------------------- Riccati messages
+  // I2cCell._backward_ricatti_msgs / I2cGraph._backward_ricatti_msgs (i2c.py:612-678, 888-893): backward
+  // information-form recursion that reproduces the LQR value function; overwrites K, k, sigK of every cell.
+  // Forward-pass quantities are re-derived from the stored records (prior joint = auxf, filtered, posterior).
+  __device__ void riccati_sweep(double alpha) {
+    if constexpr (Env::LINEAR) {
+      constexpr int X2 = DX * DX;
+      double Lb[X2], nb[DX];
+      double A[X2], Bm[DX * DU], av[DX], Se[X2];
+#pragma unroll
+      for (int i = 0; i < X2; ++i) A[i] = par[i];
+#pragma unroll
+      for (int i = 0; i < DX * DU; ++i) Bm[i] = par[X2 + i];
+#pragma unroll
+      for (int i = 0; i < DX; ++i) av[i] = par[X2 + DX * DU + i];
+#pragma unroll
+      for (int i = 0; i < DX; ++i)
+#pragma unroll
+        for (int j = 0; j < DX; ++j) Se[i * DX + j] = p.sig_eta[six(i, j)];
+      for (int t = p.T - 1; t >= 0; --t) {
+        const double* af = rec(p.auxf, t, LY::E_AUXF);
+        const double* fr = rec(p.filt, t, LY::E_FILT);
+        double* po = rec(latest, t, LY::E_POST);
+        const int flags = p.cell_flags[slot(t)];
+        const double a_cell = cell_alpha(t, flags, alpha);
+        double mu0[N], S0[TRI(N)], S1[TRI(N)], mu1[N], z[DZ];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          mu0[i] = af[(LY::AF_MU0 + i) * TILE];
+          mu1[i] = fr[(LY::F_MU1 + i) * TILE];
+        }
+#pragma unroll
+        for (int i = 0; i < TRI(N); ++i) {
+          S0[i] = af[(LY::AF_SIG0 + i) * TILE];
+          S1[i] = fr[(LY::F_SIG1 + i) * TILE];
+        }
+        load_z(t, z);
+        if (t == p.T - 1) {
+          // end of chain: nu_x3_b = sig_x3_m^{-1} mu_x3_m - nu_x3_f;  lambda_x3_b = sig_x3_m^{-1} - lambda_x3_f
+          const double* ab = rec(p.auxb, t, LY::E_AUXB);
+          double Sm[X2], Sf[X2], mm_[DX], mf[DX];
+#pragma unroll
+          for (int i = 0; i < DX; ++i) {
+            mm_[i] = ab[(LY::AB_MU3M + i) * TILE];
+            mf[i] = fr[(LY::F_MU3 + i) * TILE];
+#pragma unroll
+            for (int j = 0; j < DX; ++j) {
+              Sm[i * DX + j] = ab[(LY::AB_SIG3M + six(i, j)) * TILE];
+              Sf[i * DX + j] = fr[(LY::F_SIG3 + six(i, j)) * TILE];
+            }
+          }
+          inv_gj<DX>(Sm);
+          inv_gj<DX>(Sf);
+#pragma unroll
+          for (int i = 0; i < DX; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < DX; ++j) {
+              s = fma(Sm[i * DX + j], mm_[j], s);
+              s = fma(-Sf[i * DX + j], mf[j], s);
+              Lb[i * DX + j] = Sm[i * DX + j] - Sf[i * DX + j];
+            }
+            nb[i] = s;
+          }
+        }
+        double* rr = rec(p.ric, t, LY::E_RIC);
+#pragma unroll
+        for (int i = 0; i < X2; ++i) rr[(LY::R_L3 + i) * TILE] = Lb[i];
+#pragma unroll
+        for (int i = 0; i < DX; ++i) rr[(LY::R_N3 + i) * TILE] = nb[i];
+        // lambda_z1_f = (sig_xi + F sig_u0_f F^T)^{-1};  nu_z1_f = E^T lambda_z1 (z - F mu_u0_f)
+        double Lz1[DZ * DZ], Lz2[DZ * DZ];
+#pragma unroll
+        for (int a = 0; a < DZ; ++a)
+#pragma unroll
+          for (int bb = 0; bb < DZ; ++bb) {
+            double s1 = a_cell * p.QRinv[a * DZ + bb], s2 = s1;
+#pragma unroll
+            for (int i = 0; i < DU; ++i)
+#pragma unroll
+              for (int k = 0; k < DU; ++k) s1 = fma(Env::obsF(a, i) * Env::obsF(bb, k), S0[six(DX + i, DX + k)], s1);
+#pragma unroll
+            for (int i = 0; i < DX; ++i)
+#pragma unroll
+              for (int k = 0; k < DX; ++k) s2 = fma(Env::obsE(a, i) * Env::obsE(bb, k), S0[six(i, k)], s2);
+            Lz1[a * DZ + bb] = s1;
+            Lz2[a * DZ + bb] = s2;
+          }
+        inv_gj<DZ>(Lz1);
+        inv_gj<DZ>(Lz2);
+        double r1[DZ], r2[DZ], nz1[DX], Rug[DU], Q[X2];
+#pragma unroll
+        for (int a = 0; a < DZ; ++a) {
+          double s1 = z[a], s2 = z[a];
+#pragma unroll
+          for (int i = 0; i < DU; ++i) s1 = fma(-Env::obsF(a, i), mu0[DX + i], s1);
+#pragma unroll
+          for (int i = 0; i < DX; ++i) s2 = fma(-Env::obsE(a, i), mu0[i], s2);
+          r1[a] = s1;
+          r2[a] = s2;
+        }
+#pragma unroll
+        for (int i = 0; i < DX; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DZ; ++a)
+#pragma unroll
+            for (int bb = 0; bb < DZ; ++bb) s = fma(Env::obsE(a, i) * Lz1[a * DZ + bb], r1[bb], s);
+          nz1[i] = s;
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double q = 0.0;
+#pragma unroll
+            for (int a = 0; a < DZ; ++a)
+#pragma unroll
+              for (int bb = 0; bb < DZ; ++bb) q = fma(Env::obsE(a, i) * Lz1[a * DZ + bb], Env::obsE(bb, j), q);
+            Q[i * DX + j] = q;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < DU; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DZ; ++a)
+#pragma unroll
+            for (int bb = 0; bb < DZ; ++bb) s = fma(Env::obsF(a, i) * Lz2[a * DZ + bb], r2[bb], s);
+          Rug[i] = s;
+        }
+        // nu_u_0 = sig_u0_f^{-1} mu_u0_f
+        double Su0[DU * DU], nu_u0[DU];
+#pragma unroll
+        for (int i = 0; i < DU; ++i)
+#pragma unroll
+          for (int k = 0; k < DU; ++k) Su0[i * DU + k] = S0[six(DX + i, DX + k)];
+        inv_gj<DU>(Su0);
+#pragma unroll
+        for (int i = 0; i < DU; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < DU; ++k) s = fma(Su0[i * DU + k], mu0[DX + k], s);
+          nu_u0[i] = s;
+        }
+        // sig_u2_f = B sig_u1_f B^T; sig_x2_f = A sig_x1_f A^T + sig_eta; lambda_x2_f = inv(sig_x2_f)
+        double Su2[X2], Sx2[X2], Lx2[X2], Sx1[X2], T1[X2];
+#pragma unroll
+        for (int i = 0; i < DX; ++i)
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < DU; ++k)
+#pragma unroll
+              for (int l = 0; l < DU; ++l) s = fma(Bm[i * DU + k] * S1[six(DX + k, DX + l)], Bm[j * DU + l], s);
+            Su2[i * DX + j] = s;
+            Sx1[i * DX + j] = S1[six(i, j)];
+          }
+        mm<DX, DX, DX>(A, Sx1, T1);
+#pragma unroll
+        for (int i = 0; i < DX; ++i)
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double s = Se[i * DX + j];
+#pragma unroll
+            for (int k = 0; k < DX; ++k) s = fma(T1[i * DX + k], A[j * DX + k], s);
+            Sx2[i * DX + j] = s;
+            Lx2[i * DX + j] = s;
+          }
+        inv_gj<DX>(Lx2);
+        // gamma = lambda_x2 inv(lambda_x2 + Lb)
+        double G1[X2], gamma[X2];
+#pragma unroll
+        for (int i = 0; i < X2; ++i) G1[i] = Lx2[i] + Lb[i];
+        inv_gj<DX>(G1);
+        mm<DX, DX, DX>(Lx2, G1, gamma);
+        // M = inv(sig_eta + sig_u2) + Lb
+        double M[X2], Minv[X2];
+#pragma unroll
+        for (int i = 0; i < X2; ++i) M[i] = Se[i] + Su2[i];
+        inv_gj<DX>(M);
+#pragma unroll
+        for (int i = 0; i < X2; ++i) {
+          M[i] += Lb[i];
+          Minv[i] = M[i];
+        }
+        inv_gj<DX>(Minv);
+        // lambda_x0_b = Q + A^T Lb A - A^T Lb M^{-1} Lb A;   AILM = A^T (I - Lb M^{-1})
+        double LbA[X2], LM[X2], ILM[X2], T2[X2], L0[X2], AILM[X2];
+        mm<DX, DX, DX>(Lb, A, LbA);
+        mm<DX, DX, DX>(Lb, Minv, LM);
+#pragma unroll
+        for (int i = 0; i < X2; ++i) ILM[i] = (((i / DX) == (i % DX)) ? 1.0 : 0.0) - LM[i];
+        mm<DX, DX, DX>(ILM, LbA, T2);  // (I - Lb M^-1) Lb A
+#pragma unroll
+        for (int i = 0; i < DX; ++i)
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double s = Q[i * DX + j], w = 0.0;
+#pragma unroll
+            for (int k = 0; k < DX; ++k) {
+              s = fma(A[k * DX + i], T2[k * DX + j], s);
+              w = fma(A[k * DX + i], ILM[k * DX + j], w);
+            }
+            L0[i * DX + j] = s;
+            AILM[i * DX + j] = w;
+          }
+        // nu_x0_b = nu_z1_f + AILM (nu_x3_b - Lb a - Lb B mu_u1)
+        double Bu[DX], v[DX], n0[DX];
+#pragma unroll
+        for (int i = 0; i < DX; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < DU; ++k) s = fma(Bm[i * DU + k], mu1[DX + k], s);
+          Bu[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < DX; ++i) {
+          double s = nb[i];
+#pragma unroll
+          for (int k = 0; k < DX; ++k) s = fma(-Lb[i * DX + k], av[k] + Bu[k], s);
+          v[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < DX; ++i) {
+          double s = nz1[i];
+#pragma unroll
+          for (int k = 0; k < DX; ++k) s = fma(AILM[i * DX + k], v[k], s);
+          n0[i] = s;
+        }
+        // psi = gamma Lb (sig_x2 (lambda_x2 + inv(inv(Lb) + sig_u2)));  nu_x2_b = lambda_x2_b inv(Lb) nu_x3_b - B mu_u1
+        double S3b[X2], Lx2b[X2], T3[X2], T4[X2], gL[X2], psi[X2], nx2b[DX];
+#pragma unroll
+        for (int i = 0; i < X2; ++i) S3b[i] = Lb[i];
+        inv_gj<DX>(S3b);
+#pragma unroll
+        for (int i = 0; i < X2; ++i) Lx2b[i] = S3b[i] + Su2[i];
+        inv_gj<DX>(Lx2b);
+#pragma unroll
+        for (int i = 0; i < X2; ++i) T3[i] = Lx2[i] + Lx2b[i];
+        mm<DX, DX, DX>(Sx2, T3, T4);
+        mm<DX, DX, DX>(gamma, Lb, gL);
+        mm<DX, DX, DX>(gL, T4, psi);
+        mm<DX, DX, DX>(Lx2b, S3b, T3);
+#pragma unroll
+        for (int i = 0; i < DX; ++i) {
+          double s = -Bu[i];
+#pragma unroll
+          for (int k = 0; k < DX; ++k) s = fma(T3[i * DX + k], nb[k], s);
+          nx2b[i] = s;
+        }
+        // K = -sig_u B^T psi A;  k = sig_u (nu_u_0 + Rug + B^T (gamma nu_x3_b + (I - gamma) nu_x2_b - psi a))
+        double w2[DX], Su[DU * DU], BtPsiA[DU * DX], PA[X2];
+#pragma unroll
+        for (int i = 0; i < DX; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < DX; ++k) {
+            s = fma(gamma[i * DX + k], nb[k], s);
+            s = fma((((i == k) ? 1.0 : 0.0) - gamma[i * DX + k]), nx2b[k], s);
+            s = fma(-psi[i * DX + k], av[k], s);
+          }
+          w2[i] = s;
+        }
+        mm<DX, DX, DX>(psi, A, PA);
+#pragma unroll
+        for (int r = 0; r < DU; ++r) {
+#pragma unroll
+          for (int q = 0; q < DU; ++q) Su[r * DU + q] = po[(LY::P_SIG + six(DX + r, DX + q)) * TILE];
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < DX; ++k) s = fma(Bm[k * DU + r], PA[k * DX + j], s);
+            BtPsiA[r * DX + j] = s;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < DU; ++r) {
+          double kk = 0.0;
+#pragma unroll
+          for (int q = 0; q < DU; ++q) {
+            double inner = nu_u0[q] + Rug[q];
+#pragma unroll
+            for (int k = 0; k < DX; ++k) inner = fma(Bm[k * DU + q], w2[k], inner);
+            kk = fma(Su[r * DU + q], inner, kk);
+          }
+          po[(LY::P_KK + r) * TILE] = kk;
+#pragma unroll
+          for (int j = 0; j < DX; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < DU; ++q) s = fma(-Su[r * DU + q], BtPsiA[q * DX + j], s);
+            po[(LY::P_K + r * DX + j) * TILE] = s;
+          }
+#pragma unroll
+          for (int q = 0; q <= r; ++q) po[(LY::P_SIGK + tix(r, q)) * TILE] = Su[r * DU + q];
+        }
+#pragma unroll
+        for (int i = 0; i < X2; ++i) {
+          rr[(LY::R_L0 + i) * TILE] = L0[i];
+          Lb[i] = L0[i];
+        }
+#pragma unroll
+        for (int i = 0; i < DX; ++i) {
+          rr[(LY::R_N0 + i) * TILE] = n0[i];
+          nb[i] = n0[i];
+        }
+      }
+    }
+  }
+
   __device__ __forceinline__ bool load_x0(Carry<DX>& c) {
     const double* q = p.x0 + ((size_t)tile * DX) * TILE + lane;
 #pragma unroll
@@ -906,7 +1387,7 @@ struct Worker {
           chol_rows<DX>(c.L, c.invd);
         }
         double m3m[DX], S3m[TRI(DX)];
-        backward_terminal(it, T - 1, temp, c, m3m, S3m, tr_term);
+        backward_terminal(it, T - 1, temp, cell_alpha(T - 1, p.cell_flags[slot(T - 1)], alpha), c, m3m, S3m, tr_term);
         if (p.cov_ctrl) temp += p.dtemp;
         __threadfence();
         stage_record<LY::E_FILT>(stage + ((T - 1) & 1) * (LY::E_STAGE * TILE), rec(p.filt, T - 1, LY::E_FILT));
@@ -967,6 +1448,7 @@ struct Worker {
           metric(I2C_M_KL_TERM, it, 0.5 * (p.sxt_logdet - 2.0 * ld1 + tr + dist - (double)DX));
         }
       }
+      if (p.phases & I2C_PH_RICCATI) riccati_sweep(alpha);
       if (p.phases & I2C_PH_MSTEP) {
         metric(I2C_M_COST_M, it, st.cost);
         metric(I2C_M_COST_M_VAR, it, st.cost_var);

@@ -24,12 +24,14 @@ struct KParams {
   double* auxb;   // [T][ntiles][E_AUXB][32]  optional
   double* pf;     // [T][ntiles][E_PF][32]    optional (propagate messages)
   double* term;   // [ntiles][E_TERM][32]     terminal cost-feature moments of the last cell
+  double* ric;    // [T][ntiles][E_RIC][32]   Riccati messages (optional): lambda_x3_b, nu_x3_b, lambda_x0_b, nu_x0_b
   // ---- per-problem
   double* x0;      // [ntiles][DX][32]
   double* sig_x0;  // [ntiles][TRI(DX)][32]
   double* alpha;   // [Bpad]
   double* alpha_cell;   // [T][Bpad]   (cells flagged OWN_ALPHA)
   const double* z_cell; // [T][DZ] or [T][ntiles][DZ][32]
+  const double* z_term_pp;  // [ntiles][DZT][32] per-problem terminal targets (z_per_problem), else NULL
   const double* envpar; // [ntiles][NP][32]
   int32_t* cell_flags;  // [T]
   const int32_t* cell_index;  // [T]
@@ -41,6 +43,7 @@ struct KParams {
   int32_t n_iter, phases, tau, max_iters;
   int32_t cell_head;  // ring offset: logical cell t lives in slot (t + cell_head) % T (O(1) MPC horizon shift)
   int32_t z_per_problem, qr_diag, has_qf, cov_ctrl;
+  int32_t linearize;  // Linearize inference (linear envs only): exact moments instead of sigma points
   double alpha_tol, temp0, dtemp;
   double sf_n, w0_n, wi_n;  // cubature rule in dim n = dx+du (exp_types.py:36-49)
   double sf_x, w0_x, wi_x;  // cubature rule in dim dx
@@ -65,6 +68,7 @@ struct RecDims {
   __host__ __device__ constexpr int e_auxb() const { return dz + tri(dz) + dx + tri(dx); }
   __host__ __device__ constexpr int e_pf() const { return n + tri(n) + dz + tri(dz) + dx + tri(dx); }
   __host__ __device__ constexpr int e_term() const { return dzt + tri(dzt); }
+  __host__ __device__ constexpr int e_ric() const { return 2 * (dx * dx + dx); }
 };
 
 // launchers implemented in i2c_kernels.cu

@@ -62,6 +62,64 @@ __device__ __forceinline__ void bwd_subst(const double* L, const double* invd, d
   }
 }
 
+// In-place inverse of a small dense N x N matrix (row-major, not necessarily symmetric) by Gauss-Jordan
+// elimination with partial pivoting (np.linalg.inv / gesv in the reference's Linearize + Riccati code).
+template <int N>
+__device__ __forceinline__ void inv_gj(double* A) {
+  double I[N * N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) I[i] = ((i / N) == (i % N)) ? 1.0 : 0.0;
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    // pivot search (select, no dynamic indexing: swap rows conditionally)
+#pragma unroll
+    for (int r = c + 1; r < N; ++r) {
+      const bool sw = fabs(A[r * N + c]) > fabs(A[c * N + c]);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        double t0 = A[c * N + k], t1 = A[r * N + k];
+        A[c * N + k] = sw ? t1 : t0;
+        A[r * N + k] = sw ? t0 : t1;
+        double u0 = I[c * N + k], u1 = I[r * N + k];
+        I[c * N + k] = sw ? u1 : u0;
+        I[r * N + k] = sw ? u0 : u1;
+      }
+    }
+    const double ip = 1.0 / A[c * N + c];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      A[c * N + k] *= ip;
+      I[c * N + k] *= ip;
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      if (r == c) continue;
+      const double f = A[r * N + c];
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        A[r * N + k] = fma(-f, A[c * N + k], A[r * N + k]);
+        I[r * N + k] = fma(-f, I[c * N + k], I[r * N + k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) A[i] = I[i];
+}
+
+// C = A B for small row-major matrices (R x K)(K x Cc)
+template <int R, int K, int Cc>
+__device__ __forceinline__ void mm(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < Cc; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) s = fma(A[i * K + k], B[k * Cc + j], s);
+      C[i * Cc + j] = s;
+    }
+}
+
 // Running log-determinant accumulator that avoids one fp64 log() per pivot: keeps a renormalised
 // mantissa product and an integer exponent; value() = log(product).
 struct LogAcc {

@@ -24,7 +24,8 @@ ENV_IDS = {
 }
 # enum i2c_phase
 PH_FORWARD, PH_BACKWARD, PH_PROPAGATE, PH_MSTEP, PH_UPDATE_PRIORS = 1, 2, 4, 8, 16
-PH_CALIBRATE, PH_ONLY_DECREASE, PH_STORE_AUX = 32, 64, 128
+PH_CALIBRATE, PH_ONLY_DECREASE, PH_STORE_AUX, PH_RICCATI = 32, 64, 128, 256
+INF_CUBATURE, INF_LINEARIZE = 0, 1
 PH_LEARN = PH_FORWARD | PH_BACKWARD | PH_MSTEP | PH_UPDATE_PRIORS
 # enum i2c_cell_flag
 CELL_INDEPENDENT, CELL_TERMINAL, CELL_EXPERT, CELL_OWN_ALPHA = 1, 2, 4, 8
@@ -33,7 +34,8 @@ FIELDS = {name: i for i, name in enumerate([
     "mu_xu0_m", "sig_xu0_m", "K", "k", "sigK", "prior_mu", "prior_sig", "prior_K",
     "mu_xu1_f", "sig_xu1_f", "mu_x3_f", "sig_x3_f", "J_dyn",
     "mu_xu0_f", "sig_xu0_f", "mu_z0_f", "sig_z0_f", "mu_z0_m", "sig_z0_m", "mu_x3_m", "sig_x3_m",
-    "mu_xu0_pf", "sig_xu0_pf", "mu_z0_pf", "sig_z0_pf", "mu_x3_pf", "sig_x3_pf", "mu_z3_m", "sig_z3_m"])}
+    "mu_xu0_pf", "sig_xu0_pf", "mu_z0_pf", "sig_z0_pf", "mu_x3_pf", "sig_x3_pf", "mu_z3_m", "sig_z3_m",
+    "lambda_x3_b", "nu_x3_b", "lambda_x0_b", "nu_x0_b"])}
 # enum i2c_metric
 METRICS = {name: i for i, name in enumerate([
     "alpha", "alpha_desired", "alpha_pf", "cost_m", "cost_m_var", "cost_pf", "cost_pf_var", "cost_pf_min",

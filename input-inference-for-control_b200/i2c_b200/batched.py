@@ -28,7 +28,7 @@ class BatchedI2c:
     def __init__(self, env, n_problems, horizon, Q, R, Qf, alpha, alpha_update_tol, mu_u, sig_u, mu_x_terminal=None,
                  sig_x_terminal=None, x0=None, sig_x0=None, sig_eta=None, z=None, z_term=None, env_par=None,
                  quadrature=(1.0, 0.0, 0.0), device=0, enable_aux=False, max_iters=256, dtemp=1.0, stream=None,
-                 z_per_problem=False, torch_workspace=True):
+                 z_per_problem=False, torch_workspace=True, inference="cubature"):
         self.lib = capi.lib()
         self.env = _envs.make(env) if isinstance(env, str) else env
         self.env_id = capi.ENV_IDS[self.env.name]
@@ -40,7 +40,9 @@ class BatchedI2c:
         self.device = device
         self.enable_aux = bool(enable_aux)
         self.max_iters = int(max_iters)
-        cfg = capi.Config(capi.ABI_VERSION, self.env_id, 0, B, T, self.max_iters, device, int(bool(z_per_problem)),
+        self.inference = inference
+        inf_id = {"cubature": capi.INF_CUBATURE, "linearize": capi.INF_LINEARIZE}[inference]
+        cfg = capi.Config(capi.ABI_VERSION, self.env_id, inf_id, B, T, self.max_iters, device, int(bool(z_per_problem)),
                           int(self.enable_aux), *map(float, quadrature))
         self._cfg = cfg
         self._ws = None
@@ -79,7 +81,8 @@ class BatchedI2c:
             z = np.broadcast_to(self.z_graph, (T, dz))
         self.z_per_problem = bool(z_per_problem)
         self.z = capi.f64(z, (B, T, dz) if z_per_problem else (T, dz))
-        self.z_term = capi.f64(np.asarray(e.zg_term if z_term is None else z_term, float).reshape(-1), (dzt,))
+        zt = np.asarray(e.zg_term if z_term is None else z_term, float)
+        self.z_term = capi.f64(np.broadcast_to(zt.reshape((-1, dzt)), (B, dzt)).copy()) if z_per_problem else capi.f64(zt.reshape(-1), (dzt,))
         self.alpha0 = capi.f64(np.broadcast_to(np.asarray(alpha, float), (B,)).copy())
         self.mu_x_terminal = None if mu_x_terminal is None else capi.f64(np.asarray(mu_x_terminal, float).reshape(-1), (dx,))
         self.sig_x_terminal = None if sig_x_terminal is None else capi.f64(sig_x_terminal, (dx, dx))
@@ -177,6 +180,10 @@ class BatchedI2c:
     def propagate(self):
         return self.run(1, capi.PH_PROPAGATE, False)
 
+    def backward_ricatti(self):
+        """I2cGraph._backward_ricatti_msgs (i2c.py:888-893): Linearize inference on linear envs, enable_aux=True."""
+        return self.run(1, capi.PH_RICCATI, False)
+
     def calibrate_alpha(self, only_decrease=False):
         """I2cGraph.calibrate_alpha (i2c.py:895-911)."""
         return self.run(1, capi.PH_PROPAGATE | capi.PH_CALIBRATE | (capi.PH_ONLY_DECREASE if only_decrease else 0))
@@ -211,7 +218,7 @@ class BatchedI2c:
             t0, t1 = 0, 1
         out = np.empty((self.B, t1 - t0, r.value, c.value))
         capi.check(self.lib.i2c_get_field(self._h, fid, t0, t1, capi.ptr(out)))
-        is_vec = c.value == 1 and not name.startswith(("sig", "K", "J"))
+        is_vec = c.value == 1 and not name.startswith(("sig", "K", "J", "lambda"))
         if name == "K" or name == "prior_K" or name == "J_dyn":
             is_vec = False
         return out[..., 0] if is_vec else out
