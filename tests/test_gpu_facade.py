@@ -1,0 +1,166 @@
+"""The drop-in mirror (`from i2c.i2c import I2cGraph` ...) driven the way the reference's scripts drive the reference
+(scripts/i2c_run.py:29-131, lqr_compare.py:120-176, nonlinear_covariance_control.py:81-115,
+mpc_state_est/mpc_quad.py:538-652), checked against goldens produced by the unmodified reference."""
+import copy
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import GAINS, golden, relerr
+from test_gpu_parity import i2c_b200  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mirror(i2c_b200):
+    from i2c.exp_types import CubatureQuadrature, GaussianI2c, Linearize
+    from i2c.i2c import I2cGraph
+    from i2c.inference.quadrature import QuadratureInference
+    from i2c.model import make_env_model, QuadrotorKnown
+    from i2c.policy.linear import ExpertTimeIndexedLinearGaussianPolicy, TimeIndexedLinearGaussianPolicy
+    from i2c.policy.mpc import PartiallyObservedMpcPolicy
+    from i2c.utils import finite_horizon_lqr
+    import types
+
+    return types.SimpleNamespace(**locals())
+
+
+def test_i2c_run_inference_loop(mirror):
+    """scripts/i2c_run.py:29-47,89-98 with experiments/pendulum_known_quad.py (seed 0)."""
+    g = golden("pendulum_known_quad_seed0")
+    model = mirror.make_env_model("PendulumKnown", None)
+    inf = mirror.GaussianI2c(inference=mirror.CubatureQuadrature(1, 0, 0), Q=g["Q"], R=g["R"], Qf=g["Qf"], alpha=100,
+                             alpha_update_tol=0.0, mu_u=g["mu_u"], sig_u=g["sig_u"], mu_x_term=None, sig_x_term=None)
+    i2c = mirror.I2cGraph(model, 100, inf.Q, inf.R, inf.Qf, inf.alpha, inf.alpha_update_tol, inf.mu_u, inf.sig_u,
+                          inf.mu_x_term, inf.sig_x_term, inf.inference, res_dir=None)
+    policy_linear = mirror.TimeIndexedLinearGaussianPolicy(0.0 * np.eye(1), 100, i2c.sys.dim_u, i2c.sys.dim_x)
+    policy = mirror.ExpertTimeIndexedLinearGaussianPolicy(0.0 * np.eye(1), 100, i2c.sys.dim_u, i2c.sys.dim_x, soft=False)
+    i2c.reset_metrics()
+    for i in range(200):
+        i2c.learn_msgs()
+        if i < 3:
+            c = i2c.cells[10]
+            for a in ["mu_x0_f", "sig_x0_f", "mu_xu1_f", "sig_xu1_f", "mu_x3_f", "sig_x3_f", "J_dyn", "mu_x3_m", "sig_x3_m",
+                      "mu_xu0_m", "sig_xu0_m", "mu_z0_m", "sig_z0_m", "K", "k", "sigK", "mu_xu0_f"]:
+                mine = np.asarray(getattr(c, a))
+                ref = g[f"it{i + 1}/{a}"][10]
+                assert relerr(mine.reshape(ref.shape), ref, 1e-6 if a in GAINS else 0.0) < (1e-7 if a in GAINS else 1e-9), a
+        policy_linear.write(*i2c.get_local_linear_policy())
+        policy.write(*i2c.get_local_expert_linear_policy())
+    assert i2c.alphas[0] == 100 and len(i2c.alphas) == 201 and len(i2c.costs_m) == 200
+    # golden schedule quoted in SURVEY.md section 6
+    assert abs(i2c.alphas[1] - 99.23063222598958) < 1e-9 and abs(i2c.alphas[2] - 93.70997137355181) < 1e-8
+    assert relerr(np.array(i2c.alphas), g["alphas"]) < 1e-8
+    assert relerr(np.array(i2c.costs_m), g["costs_m"]) < 1e-8
+    assert abs(i2c.costs_m[0] - 39606.560956855086) < 1e-6
+    assert relerr(policy_linear.K, g["final/K"]) < 1e-6
+    assert relerr(policy_linear.k, g["final/k"]) < 1e-6
+    u = policy_linear(0, np.asarray(model.x0, float))
+    assert u.shape == (1, 1)
+    z_est, z_term_est = i2c.get_marginal_observed_trajectory()
+    assert z_est.shape == (100, 4) and z_term_est.shape == (3, 1)
+    assert i2c.get_marginal_trajectory().shape == (100, 3)
+    # deepcopy / pickle round trip keeps the device state (policy/mpc.py:24, i2c.py:1392-1401)
+    clone = copy.deepcopy(i2c)
+    blob = pickle.dumps(i2c)
+    i2c.learn_msgs()
+    clone.learn_msgs()
+    again = pickle.loads(blob)
+    again.learn_msgs()
+    for other in (clone, again):
+        assert other.alphas[-1] == i2c.alphas[-1]
+        assert np.array_equal(other.get_local_linear_policy()[0], i2c.get_local_linear_policy()[0])
+
+
+def test_lqr_compare_flow(mirror):
+    """scripts/lqr_compare.py:120-176."""
+    g = golden("lqr_linearize")
+    model = mirror.make_env_model("LinearKnown", None)
+    model.xag = 10 * np.ones((2, 1))
+    model.zg_term = 10 * np.ones((2, 1))
+    model.a = model.xag - model.A @ model.xag
+    H = int(g["H"])
+    x_lqr, u_lqr, K_lqr, k_lqr, cost_lqr, P, p = mirror.finite_horizon_lqr(
+        H, model.A, model.a[:, 0], model.B, g["Q"], g["R"], model.x0[:, 0], model.xag[:, 0], np.zeros((1,)), 2, 1)
+    assert relerr(K_lqr, g["K_lqr"]) < 1e-14 and relerr(k_lqr, g["k_lqr"]) < 1e-13 and relerr(P, g["P"]) < 1e-14
+    i2c = mirror.I2cGraph(sys=model, horizon=H, Q=g["Q"], R=g["R"], Qf=g["Qf"], alpha=1e-5, alpha_update_tol=0.0,
+                          mu_u=np.zeros((H, 1)), sig_u=1e2 * np.eye(1), mu_x_terminal=None, sig_x_terminal=None,
+                          inference=mirror.Linearize(), res_dir=None)
+    i2c.use_expert_controller = False
+    for c in i2c.cells:
+        c.state_action_independence = True
+    i2c._forward_backward_msgs()
+    K, k, _ = i2c.get_local_linear_policy()
+    assert np.max(np.abs(K - K_lqr)) < 1e-5 * np.max(np.abs(K_lqr))
+    assert np.max(np.abs(k - k_lqr)) < 1e-4 * np.max(np.abs(k_lqr))
+    x, u = i2c.get_state_and_action()
+    assert np.max(np.abs(x[:, :, 0] - x_lqr)) < 1e-5 and np.max(np.abs(u[:, :, 0] - u_lqr)) < 1e-4
+    i2c._backward_ricatti_msgs()
+    lam = np.asarray([c.lambda_x3_b for c in i2c.cells]) * i2c.alpha
+    assert relerr(lam, P) < 1e-3
+
+
+def test_nonlinear_covariance_control_flow(mirror):
+    """scripts/nonlinear_covariance_control.py:81-115 with experiments/pendulum_known_act_reg_quad.py."""
+    g = golden("pendulum_actreg_covctrl_T100")
+    model = mirror.make_env_model("PendulumKnownActReg", None)
+    i2c = mirror.I2cGraph(sys=model, horizon=100, Q=None, R=g["R"], Qf=None, alpha=300.0, alpha_update_tol=1.0,
+                          mu_u=g["mu_u"], sig_u=g["sig_u"], mu_x_terminal=g["mu_x_term"], sig_x_terminal=g["sig_x_term"],
+                          inference=mirror.CubatureQuadrature(1, 0, 0), res_dir=None)
+    for c in i2c.cells:
+        c.use_expert_controller = False
+    i2c._propagate = True
+    i2c.propagate()
+    for i in range(15):
+        i2c.learn_msgs()
+    c = i2c.cells[-1]
+    assert c.mu_x3_m.shape == (2, 1) and c.sig_x3_pf.shape == (2, 2)
+    assert relerr(np.array(i2c.kl_terms), g["kl_terms"]) < 1e-5
+    assert relerr(np.array(i2c.costs_pf), g["costs_pf"]) < 1e-6
+    assert relerr(np.array(i2c.alphas), g["alphas"]) < 1e-12  # tol = 1.0: alpha frozen, exact
+    K, k, s = i2c.get_local_linear_policy()
+    assert relerr(K, g["final/K"], 1e-6) < 1e-5
+
+
+def test_quadrature_inference_mirror(mirror):
+    g = golden("quadrature_kat")
+    model = mirror.make_env_model("CartpoleKnown", None)
+    q = mirror.QuadratureInference(mirror.CubatureQuadrature(1, 0, 0), model.dim_xu)
+    m, S = q.forward(model.observe, g["CartpoleKnown/0/m_in"][:, None], g["CartpoleKnown/0/S_in"])
+    assert m.shape == (6, 1) and relerr(m[:, 0], g["CartpoleKnown/0/obs_m"]) < 1e-13
+    assert relerr(S, g["CartpoleKnown/0/obs_S"]) < 1e-11 and relerr(q.sig_xy, g["CartpoleKnown/0/obs_Sxy"]) < 1e-11
+    m, S, Sn = q.forward_gaussian(model.forward, g["CartpoleKnown/0/m_in"][:, None], g["CartpoleKnown/0/S_in"])
+    assert relerr(m[:, 0], g["CartpoleKnown/0/dyn_m"]) < 1e-13 and relerr(Sn, g["CartpoleKnown/0/dyn_Sn"]) < 1e-15
+    with pytest.raises(NotImplementedError):  # arbitrary callables cannot run in-kernel: no CPU fallback
+        q.forward(lambda x: x, np.zeros((5, 1)), np.eye(5))
+    with pytest.raises(np.linalg.LinAlgError):
+        q.forward(model.observe, np.zeros((5, 1)), -np.eye(5))
+
+
+@pytest.mark.parametrize("mode", ["ff_low", "fb_high"])
+def test_mpc_quad_flow(mirror, mode):
+    """scripts/mpc_state_est/mpc_quad.py:538-652 (i2c branch), closed loop with the golden's noise draws."""
+    g = golden(f"mpc_quadrotor_{mode}")
+    model = mirror.QuadrotorKnown()
+    model.sig_zeta = g["sig_zeta"]
+    T_plan = int(g["T_plan"])
+    _i2c = mirror.I2cGraph(sys=model, horizon=T_plan, Q=g["Q"], R=g["R"], Qf=g["Qf"], alpha=1.0, alpha_update_tol=1.0,
+                           mu_u=g["u_init"], sig_u=g["sig_u"], mu_x_terminal=None, sig_x_terminal=None,
+                           inference=mirror.CubatureQuadrature(1, 0, 0), res_dir=None)
+    _i2c._propagate = True
+    policy = mirror.PartiallyObservedMpcPolicy(_i2c, int(g["mpc_iter"]), g["sig_u"], np.copy(g["z_traj"]))
+    policy.set_control(feedforward=bool(g["feedforward"]))
+    policy.i2c.calibrate_alpha()
+    assert abs(policy.i2c.alpha - g["alpha_cal1"]) < 1e-10 * g["alpha_cal1"]
+    policy.optimize(25, model.x0, model.sig_x0)
+    policy.i2c.calibrate_alpha()
+    assert abs(policy.i2c.alpha - g["alpha_cal2"]) < 1e-8 * g["alpha_cal2"]
+    u = np.zeros((model.dim_u, 1))
+    for t in range(g["u"].shape[0]):
+        u = policy(t, g["y"][t][:, None], u)
+        u = model.clip_u(u.T).T
+        assert relerr(u[:, 0], g["u"][t]) < 1e-6, t
+        assert relerr(policy.mus[-1][:, 0], g["mu"][t]) < 1e-7, t
+        assert relerr(policy.xu_history[-1][:, :, 0], g["plan"][t]) < 1e-6, t
