@@ -221,10 +221,12 @@ def run_cuda(args, rank, world, local_rank):
         e2e_step()
     if dist is not None:
         # the path's only collective: final gather of controllers and costs over NVLink
+        from i2c_b200 import dist as idist
+
         Kd, kd, sd = g.policy_device_tensors()
-        outs = [[torch.empty_like(x) for _ in range(world)] for x in (Kd, kd, sd)]
-        for o, x in zip(outs, (Kd, kd, sd)):
-            dist.all_gather(o, x)
+        cost = torch.from_numpy(np.ascontiguousarray(h_m[0])).to(Kd.device)
+        gathered = idist.gather_controllers(Kd, kd, sd, world * B, extra=(cost,))
+        assert gathered[0].shape[0] == world * B
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * B * T * Ke / (e2e_ms * 1e-3)
@@ -270,6 +272,25 @@ def run_cuda(args, rank, world, local_rank):
                               "frac_of_measured": (fp64_ach / fp64_peak) if fp64_peak else None,
                               "peak_nominal_tflops": FP64_NOMINAL_TFLOPS, "frac_of_nominal": fp64_ach / FP64_NOMINAL_TFLOPS}},
     }
+    if world == 1 and args.saturation > B:
+        # same kernel at a batch that fills the machine (the 4096-problem headline is bound by the latency of the
+        # sequential recursion over t: 128 warps on 592 sub-partitions)
+        Bs = args.saturation
+        x0s, mu_us = make_inputs(Bs, T, 99)
+        del g
+        torch.cuda.empty_cache()
+        gs = i2c_b200.BatchedI2c("PendulumKnown", Bs, T, HYPER["Q"], HYPER["R"], HYPER["Q"], HYPER["alpha"], HYPER["tol"],
+                                 mu_us, HYPER["sig_u"], x0=x0s, device=dev, max_iters=8)
+        gs.run(3, capi.PH_LEARN, collect=False)
+        gs.run(5, capi.PH_LEARN, collect=False)
+        torch.cuda.synchronize(dev)
+        ms_s = gs.last_run_ms()
+        rate_s = Bs * T * 5 / (ms_s * 1e-3)
+        line["saturation"] = {"problems": Bs, "value": rate_s, "unit": UNIT, "ms_per_step": ms_s / 5,
+                              "hbm_frac": B_ALG * rate_s / 1e9 / hbm_peak,
+                              "fp64_frac_of_measured": (F_ALG * rate_s / 1e12 / fp64_peak) if fp64_peak else None,
+                              "failed_problems": int(np.count_nonzero(gs.status()[0]))}
+        del gs
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate, dt, wall = cpu_rate(T, 2, 1, 64, cores)
@@ -290,6 +311,7 @@ def main():
     ap.add_argument("--problems", type=int, default=4096, help="problems per GPU")
     ap.add_argument("--horizon", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--saturation", type=int, default=65536, help="extra large-batch measurement at N=1 (0 = off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
