@@ -233,6 +233,7 @@ def run_cuda(args, rank, world, local_rank):
     h2d = h_x0.nbytes + h_s0.nbytes
     d2h = h_K.nbytes + h_k.nbytes + h_s.nbytes + 2 * h_m.nbytes
 
+    mpc = mpc_leg(args, dev, rank, world, max_over_ranks, barrier) if args.mpc_rollouts > 0 else None
     if rank != 0:
         return
     peaks = {}
@@ -291,6 +292,8 @@ def run_cuda(args, rank, world, local_rank):
                               "fp64_frac_of_measured": (F_ALG * rate_s / 1e12 / fp64_peak) if fp64_peak else None,
                               "failed_problems": int(np.count_nonzero(gs.status()[0]))}
         del gs
+    if mpc is not None:
+        line["mpc"] = mpc
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate, dt, wall = cpu_rate(T, 2, 1, 64, cores)
@@ -300,6 +303,58 @@ def run_cuda(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def mpc_leg(args, dev, rank, world, max_over_ranks, barrier):
+    """Second half of BASELINE.json's metric: microseconds per MPC solve.  Quadrotor MPC with cubature Kalman filter
+    state estimation (BASELINE configs[4], scripts/mpc_state_est/mpc_quad.py:538-652): `mpc_rollouts` parallel
+    closed-loop roll-outs per GPU, T_plan = 10, mpc_iter = 2; one solve = PartiallyObservedMpcPolicy.__call__ =
+    CKF step + 2 x (forward + backward sweep, _update_priors) + first action + horizon shift, through the public
+    API with HOST measurement / action buffers (so H2D / D2H are inside the timed region)."""
+    import torch
+    import i2c_b200
+
+    B = args.mpc_rollouts
+    W_, H_ = i2c_b200.envs.QUAD_W, i2c_b200.envs.QUAD_H
+    T, T_plan, mpc_iter = 100, 10, 2
+    z_traj = np.zeros((T, 8))
+    z_traj[:, 0] = np.linspace(W_ / 4, 3 * W_ / 4, T)
+    z_traj[:, 1] = H_ / 2 + (H_ / 4) * np.sin(np.linspace(0, 2 * np.pi, T))
+    z_traj[:, 2] = 2 * np.pi * np.heaviside(np.linspace(-1, 1, T), 1)
+    Q, R = np.diag([1e3, 1e3, 1e3, 1, 1, 1]), np.diag([1e-3, 1e-3])
+    sig_zeta = np.diag([1e-6] * 8)
+    u_init = 0.5 * 9.81 * i2c_b200.envs.QUAD_MASS * np.ones((T_plan, 2))
+    g = i2c_b200.BatchedI2c("Quadrotor", B, T_plan, Q, R, Q / 1e3, 1.0, 1.0, u_init, 1e-2 * np.eye(2), device=dev)
+    g._propagate = True
+    pol = i2c_b200.BatchedPartiallyObservedMpc(g, mpc_iter, 1e-2 * np.eye(2), z_traj, sig_zeta=sig_zeta)
+    pol.set_control(feedforward=False)
+    g.calibrate_alpha()
+    pol.optimize(25)
+    g.calibrate_alpha()
+    rng = np.random.default_rng(7 + rank)
+    e = g.env
+    y0 = np.array([e.x0[0] - 0.8, e.x0[1], e.x0[0] + 0.8, e.x0[1], 0, 0, 0.8, 0.8])  # measure(x0)
+    y = torch.empty((B, 8), dtype=torch.float64, pin_memory=True).numpy()
+    u = np.zeros((B, 2))
+    n_warm, n_timed = 3, 12
+    launches0 = 0
+    t0 = 0.0
+    for t in range(n_warm + n_timed):
+        if t == n_warm:
+            barrier()
+            launches0 = g.kernel_launches()
+            t0 = time.perf_counter()
+        y[:] = y0 + 1e-3 * rng.normal(size=(B, 8))
+        u = np.clip(pol(t, y, u), 0.0, 30.0)
+    barrier()
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_timed
+    st = g.status()[0]
+    return {"metric": "us per MPC solve (amortised over the roll-out batch)", "value": ms * 1e3 / (world * B), "unit": "us",
+            "higher_is_better": False, "rollouts_per_gpu": B, "batch_latency_ms_per_control_step": ms,
+            "solves_per_s": world * B / (ms * 1e-3), "control_steps_timed": n_timed,
+            "launches_per_control_step": (g.kernel_launches() - launches0) / n_timed,
+            "config": "quadrotor MPC + cubature Kalman filter, T_plan=10, mpc_iter=2, feedback mode (BASELINE configs[4])",
+            "failed_rollouts": int(np.count_nonzero(st))}
 
 
 def main():
@@ -312,6 +367,7 @@ def main():
     ap.add_argument("--horizon", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--saturation", type=int, default=65536, help="extra large-batch measurement at N=1 (0 = off)")
+    ap.add_argument("--mpc-rollouts", type=int, default=8192, help="roll-outs per GPU of the MPC leg (0 = off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
