@@ -41,6 +41,11 @@ struct Lay {
   static constexpr int R_L3 = 0, R_N3 = DX * DX, R_L0 = R_N3 + DX, R_N0 = R_L0 + DX * DX, E_RIC = R_N0 + DX;
   // staged (prefetched) parts of the records: the prior / posterior without k, sigK; the whole filtered record
   static constexpr int E_STAGE_POST = P_KK, E_STAGE = E_FILT > P_KK ? E_FILT : P_KK;
+  // + the cell's target z (DZ doubles) and one 8-byte slot holding {flags, index}
+  static constexpr int S_Z = E_STAGE, S_META = E_STAGE + DZ, E_STAGE_TOT = E_STAGE + DZ + 1;
+  // big records (double cart-pole, quadrotor): a cell costs tens of thousands of cycles, staging would only cost
+  // occupancy (2 x 58 KB per warp) -> read the records straight from global memory
+  static constexpr bool STAGED = E_FILT <= 64;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -120,17 +125,18 @@ __device__ __forceinline__ void sigma_transform(const double* m, const double* L
     for (int b = 0; b <= a; ++b) Syy[tix(a, b)] = fma(-my[a], my[b], Syy[tix(a, b)]);
 }
 
-// S_xy[i][a] = sum_{j<=i} L[i][j] Dm[j][a]
+// S_xy[i][a] = sum_{j<=i} L[i][j] Dm[j][a], computed IN PLACE (bottom row first: row i only needs rows j <= i), so
+// that Dm and S_xy never coexist in registers.
 template <int D, int DY>
-__device__ __forceinline__ void cross_cov(const double* L, const double* Dm, double* Sxy) {
+__device__ __forceinline__ void cross_cov(const double* L, double* DmSxy) {
 #pragma unroll
-  for (int i = 0; i < D; ++i)
+  for (int i = D - 1; i >= 0; --i)
 #pragma unroll
     for (int a = 0; a < DY; ++a) {
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j <= i; ++j) s = fma(L[tix(i, j)], Dm[j * DY + a], s);
-      Sxy[i * DY + a] = s;
+      for (int j = 0; j <= i; ++j) s = fma(L[tix(i, j)], DmSxy[j * DY + a], s);
+      DmSxy[i * DY + a] = s;
     }
 }
 
@@ -138,27 +144,21 @@ __device__ __forceinline__ void cross_cov(const double* L, const double* Dm, dou
 //   G = Sxy Sy^{-1};  mu += G (z - my);  Sig -= G Sxy^T      (i2c.py:398-403 / :438-443)
 // done through the Cholesky factor of Sy: W_i = Ly^{-1} Sxy[i,:]^T, r = Ly^{-1}(z - my).
 template <int D, int DY>
-__device__ __forceinline__ bool condition(double* mu, double* Sig, double* Sy, const double* Sxy, const double* my,
-                                          const double* z) {
+__device__ __forceinline__ bool condition(double* mu, double* Sig, double* Sy, double* Sxy /* overwritten by W */,
+                                          const double* my, const double* z) {
   double invd[DY];
   bool ok = chol_rows<DY>(Sy, invd);
   double r[DY];
 #pragma unroll
   for (int a = 0; a < DY; ++a) r[a] = z[a] - my[a];
   fwd_subst<DY>(Sy, invd, r);
-  double W[D * DY];
+  double* W = Sxy;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    double w[DY];
-#pragma unroll
-    for (int a = 0; a < DY; ++a) w[a] = Sxy[i * DY + a];
-    fwd_subst<DY>(Sy, invd, w);
+    fwd_subst<DY>(Sy, invd, W + i * DY);
     double dm = 0.0;
 #pragma unroll
-    for (int a = 0; a < DY; ++a) {
-      W[i * DY + a] = w[a];
-      dm = fma(w[a], r[a], dm);
-    }
+    for (int a = 0; a < DY; ++a) dm = fma(W[i * DY + a], r[a], dm);
     mu[i] += dm;
   }
 #pragma unroll
@@ -310,6 +310,69 @@ struct Worker {
 #pragma unroll
       for (int a = 0; a < DZ; ++a) z[a] = p.z_cell[slot(t) * DZ + a];
     }
+  }
+  // stage the cell's target and {flags, index} next to its record (same cp.async group)
+  __device__ __forceinline__ void stage_meta(double* sbuf, int t) const {
+    const int sl = slot(t);
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(sbuf);
+    const double* zsrc = p.z_per_problem ? p.z_cell + ((size_t)sl * p.ntiles + tile) * DZ * TILE + lane : p.z_cell + sl * DZ;
+    const size_t zstride = p.z_per_problem ? TILE : 1;
+#pragma unroll
+    for (int a = 0; a < DZ; ++a)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s0 + (LY::S_Z + a) * TILE * 8), "l"(zsrc + a * zstride) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s0 + LY::S_META * TILE * 8), "l"(p.cell_flags + sl) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s0 + LY::S_META * TILE * 8 + 4), "l"(p.cell_index + sl) : "memory");
+  }
+  __device__ __forceinline__ void staged_z(const double* sbuf, int t, double* z) const {
+    if (LY::STAGED && p.stage_meta) {
+#pragma unroll
+      for (int a = 0; a < DZ; ++a) z[a] = sbuf[(LY::S_Z + a) * TILE];
+    } else {
+      load_z(t, z);
+    }
+  }
+  __device__ __forceinline__ int staged_flags(const double* sbuf, int t, bool flipped) const {
+    int flags, index;
+    if (LY::STAGED && p.stage_meta) {
+      const int2 m = *reinterpret_cast<const int2*>(sbuf + LY::S_META * TILE);
+      flags = m.x;
+      index = m.y;
+    } else {
+      flags = p.cell_flags[slot(t)];
+      index = flipped ? p.cell_index[slot(t)] : 0;
+    }
+    if (flipped && p.tau > 0 && index <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
+    return flags;
+  }
+  // double-buffered record stream: issue the copy of cell `tn` (if valid) while cell `t` is consumed
+  template <int E>
+  __device__ __forceinline__ const double* stream(double* base_g, int Erec, int t, int tn, bool tn_valid) {
+    if constexpr (LY::STAGED) {
+      double* cur = stage + (t & 1) * (LY::E_STAGE_TOT * TILE);
+      if (tn_valid) {
+        double* nxt = stage + (tn & 1) * (LY::E_STAGE_TOT * TILE);
+        stage_record<E>(nxt, rec(base_g, tn, Erec));
+        if (p.stage_meta) stage_meta(nxt, tn);
+      }
+      stage_commit();
+      stage_wait<1>();
+      return cur;
+    } else {
+      return rec(base_g, t, Erec);
+    }
+  }
+  template <int E>
+  __device__ __forceinline__ void stream_begin(double* base_g, int Erec, int t) {
+    __threadfence();  // records written by earlier sweeps of this thread are read back through cp.async
+    if constexpr (LY::STAGED) {
+      double* nxt = stage + (t & 1) * (LY::E_STAGE_TOT * TILE);
+      stage_record<E>(nxt, rec(base_g, t, Erec));
+      if (p.stage_meta) stage_meta(nxt, t);
+      stage_commit();
+    }
+  }
+  __device__ __forceinline__ void stream_end() {
+    if constexpr (LY::STAGED) stage_wait<0>();
   }
   __device__ __forceinline__ void load_zterm(double* zt) const {
     if (p.z_term_pp) {
@@ -522,12 +585,11 @@ struct Worker {
       if (lin()) {
         lin_obs_moments(mu, Sig, mz, Sz, Sxy);
       } else {
-        double Dm[N * DZ];
         TrigT ctx;
         Env::center(mu, ctx);
         sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
-                               [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
-        cross_cov<N, DZ>(L, Dm, Sxy);
+                               [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Sxy);
+        cross_cov<N, DZ>(L, Sxy);
       }
       const double a_cell = cell_alpha(t, flags, alpha);
 #pragma unroll
@@ -540,7 +602,7 @@ struct Worker {
 #pragma unroll
         for (int i = 0; i < TRI(DZ); ++i) af[(LY::AF_SIGZ + i) * TILE] = Sz[i];
       }
-      load_z(t, z);
+      staged_z(pr, t, z);
       if (!condition<N, DZ>(mu, Sig, Sz, Sxy, mz, z)) fail(I2C_FAIL_CHOL_OBS, it, t);
     }
     double* fr = rec(p.filt, t, LY::E_FILT);
@@ -558,12 +620,11 @@ struct Worker {
       if (lin()) {
         lin_dyn_moments(mu, Sig, c.m, c.S, Sxy);
       } else {
-        double Dm[N * DX];
         TrigT ctx;
         Env::center(mu, ctx);
         sigma_transform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
-                               [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Dm);
-        cross_cov<N, DX>(L, Dm, Sxy);
+                               [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Sxy);
+        cross_cov<N, DX>(L, Sxy);
       }
 #pragma unroll
       for (int i = 0; i < TRI(DX); ++i) {
@@ -585,12 +646,12 @@ struct Worker {
     }
     // ---- terminal cost update on the outgoing message (i2c.py:430-443)
     if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf && !lin()) {
-      double mz[DZT], Sz[TRI(DZT)], Dm[DX * DZT], Sxy[DX * DZT];
+      double mz[DZT], Sz[TRI(DZT)], Sxy[DX * DZT];
       TrigT ctx;
       Env::center(c.m, ctx);
       sigma_transform<DX, DZT>(c.m, c.L, p.sf_x, p.w0_x, p.wi_x,
-                               [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Dm);
-      cross_cov<DX, DZT>(c.L, Dm, Sxy);
+                               [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Sxy);
+      cross_cov<DX, DZT>(c.L, Sxy);
       const double a_cell = cell_alpha(t, flags, alpha);
 #pragma unroll
       for (int a = 0; a < DZT; ++a)
@@ -764,7 +825,7 @@ struct Worker {
       }
       st.cost += cm;
       st.cost_var += cv;
-      load_z(t, z);
+      staged_z(fr, t, z);
       st.tr += alpha_trace<DZ>(p.QR, p.qr_diag, mz, Sz, z);
     }
   }
@@ -988,7 +1049,7 @@ struct Worker {
       st.cost += cm;
       st.cost_var += cv;
       st.cost_min = fmin(st.cost_min, cm);
-      load_z(t, z);
+      staged_z(po, t, z);
       st.tr += alpha_trace<DZ>(p.QR, p.qr_diag, mz, Sz, z);
     }
     {
@@ -1359,19 +1420,12 @@ struct Worker {
       double tr_term = 0.0;
       if (p.phases & I2C_PH_FORWARD) {
         if (!load_x0(c)) fail(I2C_FAIL_CHOL_PRIOR, it, 0);
-        __threadfence();  // records written by earlier sweeps of this thread are read back through cp.async
-        stage_record<LY::E_STAGE_POST>(stage, rec(prior, 0, LY::E_POST));
-        stage_commit();
+        stream_begin<LY::E_STAGE_POST>(prior, LY::E_POST, 0);
         for (int t = 0; t < T; ++t) {
-          double* cur = stage + (t & 1) * (LY::E_STAGE * TILE);
-          if (t + 1 < T) stage_record<LY::E_STAGE_POST>(stage + ((t + 1) & 1) * (LY::E_STAGE * TILE), rec(prior, t + 1, LY::E_POST));
-          stage_commit();
-          int flags = p.cell_flags[slot(t)];
-          if (flipped && p.tau > 0 && p.cell_index[slot(t)] <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
-          stage_wait<1>();
-          forward_cell(it, t, flags, alpha, aux, cur, c, ent_x);
+          const double* cur = stream<LY::E_STAGE_POST>(prior, LY::E_POST, t, t + 1, t + 1 < T);
+          forward_cell(it, t, staged_flags(cur, t, flipped), alpha, aux, cur, c, ent_x);
         }
-        stage_wait<0>();
+        stream_end();
       }
       if (p.phases & I2C_PH_BACKWARD) {
         if (!(p.phases & I2C_PH_FORWARD)) {
@@ -1389,17 +1443,12 @@ struct Worker {
         double m3m[DX], S3m[TRI(DX)];
         backward_terminal(it, T - 1, temp, cell_alpha(T - 1, p.cell_flags[slot(T - 1)], alpha), c, m3m, S3m, tr_term);
         if (p.cov_ctrl) temp += p.dtemp;
-        __threadfence();
-        stage_record<LY::E_FILT>(stage + ((T - 1) & 1) * (LY::E_STAGE * TILE), rec(p.filt, T - 1, LY::E_FILT));
-        stage_commit();
+        stream_begin<LY::E_FILT>(p.filt, LY::E_FILT, T - 1);
         for (int t = T - 1; t >= 0; --t) {
-          double* cur = stage + (t & 1) * (LY::E_STAGE * TILE);
-          if (t > 0) stage_record<LY::E_FILT>(stage + ((t - 1) & 1) * (LY::E_STAGE * TILE), rec(p.filt, t - 1, LY::E_FILT));
-          stage_commit();
-          stage_wait<1>();
-          backward_cell(it, t, p.cell_flags[slot(t)], aux, cur, m3m, S3m, st);
+          const double* cur = stream<LY::E_FILT>(p.filt, LY::E_FILT, t, t - 1, t > 0);
+          backward_cell(it, t, staged_flags(cur, t, false), aux, cur, m3m, S3m, st);
         }
-        stage_wait<0>();
+        stream_end();
         latest = post;
       }
       PStats ps;
@@ -1409,19 +1458,12 @@ struct Worker {
       if (p.phases & I2C_PH_PROPAGATE) {
         Carry<DX> cp;
         if (!load_x0(cp)) fail(I2C_FAIL_CHOL_PROPAGATE, it, 0);
-        __threadfence();
-        stage_record<LY::E_STAGE_POST>(stage, rec(latest, 0, LY::E_POST));
-        stage_commit();
+        stream_begin<LY::E_STAGE_POST>(latest, LY::E_POST, 0);
         for (int t = 0; t < T; ++t) {
-          double* cur = stage + (t & 1) * (LY::E_STAGE * TILE);
-          if (t + 1 < T) stage_record<LY::E_STAGE_POST>(stage + ((t + 1) & 1) * (LY::E_STAGE * TILE), rec(latest, t + 1, LY::E_POST));
-          stage_commit();
-          int flags = p.cell_flags[slot(t)];
-          if (flipped && p.tau > 0 && p.cell_index[slot(t)] <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
-          stage_wait<1>();
-          propagate_cell(it, t, flags, aux, cur, cp, ps);
+          const double* cur = stream<LY::E_STAGE_POST>(latest, LY::E_POST, t, t + 1, t + 1 < T);
+          propagate_cell(it, t, staged_flags(cur, t, flipped), aux, cur, cp, ps);
         }
-        stage_wait<0>();
+        stream_end();
         if (p.cov_ctrl) {
           // KL(N(mu_x3_pf, sig_x3_pf) || N(mu_xT, sig_xT)) of the last cell (i2c.py:1012-1019, 1223-1229)
           double A[TRI(DX)], ia[DX], d[DX];
@@ -1519,15 +1561,37 @@ struct Worker {
   }
 };
 
-template <class Env>
-__global__ void __launch_bounds__(128) em_kernel(const __grid_constant__ KParams pin) {
+// MINB = minimum resident 128-thread blocks per SM: 1 lets ptxas use up to 255 registers (best per-warp latency,
+// used when the batch cannot fill the machine anyway); 4 caps the kernel at 128 registers so that 16 warps per SM
+// are resident (throughput regime, small envs only).
+template <class Env, int MINB>
+__global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ KParams pin) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / TILE;
   const int lane = threadIdx.x % TILE;
   if (warp >= pin.ntiles) return;
   extern __shared__ __align__(16) double stage_smem[];
-  double* stage = stage_smem + (size_t)(threadIdx.x / TILE) * (2 * Lay<Env>::E_STAGE * TILE) + lane;
+  double* stage = stage_smem + (size_t)(threadIdx.x / TILE) * (2 * Lay<Env>::E_STAGE_TOT * TILE) + lane;
   Worker<Env> w(pin, warp, lane, stage);
   w.run();
+}
+
+template <class Env, int MINB>
+static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
+  int wpb = threads / TILE;
+  int blocks = (p.ntiles + wpb - 1) / wpb;
+  const size_t smem = Lay<Env>::STAGED ? (size_t)wpb * 2 * Lay<Env>::E_STAGE_TOT * TILE * sizeof(double) : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  KParams q = p;
+  // staging the per-cell targets / flags removes their exposed load latency when a warp is alone on its
+  // sub-partition; in the throughput regime the extra LDGSTS instructions cost more than they hide
+  q.stage_meta = Lay<Env>::STAGED && p.ntiles < 148 * 8;
+  em_kernel<Env, MINB><<<blocks, threads, smem, s>>>(q);
+  return (int)cudaGetLastError();
 }
 
 template <class Env>
@@ -1536,17 +1600,11 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   int threads = 32;
   if (p.ntiles >= 148 * 8) threads = 64;
   if (p.ntiles >= 148 * 32) threads = 128;
-  int wpb = threads / TILE;
-  int blocks = (p.ntiles + wpb - 1) / wpb;
-  const size_t smem = (size_t)wpb * 2 * Lay<Env>::E_STAGE * TILE * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+  if constexpr (Lay<Env>::N <= 3) {
+    // small envs fit 128 registers with a few bytes of spill: worth it once >= 12 warps per SM are available
+    if (p.ntiles >= 148 * 12) return launch_em_v<Env, 4>(p, s, 128);
   }
-  em_kernel<Env><<<blocks, threads, smem, s>>>(p);
-  return (int)cudaGetLastError();
+  return launch_em_v<Env, 1>(p, s, threads);
 }
 
 int launch_em(int env, const KParams& p, void* stream) {
@@ -1588,7 +1646,7 @@ __global__ void __launch_bounds__(64) quad_kernel(const __grid_constant__ QuadAr
 #pragma unroll
   for (int i = 0; i < TRI(D); ++i) L[i] = a.S[((size_t)tile * TRI(D) + i) * TILE + lane];
   bool ok = chol_rows<D>(L, invd);
-  double my[DY], Sy[TRI(DY)], Dm[D * DY], Sxy[D * DY];
+  double my[DY], Sy[TRI(DY)], Sxy[D * DY];
   typename Env::TrigT ctx;
   Env::center(m, ctx);
   sigma_transform<D, DY>(m, L, a.sf, a.w0, a.wi,
@@ -1598,8 +1656,8 @@ __global__ void __launch_bounds__(64) quad_kernel(const __grid_constant__ QuadAr
                            else if (FN == 2) Env::dyn(x, j, ctx, par, y);
                            else Env::measure(x, j, ctx, y);
                          },
-                         my, Sy, Dm);
-  cross_cov<D, DY>(L, Dm, Sxy);
+                         my, Sy, Sxy);
+  cross_cov<D, DY>(L, Sxy);
 #pragma unroll
   for (int i = 0; i < DY; ++i) a.my[((size_t)tile * DY + i) * TILE + lane] = my[i];
 #pragma unroll
@@ -1678,11 +1736,11 @@ __global__ void __launch_bounds__(64) ckf_kernel(const __grid_constant__ CkfArgs
   }
   ok = chol_rows<DX>(L, invd) && ok;
   // update on the measurement
-  double my[DY], Sy[TRI(DY)], Dm[DX * DY], Sxy[DX * DY], yv[DY];
+  double my[DY], Sy[TRI(DY)], Sxy[DX * DY], yv[DY];
   Env::center(mf, ctx);
   sigma_transform<DX, DY>(mf, L, a.sf, a.w0, a.wi,
-                          [&](const double* x, int j, double* y) { Env::measure(x, j, ctx, y); }, my, Sy, Dm);
-  cross_cov<DX, DY>(L, Dm, Sxy);
+                          [&](const double* x, int j, double* y) { Env::measure(x, j, ctx, y); }, my, Sy, Sxy);
+  cross_cov<DX, DY>(L, Sxy);
 #pragma unroll
   for (int i = 0; i < TRI(DY); ++i) Sy[i] += a.sig_zeta[i];
 #pragma unroll
