@@ -46,6 +46,7 @@ struct Lay {
   // big records (double cart-pole, quadrotor): a cell costs tens of thousands of cycles, staging would only cost
   // occupancy (2 x 58 KB per warp) -> read the records straight from global memory
   static constexpr bool STAGED = E_FILT <= 64;
+
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -260,7 +261,8 @@ struct Carry {
   double m[DX], S[TRI(DX)], L[TRI(DX)], invd[DX];
 };
 
-template <class Env>
+// META: compile the staging of per-cell targets / flags in (latency-regime variant) or out (throughput variant)
+template <class Env, bool META>
 struct Worker {
   using LY = Lay<Env>;
   static constexpr int DX = LY::DX, DU = LY::DU, N = LY::N, DZ = LY::DZ, DZT = LY::DZT;
@@ -324,7 +326,7 @@ struct Worker {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s0 + LY::S_META * TILE * 8 + 4), "l"(p.cell_index + sl) : "memory");
   }
   __device__ __forceinline__ void staged_z(const double* sbuf, int t, double* z) const {
-    if (LY::STAGED && p.stage_meta) {
+    if (LY::STAGED && META && p.stage_meta) {
 #pragma unroll
       for (int a = 0; a < DZ; ++a) z[a] = sbuf[(LY::S_Z + a) * TILE];
     } else {
@@ -333,7 +335,7 @@ struct Worker {
   }
   __device__ __forceinline__ int staged_flags(const double* sbuf, int t, bool flipped) const {
     int flags, index;
-    if (LY::STAGED && p.stage_meta) {
+    if (LY::STAGED && META && p.stage_meta) {
       const int2 m = *reinterpret_cast<const int2*>(sbuf + LY::S_META * TILE);
       flags = m.x;
       index = m.y;
@@ -352,7 +354,7 @@ struct Worker {
       if (tn_valid) {
         double* nxt = stage + (tn & 1) * (LY::E_STAGE_TOT * TILE);
         stage_record<E>(nxt, rec(base_g, tn, Erec));
-        if (p.stage_meta) stage_meta(nxt, tn);
+        if (META && p.stage_meta) stage_meta(nxt, tn);
       }
       stage_commit();
       stage_wait<1>();
@@ -367,7 +369,7 @@ struct Worker {
     if constexpr (LY::STAGED) {
       double* nxt = stage + (t & 1) * (LY::E_STAGE_TOT * TILE);
       stage_record<E>(nxt, rec(base_g, t, Erec));
-      if (p.stage_meta) stage_meta(nxt, t);
+      if (META && p.stage_meta) stage_meta(nxt, t);
       stage_commit();
     }
   }
@@ -1571,7 +1573,7 @@ __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ K
   if (warp >= pin.ntiles) return;
   extern __shared__ __align__(16) double stage_smem[];
   double* stage = stage_smem + (size_t)(threadIdx.x / TILE) * (2 * Lay<Env>::E_STAGE_TOT * TILE) + lane;
-  Worker<Env> w(pin, warp, lane, stage);
+  Worker<Env, MINB == 1> w(pin, warp, lane, stage);
   w.run();
 }
 

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libi2c_b200.so")
+LIB_PATH = os.environ.get("I2C_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libi2c_b200.so")  # env: A/B builds
 ABI_VERSION = 1
 
 # enum i2c_env
