@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -703,6 +704,7 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   kp.pf = h->pf;
   kp.ric = h->ric;
   kp.linearize = h->cfg.inference == I2C_INF_LINEARIZE;
+  kp.no_team = getenv("I2C_B200_NO_TEAM") != nullptr;
   kp.term = h->term;
   kp.x0 = h->x0;
   kp.sig_x0 = h->sig_x0;

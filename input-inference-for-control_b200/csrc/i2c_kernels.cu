@@ -46,6 +46,9 @@ struct Lay {
   // big records (double cart-pole, quadrotor): a cell costs tens of thousands of cycles, staging would only cost
   // occupancy (2 x 58 KB per warp) -> read the records straight from global memory
   static constexpr bool STAGED = E_FILT <= 64;
+  // team kernel: depth of the filtered-record stream of the RTS head loop, and the staging area it needs
+  static constexpr int TEAM_DEPTH = 6;
+  static constexpr int E_TEAM_STAGE = (TEAM_DEPTH * E_FILT > 2 * E_STAGE_TOT) ? TEAM_DEPTH * E_FILT : 2 * E_STAGE_TOT;
 
 };
 
@@ -682,9 +685,11 @@ struct Worker {
     double cost, cost_var, tr;
     LogAcc ent_u;
   };
-  __device__ __forceinline__ void backward_cell(int it, int t, int flags, bool aux, const double* fr, double* m3m,
-                                                double* S3m, Stats& st) {
-    double mu[N], Sig[TRI(N)], J[N * DX];
+  // RTS recursion of one cell (i2c.py:578-592): posterior joint from the filtered record and the next cell's
+  // smoothed state; stores mu_xu0_m / sig_xu0_m and hands (mu_x0_m, sig_x0_m) to the previous cell.
+  __device__ __forceinline__ void backward_head(int it, int t, bool aux, const double* fr, double* m3m, double* S3m,
+                                                double* mu, double* Sig) {
+    double J[N * DX];
     {
       double dm[DX], dS[TRI(DX)];
 #pragma unroll
@@ -736,6 +741,14 @@ struct Worker {
 #pragma unroll
     for (int i = 0; i < TRI(DX); ++i) S3m[i] = Sig[i];
 
+  }
+
+  // Everything of the backward cell that does NOT feed the recursion (i2c.py:594-608 + M-step statistics):
+  // Cholesky of the posterior joint, controller K / k / sigK, marginal cost-feature moments, cost / alpha / entropy
+  // statistics.  Independent across cells => can run on other warps (team kernel).  zbuf: staged targets or NULL.
+  __device__ __forceinline__ void backward_tail(int it, int t, bool aux, const double* zbuf, const double* mu,
+                                                const double* Sig, Stats& st) {
+    double* po = rec(post, t, LY::E_POST);
     double L[TRI(N)], invd[N];
 #pragma unroll
     for (int i = 0; i < TRI(N); ++i) L[i] = Sig[i];
@@ -827,9 +840,16 @@ struct Worker {
       }
       st.cost += cm;
       st.cost_var += cv;
-      staged_z(fr, t, z);
+      if (zbuf) staged_z(zbuf, t, z); else load_z(t, z);
       st.tr += alpha_trace<DZ>(p.QR, p.qr_diag, mz, Sz, z);
     }
+  }
+
+  __device__ __forceinline__ void backward_cell(int it, int t, int flags, bool aux, const double* fr, double* m3m,
+                                                double* S3m, Stats& st) {
+    double mu[N], Sig[TRI(N)];
+    backward_head(it, t, aux, fr, m3m, S3m, mu, Sig);
+    backward_tail(it, t, aux, fr, mu, Sig, st);
   }
 
   // end-of-chain handling of the last cell (i2c.py:546-572): covariance control or plain hand-over, and
@@ -1405,7 +1425,13 @@ struct Worker {
   }
 
   // ---------------------------------------------------------------------------------- the EM loop
-  __device__ void run() {
+  // TEAM = false: one warp does everything for its tile.  TEAM = true (latency regime, one block of W warps per
+  // tile): warp 0 runs the sequential recursions (forward sweep, RTS heads, propagate); the per-cell work of the
+  // backward pass that does not feed the recursion (backward_tail) is spread over all W warps, cell t -> warp
+  // (T-1-t) mod W, and the M-step statistics are reduced through shared memory in a fixed order.
+  template <bool TEAM>
+  __device__ void run_impl(const int w, const int W, double* red) {
+    const bool main_warp = !TEAM || w == 0;
     const double HALF_LOG_2PIE = 1.4189385332046727;  // 0.5 * log(2 pi e)
     double alpha = p.alpha[b];
     const bool aux = p.phases & I2C_PH_STORE_AUX;
@@ -1420,7 +1446,7 @@ struct Worker {
       st.cost = st.cost_var = st.tr = 0.0;
       st.ent_u.reset();
       double tr_term = 0.0;
-      if (p.phases & I2C_PH_FORWARD) {
+      if (main_warp && (p.phases & I2C_PH_FORWARD)) {
         if (!load_x0(c)) fail(I2C_FAIL_CHOL_PRIOR, it, 0);
         stream_begin<LY::E_STAGE_POST>(prior, LY::E_POST, 0);
         for (int t = 0; t < T; ++t) {
@@ -1430,34 +1456,97 @@ struct Worker {
         stream_end();
       }
       if (p.phases & I2C_PH_BACKWARD) {
-        if (!(p.phases & I2C_PH_FORWARD)) {
-          // resume from the stored filtered message of the last cell
-          const double* fr = rec(p.filt, T - 1, LY::E_FILT);
-#pragma unroll
-          for (int i = 0; i < DX; ++i) c.m[i] = fr[(LY::F_MU3 + i) * TILE];
-#pragma unroll
-          for (int i = 0; i < TRI(DX); ++i) {
-            c.S[i] = fr[(LY::F_SIG3 + i) * TILE];
-            c.L[i] = c.S[i];
-          }
-          chol_rows<DX>(c.L, c.invd);
-        }
         double m3m[DX], S3m[TRI(DX)];
-        backward_terminal(it, T - 1, temp, cell_alpha(T - 1, p.cell_flags[slot(T - 1)], alpha), c, m3m, S3m, tr_term);
-        if (p.cov_ctrl) temp += p.dtemp;
-        stream_begin<LY::E_FILT>(p.filt, LY::E_FILT, T - 1);
-        for (int t = T - 1; t >= 0; --t) {
-          const double* cur = stream<LY::E_FILT>(p.filt, LY::E_FILT, t, t - 1, t > 0);
-          backward_cell(it, t, staged_flags(cur, t, false), aux, cur, m3m, S3m, st);
+        if (main_warp) {
+          if (!(p.phases & I2C_PH_FORWARD)) {
+            // resume from the stored filtered message of the last cell
+            const double* fr = rec(p.filt, T - 1, LY::E_FILT);
+#pragma unroll
+            for (int i = 0; i < DX; ++i) c.m[i] = fr[(LY::F_MU3 + i) * TILE];
+#pragma unroll
+            for (int i = 0; i < TRI(DX); ++i) {
+              c.S[i] = fr[(LY::F_SIG3 + i) * TILE];
+              c.L[i] = c.S[i];
+            }
+            chol_rows<DX>(c.L, c.invd);
+          }
+          backward_terminal(it, T - 1, temp, cell_alpha(T - 1, p.cell_flags[slot(T - 1)], alpha), c, m3m, S3m, tr_term);
+          if constexpr (TEAM) {
+            // RTS heads only: a head is a few hundred cycles, so the filtered records are streamed TEAM_DEPTH cells
+            // ahead (a one-cell double buffer would expose the DRAM latency of every record)
+            constexpr int DEPTH = LY::TEAM_DEPTH;
+            __threadfence();
+#pragma unroll
+            for (int k = 0; k < DEPTH; ++k) {
+              const int tt = T - 1 - k;
+              if (tt >= 0) stage_record<LY::E_FILT>(stage + (tt % DEPTH) * (LY::E_FILT * TILE), rec(p.filt, tt, LY::E_FILT));
+              stage_commit();
+            }
+            for (int t = T - 1; t >= 0; --t) {
+              stage_wait<DEPTH - 1>();
+              double* cur = stage + (t % DEPTH) * (LY::E_FILT * TILE);
+              double mu[N], Sig[TRI(N)];
+              backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
+              if (t - DEPTH >= 0) stage_record<LY::E_FILT>(cur, rec(p.filt, t - DEPTH, LY::E_FILT));
+              stage_commit();
+            }
+            stage_wait<0>();
+          } else {
+            stream_begin<LY::E_FILT>(p.filt, LY::E_FILT, T - 1);
+            for (int t = T - 1; t >= 0; --t) {
+              const double* cur = stream<LY::E_FILT>(p.filt, LY::E_FILT, t, t - 1, t > 0);
+              backward_cell(it, t, staged_flags(cur, t, false), aux, cur, m3m, S3m, st);
+            }
+            stream_end();
+          }
         }
-        stream_end();
+        if (p.cov_ctrl) temp += p.dtemp;
+        if constexpr (TEAM) {
+          __threadfence_block();
+          __syncthreads();  // every posterior (mu, Sigma) of this sweep is in the post records
+          for (int t = T - 1 - w; t >= 0; t -= W) {
+            const double* po = rec(post, t, LY::E_POST);
+            double mu[N], Sig[TRI(N)];
+#pragma unroll
+            for (int i = 0; i < N; ++i) mu[i] = __ldcg(po + (LY::P_MU + i) * TILE);
+#pragma unroll
+            for (int i = 0; i < TRI(N); ++i) Sig[i] = __ldcg(po + (LY::P_SIG + i) * TILE);
+            backward_tail(it, t, aux, nullptr, mu, Sig, st);
+          }
+          // fixed-order reduction of the per-warp statistics: red[k][w][lane]
+          double* r = red + (size_t)w * TILE + lane;
+          r[0 * W * TILE] = st.cost;
+          r[1 * W * TILE] = st.cost_var;
+          r[2 * W * TILE] = st.tr;
+          r[3 * W * TILE] = st.ent_u.m;
+          r[4 * W * TILE] = (double)st.ent_u.e;
+          r[5 * W * TILE] = (double)status;
+          r[6 * W * TILE] = (double)info;
+          __syncthreads();
+          if (main_warp) {
+            st.cost = st.cost_var = st.tr = 0.0;
+            st.ent_u.reset();
+            for (int ww = 0; ww < W; ++ww) {
+              const double* q = red + (size_t)ww * TILE + lane;
+              st.cost += q[0 * W * TILE];
+              st.cost_var += q[1 * W * TILE];
+              st.tr += q[2 * W * TILE];
+              st.ent_u.mul(q[3 * W * TILE]);
+              st.ent_u.e += (int)q[4 * W * TILE];
+              if (status == I2C_OK && q[5 * W * TILE] != 0.0) {
+                status = (int)q[5 * W * TILE];
+                info = (int)q[6 * W * TILE];
+              }
+            }
+          }
+        }
         latest = post;
       }
       PStats ps;
       ps.cost = ps.cost_var = ps.tr = 0.0;
       ps.cost_min = INFINITY;
       ps.ent.reset();
-      if (p.phases & I2C_PH_PROPAGATE) {
+      if (main_warp && (p.phases & I2C_PH_PROPAGATE)) {
         Carry<DX> cp;
         if (!load_x0(cp)) fail(I2C_FAIL_CHOL_PROPAGATE, it, 0);
         stream_begin<LY::E_STAGE_POST>(latest, LY::E_POST, 0);
@@ -1492,8 +1581,8 @@ struct Worker {
           metric(I2C_M_KL_TERM, it, 0.5 * (p.sxt_logdet - 2.0 * ld1 + tr + dist - (double)DX));
         }
       }
-      if (p.phases & I2C_PH_RICCATI) riccati_sweep(alpha);
-      if (p.phases & I2C_PH_MSTEP) {
+      if (main_warp && (p.phases & I2C_PH_RICCATI)) riccati_sweep(alpha);
+      if (main_warp && (p.phases & I2C_PH_MSTEP)) {
         metric(I2C_M_COST_M, it, st.cost);
         metric(I2C_M_COST_M_VAR, it, st.cost_var);
         if (p.phases & I2C_PH_PROPAGATE) {
@@ -1517,7 +1606,7 @@ struct Worker {
         }
         flipped = true;
       }
-      if (p.phases & I2C_PH_MSTEP) {
+      if (main_warp && (p.phases & I2C_PH_MSTEP)) {
         // compute_update_alpha(update_alpha=True) (i2c.py:921-963)
         double sf = (double)(DZ * T);
         double tr = st.tr;
@@ -1544,7 +1633,7 @@ struct Worker {
         own_alpha_valid = false;  // update_xi pushes the new sig_xi to every cell (i2c.py:976-981)
         metric(I2C_M_ALPHA, it, alpha);
       }
-      if (p.phases & I2C_PH_CALIBRATE) {
+      if (main_warp && (p.phases & I2C_PH_CALIBRATE)) {
         // calibrate_alpha (i2c.py:895-911): alpha from the propagated cost features, no terminal term
         double a_pf = ps.tr / (double)(DZ * T);
         bool upd = (p.phases & I2C_PH_ONLY_DECREASE) ? (a_pf < alpha) : true;
@@ -1555,12 +1644,14 @@ struct Worker {
         metric(I2C_M_ALPHA, it, alpha);
       }
     }
+    if (!main_warp) return;
     p.alpha[b] = alpha;
     if (status != I2C_OK && p.status[b] == I2C_OK) {
       p.status[b] = status;
       p.info[b] = info;
     }
   }
+  __device__ void run() { run_impl<false>(0, 1, nullptr); }
 };
 
 // MINB = minimum resident 128-thread blocks per SM: 1 lets ptxas use up to 255 registers (best per-warp latency,
@@ -1575,6 +1666,31 @@ __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ K
   double* stage = stage_smem + (size_t)(threadIdx.x / TILE) * (2 * Lay<Env>::E_STAGE_TOT * TILE) + lane;
   Worker<Env, MINB == 1> w(pin, warp, lane, stage);
   w.run();
+}
+
+// Latency-regime kernel: one block of W warps per tile (see Worker::run_impl<true>).
+template <class Env, int W>
+__global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_constant__ KParams pin) {
+  const int w = threadIdx.x / TILE, lane = threadIdx.x % TILE;
+  extern __shared__ __align__(16) double stage_smem[];
+  double* red = stage_smem + Lay<Env>::E_TEAM_STAGE * TILE;
+  Worker<Env, true> wk(pin, blockIdx.x, lane, stage_smem + lane);
+  wk.template run_impl<true>(w, W, red);
+}
+
+template <class Env, int W>
+static int launch_em_team(const KParams& p, cudaStream_t s) {
+  const size_t smem = (size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(em_team_kernel<Env, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  KParams q = p;
+  q.stage_meta = 1;
+  em_team_kernel<Env, W><<<p.ntiles, W * TILE, smem, s>>>(q);
+  return (int)cudaGetLastError();
 }
 
 template <class Env, int MINB>
@@ -1602,6 +1718,11 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   int threads = 32;
   if (p.ntiles >= 148 * 8) threads = 64;
   if (p.ntiles >= 148 * 32) threads = 128;
+  if constexpr (Lay<Env>::STAGED) {
+    // fewer tiles than SMs: spread each tile's backward pass over the 8 warps of a block (one block per SM)
+    if (p.ntiles <= 148 && p.T >= 16 && !p.no_team) return launch_em_team<Env, 8>(p, s);
+    if (p.ntiles <= 296 && p.T >= 16 && !p.no_team) return launch_em_team<Env, 4>(p, s);  // two blocks per SM
+  }
   if constexpr (Lay<Env>::N <= 3) {
     // small envs fit 128 registers with a few bytes of spill: worth it once >= 12 warps per SM are available
     if (p.ntiles >= 148 * 12) return launch_em_v<Env, 4>(p, s, 128);
