@@ -48,7 +48,7 @@ struct Lay {
   static constexpr bool STAGED = E_FILT <= 64;
   // team kernel: depth of the filtered-record stream of the RTS head loop, and the staging area it needs
   static constexpr int TEAM_DEPTH = 6;
-  static constexpr int E_TEAM_STAGE = (TEAM_DEPTH * E_FILT > 2 * E_STAGE_TOT) ? TEAM_DEPTH * E_FILT : 2 * E_STAGE_TOT;
+  static constexpr int E_TEAM_STAGE = !STAGED ? 0 : ((TEAM_DEPTH * E_FILT > 2 * E_STAGE_TOT) ? TEAM_DEPTH * E_FILT : 2 * E_STAGE_TOT);
 
 };
 
@@ -1474,23 +1474,30 @@ struct Worker {
           if constexpr (TEAM) {
             // RTS heads only: a head is a few hundred cycles, so the filtered records are streamed TEAM_DEPTH cells
             // ahead (a one-cell double buffer would expose the DRAM latency of every record)
-            constexpr int DEPTH = LY::TEAM_DEPTH;
-            __threadfence();
+            if constexpr (LY::STAGED) {
+              constexpr int DEPTH = LY::TEAM_DEPTH;
+              __threadfence();
 #pragma unroll
-            for (int k = 0; k < DEPTH; ++k) {
-              const int tt = T - 1 - k;
-              if (tt >= 0) stage_record<LY::E_FILT>(stage + (tt % DEPTH) * (LY::E_FILT * TILE), rec(p.filt, tt, LY::E_FILT));
-              stage_commit();
+              for (int k = 0; k < DEPTH; ++k) {
+                const int tt = T - 1 - k;
+                if (tt >= 0) stage_record<LY::E_FILT>(stage + (tt % DEPTH) * (LY::E_FILT * TILE), rec(p.filt, tt, LY::E_FILT));
+                stage_commit();
+              }
+              for (int t = T - 1; t >= 0; --t) {
+                stage_wait<DEPTH - 1>();
+                double* cur = stage + (t % DEPTH) * (LY::E_FILT * TILE);
+                double mu[N], Sig[TRI(N)];
+                backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
+                if (t - DEPTH >= 0) stage_record<LY::E_FILT>(cur, rec(p.filt, t - DEPTH, LY::E_FILT));
+                stage_commit();
+              }
+              stage_wait<0>();
+            } else {
+              for (int t = T - 1; t >= 0; --t) {
+                double mu[N], Sig[TRI(N)];
+                backward_head(it, t, aux, rec(p.filt, t, LY::E_FILT), m3m, S3m, mu, Sig);
+              }
             }
-            for (int t = T - 1; t >= 0; --t) {
-              stage_wait<DEPTH - 1>();
-              double* cur = stage + (t % DEPTH) * (LY::E_FILT * TILE);
-              double mu[N], Sig[TRI(N)];
-              backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
-              if (t - DEPTH >= 0) stage_record<LY::E_FILT>(cur, rec(p.filt, t - DEPTH, LY::E_FILT));
-              stage_commit();
-            }
-            stage_wait<0>();
           } else {
             stream_begin<LY::E_FILT>(p.filt, LY::E_FILT, T - 1);
             for (int t = T - 1; t >= 0; --t) {
@@ -1688,7 +1695,7 @@ static int launch_em_team(const KParams& p, cudaStream_t s) {
     attr_set = true;
   }
   KParams q = p;
-  q.stage_meta = 1;
+  q.stage_meta = Lay<Env>::STAGED;
   em_team_kernel<Env, W><<<p.ntiles, W * TILE, smem, s>>>(q);
   return (int)cudaGetLastError();
 }
@@ -1718,11 +1725,9 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   int threads = 32;
   if (p.ntiles >= 148 * 8) threads = 64;
   if (p.ntiles >= 148 * 32) threads = 128;
-  if constexpr (Lay<Env>::STAGED) {
-    // fewer tiles than SMs: spread each tile's backward pass over the 8 warps of a block (one block per SM)
-    if (p.ntiles <= 148 && p.T >= 16 && !p.no_team) return launch_em_team<Env, 8>(p, s);
-    if (p.ntiles <= 296 && p.T >= 16 && !p.no_team) return launch_em_team<Env, 4>(p, s);  // two blocks per SM
-  }
+  // fewer tiles than SMs: spread each tile's backward pass over the 8 warps of a block (one block per SM)
+  if (p.ntiles <= 148 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 8>(p, s);
+  if (p.ntiles <= 296 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 4>(p, s);  // two blocks per SM
   if constexpr (Lay<Env>::N <= 3) {
     // small envs fit 128 registers with a few bytes of spill: worth it once >= 12 warps per SM are available
     if (p.ntiles >= 148 * 12) return launch_em_v<Env, 4>(p, s, 128);
