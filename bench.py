@@ -28,6 +28,9 @@ METRIC = "problem-timestep updates/sec (fp64, batched)"
 UNIT = "updates/s"
 # SURVEY.md section 8(d), pendulum row: algorithmic work per problem-timestep update
 F_ALG, B_ALG = 3192.0, 704.0
+# measured DRAM bytes per update of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture / updates in that launch): profiles/r01d_ncu_full_em_team_kernel_pendulum_4096.txt
+NCU_DRAM_BYTES_PER_UPDATE = (567.175936e6 + 621.642752e6) / (3 * 4096 * 200)
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
 
 
@@ -266,7 +269,11 @@ def run_cuda(args, rank, world, local_rank):
                         + ("; + final NCCL all_gather of controllers" if world > 1 else "")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "em_kernel<EnvPendulum>",
+                     "traffic": NCU_DRAM_BYTES_PER_UPDATE * B * T * K if (B == 4096 and T == 200) else None,
+                     "traffic_source": "ncu dram bytes/update (profiles/r01d_ncu_full_em_team_kernel_pendulum_4096.txt) x updates "
+                                       "per launch; algorithmic bytes per launch = %.4g" % (B_ALG * B * T * K),
+                     "peak_source": peak_src,
+                     "kernel": "em_team_kernel<EnvPendulum,8>" if B <= 148 * 32 else "em_kernel<EnvPendulum>",
                      "kernel_ms_per_launch": kernel_ms,
                      "algorithmic_bytes_per_update": B_ALG, "algorithmic_flops_per_update": F_ALG,
                      "fp64": {"achieved_tflops": fp64_ach, "peak_measured_tflops": fp64_peak,
@@ -296,9 +303,10 @@ def run_cuda(args, rank, world, local_rank):
         line["mpc"] = mpc
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rate, dt, wall = cpu_rate(T, 2, 1, 64, cores)
+        n_cpu_it = 24  # ~10-30 s of CPU work per core
+        rate, dt, wall = cpu_rate(T, n_cpu_it, 1, 64, cores)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{cores} procs x 64 problems x T={T}, 2 EM iterations after 1 warm-up "
+                                "sample": f"{cores} procs x 64 problems x T={T}, {n_cpu_it} EM iterations after 1 warm-up "
                                           f"(oracle/i2c_oracle.py, batched NumPy restatement)", "seconds": wall}
     print(json.dumps(line), flush=True)
     if dist is not None:
