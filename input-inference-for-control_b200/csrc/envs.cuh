@@ -26,6 +26,12 @@ struct EnvLinear {
   // z = E x + F u (+ e = 0): observe_linearize (env_def.py:171-181): E = [I2; 0], F = [0 0 1]^T
   __host__ __device__ static constexpr double obsE(int a, int i) { return a == i ? 1.0 : 0.0; }
   __host__ __device__ static constexpr double obsF(int a, int) { return a == 2 ? 1.0 : 0.0; }
+  // structure of the cost-feature maps: feature a is the identity of joint-state component obs_src(a) >= 0, or the
+  // (-1-k)-th nonlinear (trigonometric) feature; OBS_JMAX = last sigma-point column that changes a nonlinear feature
+  static constexpr int OBS_NL = 0, OBS_JMAX = -1;
+  __host__ __device__ static constexpr int obs_src(int a) { return a; }
+  __host__ __device__ static constexpr int term_src(int a) { return a; }
+  __device__ static void trig_nl(const double*, int, const TrigT&, double*) {}
   __device__ static void center(const double*, TrigT&) {}
   __device__ static void dyn(const double* xu, int, const TrigT&, const double* par, double* y) {
     y[0] = fma(par[0], xu[0], fma(par[1], xu[1], fma(par[4], xu[2], par[6])));
@@ -44,6 +50,7 @@ struct EnvLinearMinEnergy : EnvLinear {
   // env_def.py:211-217: C = 0 (1x2), D = 1
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 1.0; }
+  __host__ __device__ static constexpr int obs_src(int) { return 2; }
   __device__ static void obs(const double* xu, int, const TrigT&, double* z) { z[0] = xu[2]; }
 };
 
@@ -59,6 +66,10 @@ struct EnvPendulum {
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
     if (j != 0) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[0], &s, &co); }
   }
+  static constexpr int OBS_NL = 2, OBS_JMAX = 0;  // z = [sin th, cos th | thd, u]
+  __host__ __device__ static constexpr int obs_src(int a) { return a < 2 ? -1 - a : a - 1; }
+  __host__ __device__ static constexpr int term_src(int a) { return a < 2 ? -1 - a : a - 1; }
+  __device__ static void trig_nl(const double* x, int j, const TrigT& c, double* y) { trig(x, j, c, y[0], y[1]); }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
     const double dt = 0.05, d = 1e-2, g = 9.80665;
     double s, co;
@@ -88,6 +99,10 @@ struct EnvPendulum {
 struct EnvPendulumActReg : EnvPendulum {
   static constexpr int DZ = 1, DZT = 1;
   static constexpr bool HAS_TERM = false;
+  static constexpr int OBS_NL = 0, OBS_JMAX = -1;
+  __host__ __device__ static constexpr int obs_src(int) { return 2; }
+  __host__ __device__ static constexpr int term_src(int) { return 0; }
+  __device__ static void trig_nl(const double*, int, const TrigT&, double*) {}
   __device__ static void obs(const double* xu, int, const TrigT&, double* z) { z[0] = xu[2]; }
   __device__ static void obs_term(const double*, int, const TrigT&, double* z) { z[0] = 0.0; }
 };
@@ -104,6 +119,10 @@ struct EnvCartpole {
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
     if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[1], &s, &co); }
   }
+  static constexpr int OBS_NL = 2, OBS_JMAX = 1;  // z = [x, sin th, cos th, xd, thd, u]
+  __host__ __device__ static constexpr int obs_src(int a) { return a == 0 ? 0 : (a <= 2 ? -a : a - 1); }
+  __host__ __device__ static constexpr int term_src(int a) { return a == 0 ? 0 : (a <= 2 ? -a : a - 1); }
+  __device__ static void trig_nl(const double* x, int j, const TrigT& c, double* y) { trig(x, j, c, y[0], y[1]); }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
     const double g = 9.81, Mc = 0.37, Mp = 0.127, Mt = Mc + Mp, l = 0.3365, dt = 1.0 / 250.0;
     double u = fmin(fmax(xu[4], -5.0), 5.0);
@@ -150,6 +169,13 @@ struct EnvDoubleCartpole {
   }
   __device__ static void trig2(const double* x, int j, const TrigT& c, double& s, double& co) {
     if (j < 0 || j > 2) { s = c.s[1]; co = c.c[1]; } else { fast_sincos(x[2], &s, &co); }
+  }
+  static constexpr int OBS_NL = 4, OBS_JMAX = 2;  // z = [x, s1, c1, s2, c2, xd, thd1, thd2, u]
+  __host__ __device__ static constexpr int obs_src(int a) { return a == 0 ? 0 : (a <= 4 ? -a : a - 2); }
+  __host__ __device__ static constexpr int term_src(int a) { return a == 0 ? 0 : (a <= 4 ? -a : a - 2); }
+  __device__ static void trig_nl(const double* x, int j, const TrigT& c, double* y) {
+    trig1(x, j, c, y[0], y[1]);
+    trig2(x, j, c, y[2], y[3]);
   }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
     const double dt = 1.0 / 125.0, g = 9.81, Mc = 0.37, Mp1 = 0.127, Mp2 = 0.127, Mt = Mc + Mp1 + Mp2;
@@ -219,6 +245,10 @@ struct EnvQuadrotor {
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
     if (j < 0 || j > 2) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[2], &s, &co); }
   }
+  static constexpr int OBS_NL = 0, OBS_JMAX = -1;  // observe / observe_terminal are identities
+  __host__ __device__ static constexpr int obs_src(int a) { return a; }
+  __host__ __device__ static constexpr int term_src(int a) { return a; }
+  __device__ static void trig_nl(const double*, int, const TrigT&, double*) {}
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
     const double h = 0.1;
     double u1 = fmin(fmax(xu[6], 0.0), 30.0), u2 = fmin(fmax(xu[7], 0.0), 30.0);

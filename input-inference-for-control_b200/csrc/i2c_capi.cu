@@ -566,6 +566,8 @@ int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, cons
   kp.alpha_tol = alpha_update_tol;
   cubature_rule(h->cfg.quad_alpha, h->cfg.quad_beta, h->cfg.quad_kappa, n, &kp.sf_n, &kp.w0_n, &kp.wi_n);
   cubature_rule(h->cfg.quad_alpha, h->cfg.quad_beta, h->cfg.quad_kappa, dx, &kp.sf_x, &kp.w0_x, &kp.wi_x);
+  kp.fast_obs = kp.w0_n == 0.0 && kp.w0_x == 0.0 && fabs(2.0 * n * kp.wi_n - 1.0) < 1e-15 &&
+                fabs(2.0 * dx * kp.wi_x - 1.0) < 1e-15 && fabs(kp.sf_n * kp.sf_n - n) < 1e-12 && getenv("I2C_B200_GENERIC_OBS") == nullptr;
   // ---- graph state
   h->cell_head = 0;
   h->flags.assign(T, I2C_CELL_INDEPENDENT | I2C_CELL_EXPERT);

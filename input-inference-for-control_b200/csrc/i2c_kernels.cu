@@ -177,6 +177,93 @@ __device__ __forceinline__ bool condition(double* mu, double* Sig, double* Sy, d
   return ok;
 }
 
+// Structured sigma-point moments of the cost-feature maps.  Every registered observe / observe_terminal map consists
+// of identity features (z_a = x_i) and trigonometric features of angles stored at low state indices.  For the
+// cubature rule with zero centre weight and sum(w) = 1 the moments of the identity features are exact linear
+// results (m_y = m_i, S_xy[:, a] = Sigma[:, i], S_yy = Sigma[i, i']), the cross moment of a nonlinear feature with an
+// identity feature is S_xy[i][nl] (both are sum_j D_j[nl] L[i][j]), and sigma-point columns j > OBS_JMAX reproduce
+// the centre value of every nonlinear feature.  Only the nonlinear block is therefore evaluated at the 2 (JMAX + 1)
+// points that differ from the centre.  Same numbers as sigma_transform + cross_cov up to round-off.
+template <class Env, int D, int DY, bool TERM>
+__device__ __forceinline__ void structured_obs_moments(const double* m, const double* Sig, const double* L, double sf,
+                                                       double wi, double* my, double* Syy, double* Sxy) {
+  constexpr int NL = Env::OBS_NL, JM = Env::OBS_JMAX;
+  constexpr int NLs = NL > 0 ? NL : 1;
+  double mnl[NLs], Snl[TRI(NLs)], Dm[(JM + 1 > 0 ? JM + 1 : 1) * NLs], Cx[D * NLs];
+  if constexpr (NL > 0) {
+    typename Env::TrigT ctx;
+    Env::center(m, ctx);
+    double yc[NL], sy[NL], syy[TRI(NL)];
+    Env::trig_nl(m, -1, ctx, yc);
+    constexpr double mult = 2.0 * (D - 1 - JM);
+#pragma unroll
+    for (int a = 0; a < NL; ++a) {
+      sy[a] = mult * yc[a];
+#pragma unroll
+      for (int b = 0; b <= a; ++b) syy[tix(a, b)] = mult * yc[a] * yc[b];
+    }
+    const double wsf = wi * sf;
+#pragma unroll
+    for (int j = 0; j <= JM; ++j) {
+      double xp[D], xm[D], yp[NL], ym[NL];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        if (i >= j) {
+          const double d = sf * L[tix(i, j)];
+          xp[i] = m[i] + d;
+          xm[i] = m[i] - d;
+        } else {
+          xp[i] = m[i];
+          xm[i] = m[i];
+        }
+      }
+      Env::trig_nl(xp, j, ctx, yp);
+      Env::trig_nl(xm, j, ctx, ym);
+#pragma unroll
+      for (int a = 0; a < NL; ++a) {
+        sy[a] += yp[a] + ym[a];
+        Dm[j * NL + a] = wsf * (yp[a] - ym[a]);
+#pragma unroll
+        for (int b = 0; b <= a; ++b) syy[tix(a, b)] = fma(yp[a], yp[b], fma(ym[a], ym[b], syy[tix(a, b)]));
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NL; ++a) mnl[a] = wi * sy[a];
+#pragma unroll
+    for (int a = 0; a < NL; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) Snl[tix(a, b)] = fma(wi, syy[tix(a, b)], -mnl[a] * mnl[b]);
+    // cross covariance with the nonlinear block: Cx[i][k] = sum_{j <= min(i, JM)} L[i][j] Dm[j][k]
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j <= JM; ++j)
+          if (j <= i) v = fma(L[tix(i, j)], Dm[j * NL + k], v);
+        Cx[i * NL + k] = v;
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < DY; ++a) {
+    const int sa = TERM ? Env::term_src(a) : Env::obs_src(a);
+    my[a] = sa >= 0 ? m[sa >= 0 ? sa : 0] : mnl[sa < 0 ? -1 - sa : 0];
+#pragma unroll
+    for (int i = 0; i < D; ++i) Sxy[i * DY + a] = sa >= 0 ? Sig[six(i, sa >= 0 ? sa : 0)] : Cx[i * NLs + (sa < 0 ? -1 - sa : 0)];
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      const int sb = TERM ? Env::term_src(b) : Env::obs_src(b);
+      double v;
+      if (sa >= 0 && sb >= 0) v = Sig[six(sa >= 0 ? sa : 0, sb >= 0 ? sb : 0)];
+      else if (sa < 0 && sb < 0) v = Snl[six(sa < 0 ? -1 - sa : 0, sb < 0 ? -1 - sb : 0)];
+      else if (sa < 0) v = Cx[(sb >= 0 ? sb : 0) * NLs + (sa < 0 ? -1 - sa : 0)];
+      else v = Cx[(sa >= 0 ? sa : 0) * NLs + (sb < 0 ? -1 - sb : 0)];
+      Syy[tix(a, b)] = v;
+    }
+  }
+}
+
 // quadratic-cost statistics of a Gaussian cost feature (i2c.py:1034-1043 and :680-683, :913-919)
 //   mean = e^T QR e + tr(Sz QR),  var = 2 tr((Sz QR)^2) + 4 e^T QR Sz QR e,   e = mz - zref
 template <int DZ>
@@ -589,6 +676,8 @@ struct Worker {
       double mz[DZ], Sz[TRI(DZ)], Sxy[N * DZ], z[DZ];
       if (lin()) {
         lin_obs_moments(mu, Sig, mz, Sz, Sxy);
+      } else if (p.fast_obs) {
+        structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Sxy);
       } else {
         TrigT ctx;
         Env::center(mu, ctx);
@@ -652,11 +741,15 @@ struct Worker {
     // ---- terminal cost update on the outgoing message (i2c.py:430-443)
     if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf && !lin()) {
       double mz[DZT], Sz[TRI(DZT)], Sxy[DX * DZT];
-      TrigT ctx;
-      Env::center(c.m, ctx);
-      sigma_transform<DX, DZT>(c.m, c.L, p.sf_x, p.w0_x, p.wi_x,
-                               [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Sxy);
-      cross_cov<DX, DZT>(c.L, Sxy);
+      if (p.fast_obs) {
+        structured_obs_moments<Env, DX, DZT, true>(c.m, c.S, c.L, p.sf_x, p.wi_x, mz, Sz, Sxy);
+      } else {
+        TrigT ctx;
+        Env::center(c.m, ctx);
+        sigma_transform<DX, DZT>(c.m, c.L, p.sf_x, p.w0_x, p.wi_x,
+                                 [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Sxy);
+        cross_cov<DX, DZT>(c.L, Sxy);
+      }
       const double a_cell = cell_alpha(t, flags, alpha);
 #pragma unroll
       for (int a = 0; a < DZT; ++a)
@@ -814,6 +907,9 @@ struct Worker {
               for (int k = 0; k < DU; ++k) s = fma(Env::obsF(a, i) * Env::obsF(bb, k), Sig[six(DX + i, DX + k)], s);
             Sz[tix(a, bb)] = s;
           }
+      } else if (p.fast_obs) {
+        double Cxy[N * DZ];
+        structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Cxy);
       } else {
         double Dm[N * DZ];
         TrigT ctx;
@@ -1056,10 +1152,14 @@ struct Worker {
     }
     {
       double mz[DZ], Sz[TRI(DZ)], Dm[N * DZ], z[DZ];
-      TrigT ctx;
-      Env::center(mu, ctx);
-      sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
-                             [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
+      if (p.fast_obs) {
+        structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Dm);
+      } else {
+        TrigT ctx;
+        Env::center(mu, ctx);
+        sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+                               [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
+      }
       if (aux) {
 #pragma unroll
         for (int i = 0; i < DZ; ++i) pf[(LY::PF_MUZ + i) * TILE] = mz[i];

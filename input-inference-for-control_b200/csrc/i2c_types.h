@@ -43,6 +43,7 @@ struct KParams {
   int32_t n_iter, phases, tau, max_iters;
   int32_t cell_head;  // ring offset: logical cell t lives in slot (t + cell_head) % T (O(1) MPC horizon shift)
   int32_t z_per_problem, qr_diag, has_qf, cov_ctrl;
+  int32_t fast_obs;   // cubature rule has zero centre weight and unit weight sum: structured cost-feature moments
   int32_t no_team;    // debugging / A-B: force the one-warp-per-tile kernel
   int32_t stage_meta; // stage the cell targets / flags with the records (latency regime only; set by the launcher)
   int32_t linearize;  // Linearize inference (linear envs only): exact moments instead of sigma points
