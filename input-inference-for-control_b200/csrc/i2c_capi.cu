@@ -14,6 +14,44 @@
 
 using namespace i2c;
 
+// per-environment launchers, one translation unit each (i2c_env_inst.cu)
+namespace i2c {
+#define I2C_DECL_ENV(k)                                                   \
+  int launch_em_env##k(const KParams& p, void* stream);                   \
+  int launch_quad_env##k(int fn, const QuadArgs& a, void* stream);        \
+  int launch_ckf_env##k(const CkfArgs& a, void* stream);
+I2C_DECL_ENV(0) I2C_DECL_ENV(1) I2C_DECL_ENV(2) I2C_DECL_ENV(3) I2C_DECL_ENV(4) I2C_DECL_ENV(5) I2C_DECL_ENV(6)
+#undef I2C_DECL_ENV
+
+#define I2C_SWITCH_ENV(env, call)   \
+  switch (env) {                    \
+    case 0: return call(0);         \
+    case 1: return call(1);         \
+    case 2: return call(2);         \
+    case 3: return call(3);         \
+    case 4: return call(4);         \
+    case 5: return call(5);         \
+    case 6: return call(6);         \
+  }                                 \
+  return -1;
+
+int launch_em(int env, const KParams& p, void* stream) {
+#define CALL(k) launch_em_env##k(p, stream)
+  I2C_SWITCH_ENV(env, CALL)
+#undef CALL
+}
+int launch_quadrature(int env, int fn, const QuadArgs& a, void* stream) {
+#define CALL(k) launch_quad_env##k(fn, a, stream)
+  I2C_SWITCH_ENV(env, CALL)
+#undef CALL
+}
+int launch_ckf(int env, const CkfArgs& a, void* stream) {
+#define CALL(k) launch_ckf_env##k(a, stream)
+  I2C_SWITCH_ENV(env, CALL)
+#undef CALL
+}
+}  // namespace i2c
+
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
   g_err = msg;

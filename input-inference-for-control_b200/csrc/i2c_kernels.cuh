@@ -1,4 +1,5 @@
-// Persistent fp64 kernels of the Gaussian i2c EM sweep for sm_100a.
+// Persistent fp64 kernels of the Gaussian i2c EM sweep for sm_100a (templates; instantiated once per environment
+// by i2c_env_inst.cu, one translation unit per env so that the build parallelises).
 //
 // One thread owns one problem for the whole launch: it runs the forward filter over the horizon, the
 // backward smoother (with the M-step statistics fused in), optionally the closed-loop propagate sweep,
@@ -13,6 +14,7 @@
 //   forward cell  i2c/i2c.py:350-447     backward cell  i2c/i2c.py:544-610
 //   propagate     i2c/i2c.py:150-199     M-step         i2c/i2c.py:1004-1065, 913-981
 //   quadrature    i2c/inference/quadrature.py:15-58, i2c/exp_types.py:36-49
+#pragma once
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -1835,20 +1837,6 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   return launch_em_v<Env, 1>(p, s, threads);
 }
 
-int launch_em(int env, const KParams& p, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  switch (env) {
-    case I2C_ENV_LINEAR: return launch_em_t<EnvLinear>(p, s);
-    case I2C_ENV_LINEAR_MIN_ENERGY: return launch_em_t<EnvLinearMinEnergy>(p, s);
-    case I2C_ENV_PENDULUM: return launch_em_t<EnvPendulum>(p, s);
-    case I2C_ENV_PENDULUM_ACT_REG: return launch_em_t<EnvPendulumActReg>(p, s);
-    case I2C_ENV_CARTPOLE: return launch_em_t<EnvCartpole>(p, s);
-    case I2C_ENV_DOUBLE_CARTPOLE: return launch_em_t<EnvDoubleCartpole>(p, s);
-    case I2C_ENV_QUADROTOR: return launch_em_t<EnvQuadrotor>(p, s);
-  }
-  return -1;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Stand-alone sigma-point transform: QuadratureInference.forward / forward_gaussian
 // (inference/quadrature.py:27-58) for the registered env maps.
@@ -1911,20 +1899,6 @@ static int launch_quad_t(int fn, const QuadArgs& a, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-int launch_quadrature(int env, int fn, const QuadArgs& a, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  switch (env) {
-    case I2C_ENV_LINEAR: return launch_quad_t<EnvLinear>(fn, a, s);
-    case I2C_ENV_LINEAR_MIN_ENERGY: return launch_quad_t<EnvLinearMinEnergy>(fn, a, s);
-    case I2C_ENV_PENDULUM: return launch_quad_t<EnvPendulum>(fn, a, s);
-    case I2C_ENV_PENDULUM_ACT_REG: return launch_quad_t<EnvPendulumActReg>(fn, a, s);
-    case I2C_ENV_CARTPOLE: return launch_quad_t<EnvCartpole>(fn, a, s);
-    case I2C_ENV_DOUBLE_CARTPOLE: return launch_quad_t<EnvDoubleCartpole>(fn, a, s);
-    case I2C_ENV_QUADROTOR: return launch_quad_t<EnvQuadrotor>(fn, a, s);
-  }
-  return -1;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Cubature Kalman filter step: PartiallyObservedMpcPolicy.filter (policy/mpc.py:125-145).
 template <class Env>
@@ -1981,14 +1955,15 @@ __global__ void __launch_bounds__(64) ckf_kernel(const __grid_constant__ CkfArgs
   if (!ok && a.status[tile * TILE + lane] == I2C_OK) a.status[tile * TILE + lane] = I2C_FAIL_CKF;
 }
 
-int launch_ckf(int env, const CkfArgs& a, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  int threads = 64, blocks = (a.ntiles * TILE + threads - 1) / threads;
-  switch (env) {
-    case I2C_ENV_QUADROTOR: ckf_kernel<EnvQuadrotor><<<blocks, threads, 0, s>>>(a); break;
-    default: return -2;  // only the quadrotor defines measure() (mpc_quad.py:371-383)
+template <class Env>
+static int launch_ckf_t(const CkfArgs& a, cudaStream_t s) {
+  if constexpr (Env::DY > 0) {
+    int threads = 64, blocks = (a.ntiles * TILE + threads - 1) / threads;
+    ckf_kernel<Env><<<blocks, threads, 0, s>>>(a);
+    return (int)cudaGetLastError();
+  } else {
+    return -2;  // only the quadrotor defines measure() (mpc_quad.py:371-383)
   }
-  return (int)cudaGetLastError();
 }
 
 }  // namespace i2c

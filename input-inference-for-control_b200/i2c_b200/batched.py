@@ -1,5 +1,5 @@
 """Batched Gaussian i2c on the GPU: thousands of independent trajectory-optimisation problems advanced by
-one persistent CUDA kernel per call (csrc/i2c_kernels.cu) through the C-ABI of include/i2c_b200.h.
+one persistent CUDA kernel per call (csrc/i2c_kernels.cuh) through the C-ABI of include/i2c_b200.h.
 
 ``BatchedI2c`` is the batched counterpart of the reference's ``I2cGraph`` (i2c/i2c.py:732-1401): same
 constructor arguments plus per-problem initial states, same method names for the sweeps, per-problem
