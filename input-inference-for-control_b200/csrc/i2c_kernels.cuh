@@ -67,6 +67,41 @@ __device__ __forceinline__ void stage_record(double* sdst, const double* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s0 + e * TILE * 8), "l"(gsrc + (size_t)e * TILE) : "memory");
 }
 __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+// ---- TMA-1D bulk copies (cp.async.bulk, SASS: UBLKCP): the record of one (cell, tile) is a single contiguous
+// E*256-byte block, so ONE elected lane moves it into the warp's staging buffer and every lane waits on the
+// buffer's mbarrier.  Replaces E LDGSTS instructions per thread and cell.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(double* sdst, const double* gsrc, unsigned bytes, uint64_t* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(b),
+      "r"(parity)
+      : "memory");
+}
+#ifdef I2C_NO_BULK
+constexpr bool kUseBulk = false;
+#else
+constexpr bool kUseBulk = true;
+#endif
+constexpr int kNumBars = 8;  // mbarriers per warp (>= deepest record pipeline)
 template <int N>
 __device__ __forceinline__ void stage_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -353,9 +388,12 @@ struct Carry {
   double m[DX], S[TRI(DX)], L[TRI(DX)], invd[DX];
 };
 
-// META: compile the staging of per-cell targets / flags in (latency-regime variant) or out (throughput variant)
+// META = latency-regime variant: per-cell targets / flags are staged with the records and the records move with
+// per-thread cp.async (lowest latency); throughput variant (META = false): records move with one TMA bulk copy per
+// warp and cell (fewest instructions), targets / flags are plain cached loads.
 template <class Env, bool META>
 struct Worker {
+  static constexpr bool BULK = kUseBulk && !META;
   using LY = Lay<Env>;
   static constexpr int DX = LY::DX, DU = LY::DU, N = LY::N, DZ = LY::DZ, DZT = LY::DZT;
   using TrigT = typename Env::TrigT;
@@ -369,9 +407,11 @@ struct Worker {
   double *prior, *post, *latest;
   bool own_alpha_valid;
   double* stage;  // this warp's double buffer: [2][E_STAGE][32], already offset by lane
+  uint64_t* bars; // this warp's mbarriers (bulk-copy completion), kNumBars of them
+  unsigned bar_phase;  // one parity bit per mbarrier
 
-  __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_)
-      : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_) {
+  __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_, uint64_t* bars_)
+      : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_), bars(bars_), bar_phase(0) {
     status = I2C_OK;
     info = 0;
     prior = p.prior;
@@ -438,6 +478,39 @@ struct Worker {
     if (flipped && p.tau > 0 && index <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
     return flags;
   }
+  // init of this warp's mbarriers (call once, all lanes)
+  __device__ __forceinline__ void pipe_init() {
+    if constexpr (BULK && LY::STAGED) {
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kNumBars; ++i) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __syncwarp();
+    }
+  }
+  // copy E elements x 32 lanes of a record into staging buffer `sbuf` (lane-offset pointers), completion on bars[bi]
+  template <int E>
+  __device__ __forceinline__ void rec_issue(double* sbuf, const double* grec, int bi) {
+    if constexpr (BULK) {
+      __syncwarp();  // every lane is done reading the buffer that is about to be overwritten
+      if (lane == 0) bulk_load(sbuf, grec, E * TILE * 8, bars + bi);
+    } else {
+      stage_record<E>(sbuf, grec);
+    }
+  }
+  __device__ __forceinline__ void rec_wait(int bi) {
+    if constexpr (BULK) {
+      mbar_wait(bars + bi, (bar_phase >> bi) & 1u);
+      bar_phase ^= 1u << bi;
+    }
+  }
+  // make this thread's earlier generic-proxy stores of records visible to later (async-proxy) bulk reads
+  __device__ __forceinline__ void rec_fence() {
+    __threadfence();
+    if constexpr (BULK) asm volatile("fence.proxy.async;" ::: "memory");
+  }
   // double-buffered record stream: issue the copy of cell `tn` (if valid) while cell `t` is consumed
   template <int E>
   __device__ __forceinline__ const double* stream(double* base_g, int Erec, int t, int tn, bool tn_valid) {
@@ -445,11 +518,12 @@ struct Worker {
       double* cur = stage + (t & 1) * (LY::E_STAGE_TOT * TILE);
       if (tn_valid) {
         double* nxt = stage + (tn & 1) * (LY::E_STAGE_TOT * TILE);
-        stage_record<E>(nxt, rec(base_g, tn, Erec));
+        rec_issue<E>(nxt, rec(base_g, tn, Erec), tn & 1);
         if (META && p.stage_meta) stage_meta(nxt, tn);
       }
       stage_commit();
       stage_wait<1>();
+      rec_wait(t & 1);
       return cur;
     } else {
       return rec(base_g, t, Erec);
@@ -457,10 +531,10 @@ struct Worker {
   }
   template <int E>
   __device__ __forceinline__ void stream_begin(double* base_g, int Erec, int t) {
-    __threadfence();  // records written by earlier sweeps of this thread are read back through cp.async
+    rec_fence();  // records written by earlier sweeps of this thread are read back through cp.async / bulk copies
     if constexpr (LY::STAGED) {
       double* nxt = stage + (t & 1) * (LY::E_STAGE_TOT * TILE);
-      stage_record<E>(nxt, rec(base_g, t, Erec));
+      rec_issue<E>(nxt, rec(base_g, t, Erec), t & 1);
       if (META && p.stage_meta) stage_meta(nxt, t);
       stage_commit();
     }
@@ -1534,6 +1608,7 @@ struct Worker {
   template <bool TEAM>
   __device__ void run_impl(const int w, const int W, double* red) {
     const bool main_warp = !TEAM || w == 0;
+    if (main_warp) pipe_init();
     const double HALF_LOG_2PIE = 1.4189385332046727;  // 0.5 * log(2 pi e)
     double alpha = p.alpha[b];
     const bool aux = p.phases & I2C_PH_STORE_AUX;
@@ -1578,19 +1653,22 @@ struct Worker {
             // ahead (a one-cell double buffer would expose the DRAM latency of every record)
             if constexpr (LY::STAGED) {
               constexpr int DEPTH = LY::TEAM_DEPTH;
-              __threadfence();
+              static_assert(DEPTH <= kNumBars, "not enough mbarriers");
+              rec_fence();
 #pragma unroll
               for (int k = 0; k < DEPTH; ++k) {
                 const int tt = T - 1 - k;
-                if (tt >= 0) stage_record<LY::E_FILT>(stage + (tt % DEPTH) * (LY::E_FILT * TILE), rec(p.filt, tt, LY::E_FILT));
+                if (tt >= 0)
+                  rec_issue<LY::E_FILT>(stage + (tt % DEPTH) * (LY::E_FILT * TILE), rec(p.filt, tt, LY::E_FILT), tt % DEPTH);
                 stage_commit();
               }
               for (int t = T - 1; t >= 0; --t) {
                 stage_wait<DEPTH - 1>();
+                rec_wait(t % DEPTH);
                 double* cur = stage + (t % DEPTH) * (LY::E_FILT * TILE);
                 double mu[N], Sig[TRI(N)];
                 backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
-                if (t - DEPTH >= 0) stage_record<LY::E_FILT>(cur, rec(p.filt, t - DEPTH, LY::E_FILT));
+                if (t - DEPTH >= 0) rec_issue<LY::E_FILT>(cur, rec(p.filt, t - DEPTH, LY::E_FILT), t % DEPTH);
                 stage_commit();
               }
               stage_wait<0>();
@@ -1766,14 +1844,15 @@ struct Worker {
 // MINB = minimum resident 128-thread blocks per SM: 1 lets ptxas use up to 255 registers (best per-warp latency,
 // used when the batch cannot fill the machine anyway); 4 caps the kernel at 128 registers so that 16 warps per SM
 // are resident (throughput regime, small envs only).
-template <class Env, int MINB>
+template <class Env, int MINB, bool LAT>
 __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ KParams pin) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / TILE;
   const int lane = threadIdx.x % TILE;
   if (warp >= pin.ntiles) return;
-  extern __shared__ __align__(16) double stage_smem[];
-  double* stage = stage_smem + (size_t)(threadIdx.x / TILE) * (2 * Lay<Env>::E_STAGE_TOT * TILE) + lane;
-  Worker<Env, MINB == 1> w(pin, warp, lane, stage);
+  extern __shared__ __align__(128) double stage_smem[];
+  constexpr int PER_WARP = 2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars;  // staging buffers + mbarriers
+  double* base = stage_smem + (size_t)(threadIdx.x / TILE) * PER_WARP;
+  Worker<Env, LAT> w(pin, warp, lane, base + lane, reinterpret_cast<uint64_t*>(base + 2 * Lay<Env>::E_STAGE_TOT * TILE));
   w.run();
 }
 
@@ -1781,15 +1860,16 @@ __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ K
 template <class Env, int W>
 __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_constant__ KParams pin) {
   const int w = threadIdx.x / TILE, lane = threadIdx.x % TILE;
-  extern __shared__ __align__(16) double stage_smem[];
-  double* red = stage_smem + Lay<Env>::E_TEAM_STAGE * TILE;
-  Worker<Env, true> wk(pin, blockIdx.x, lane, stage_smem + lane);
+  extern __shared__ __align__(128) double stage_smem[];
+  double* red = stage_smem + Lay<Env>::E_TEAM_STAGE * TILE + kNumBars;
+  Worker<Env, true> wk(pin, blockIdx.x, lane, stage_smem + lane,
+                       reinterpret_cast<uint64_t*>(stage_smem + Lay<Env>::E_TEAM_STAGE * TILE));
   wk.template run_impl<true>(w, W, red);
 }
 
 template <class Env, int W>
 static int launch_em_team(const KParams& p, cudaStream_t s) {
-  const size_t smem = (size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE * sizeof(double);
+  const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(em_team_kernel<Env, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1802,22 +1882,22 @@ static int launch_em_team(const KParams& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-template <class Env, int MINB>
+template <class Env, int MINB, bool LAT>
 static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
   int wpb = threads / TILE;
   int blocks = (p.ntiles + wpb - 1) / wpb;
-  const size_t smem = Lay<Env>::STAGED ? (size_t)wpb * 2 * Lay<Env>::E_STAGE_TOT * TILE * sizeof(double) : 0;
+  const size_t smem = Lay<Env>::STAGED ? (size_t)wpb * (2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars) * sizeof(double) : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env, MINB, LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   KParams q = p;
   // staging the per-cell targets / flags removes their exposed load latency when a warp is alone on its
   // sub-partition; in the throughput regime the extra LDGSTS instructions cost more than they hide
-  q.stage_meta = Lay<Env>::STAGED && p.ntiles < 148 * 8;
-  em_kernel<Env, MINB><<<blocks, threads, smem, s>>>(q);
+  q.stage_meta = Lay<Env>::STAGED && LAT;
+  em_kernel<Env, MINB, LAT><<<blocks, threads, smem, s>>>(q);
   return (int)cudaGetLastError();
 }
 
@@ -1832,9 +1912,11 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   if (p.ntiles <= 296 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 4>(p, s);  // two blocks per SM
   if constexpr (Lay<Env>::N <= 3) {
     // small envs fit 128 registers with a few bytes of spill: worth it once >= 12 warps per SM are available
-    if (p.ntiles >= 148 * 12) return launch_em_v<Env, 4>(p, s, 128);
+    if (p.ntiles >= 148 * 12) return launch_em_v<Env, 4, false>(p, s, 128);
   }
-  return launch_em_v<Env, 1>(p, s, threads);
+  // fewer than 4 warps per SM: every warp is latency-bound -> cp.async + staged targets; else TMA bulk copies
+  if (p.ntiles < 148 * 4) return launch_em_v<Env, 1, true>(p, s, threads);
+  return launch_em_v<Env, 1, false>(p, s, threads);
 }
 
 // ------------------------------------------------------------------------------------------------
