@@ -222,6 +222,20 @@ int i2c_quadrature(int32_t env, int32_t fn, int32_t n_problems, const double* m,
                    double quad_alpha, double quad_beta, double quad_kappa, const double* env_par,
                    double* m_y, double* S_y, double* S_xy, int32_t* status, int32_t device);
 
+/* Batched stochastic closed-loop evaluation of the extracted controllers == BaseSim.run / batch_eval
+ * (i2c/env.py:40-103; BaseKnownSim.forward :180-187) under TimeIndexedLinearGaussianPolicy /
+ * ExpertTimeIndexedLinearGaussianPolicy (i2c/policy/linear.py:31-43, 73-90): n_rollouts roll-outs of every problem's
+ * controller in one launch.  x_init[B][R][dx]; K[B][T][du][dx], k[B][T][du]; sigK[B][T][du][du] or NULL (deterministic
+ * action); expert_mu[B][T][dx] + expert_lam[B][T][dx][dx] or NULL (plain linear policy), soft_expert: exp(-e) vs hard
+ * gate; eta[B][R][T][dx] = process disturbances to add (parity runs) or NULL: drawn on the device (Philox, `seed`) from
+ * N(0, sig_eta[dx][dx]); eps_u[B][R][T][du] standard normals for the action noise or NULL (device RNG).
+ * Outputs: xu[B][R][T][dx+du] (state before the step and action), z[B][R][T][dz], z_term[B][R][dzt] (may be NULL),
+ * x_final[B][R][dx] (state after the last step, may be NULL). */
+int i2c_rollout(int32_t env, int32_t n_problems, int32_t n_rollouts, int32_t horizon, const double* x_init,
+                const double* K, const double* k, const double* sigK, const double* expert_mu, const double* expert_lam,
+                int32_t soft_expert, const double* eta, const double* eps_u, const double* sig_eta, uint64_t seed,
+                const double* env_par, double* xu, double* z, double* z_term, double* x_final, int32_t device);
+
 /* Snapshot / restore of the whole device state (deepcopy / dill pickling of the graph:
  * i2c.py:1392-1401, policy/mpc.py:24-26). */
 int i2c_snapshot_bytes(i2c_handle_t h, size_t* bytes);

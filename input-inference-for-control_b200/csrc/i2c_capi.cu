@@ -19,7 +19,8 @@ namespace i2c {
 #define I2C_DECL_ENV(k)                                                   \
   int launch_em_env##k(const KParams& p, void* stream);                   \
   int launch_quad_env##k(int fn, const QuadArgs& a, void* stream);        \
-  int launch_ckf_env##k(const CkfArgs& a, void* stream);
+  int launch_ckf_env##k(const CkfArgs& a, void* stream);              \
+  int launch_rollout_env##k(const RolloutArgs& a, void* stream);
 I2C_DECL_ENV(0) I2C_DECL_ENV(1) I2C_DECL_ENV(2) I2C_DECL_ENV(3) I2C_DECL_ENV(4) I2C_DECL_ENV(5) I2C_DECL_ENV(6)
 #undef I2C_DECL_ENV
 
@@ -47,6 +48,11 @@ int launch_quadrature(int env, int fn, const QuadArgs& a, void* stream) {
 }
 int launch_ckf(int env, const CkfArgs& a, void* stream) {
 #define CALL(k) launch_ckf_env##k(a, stream)
+  I2C_SWITCH_ENV(env, CALL)
+#undef CALL
+}
+int launch_rollout(int env, const RolloutArgs& a, void* stream) {
+#define CALL(k) launch_rollout_env##k(a, stream)
   I2C_SWITCH_ENV(env, CALL)
 #undef CALL
 }
@@ -1117,6 +1123,71 @@ int i2c_restore(i2c_handle_t h, const void* host_buf, size_t bytes) {
   CUDA_OK(cudaMemcpyAsync(h->ws, p, h->ws_bytes, cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
+}
+
+int i2c_rollout(int32_t env, int32_t n_problems, int32_t n_rollouts, int32_t horizon, const double* x_init,
+                const double* K, const double* k, const double* sigK, const double* expert_mu, const double* expert_lam,
+                int32_t soft_expert, const double* eta, const double* eps_u, const double* sig_eta, uint64_t seed,
+                const double* env_par, double* xu, double* z, double* z_term, double* x_final, int32_t device) {
+  REQUIRE(env >= 0 && env < I2C_ENV_COUNT, "unknown env id (no CPU fallback for unregistered envs)");
+  REQUIRE(n_problems >= 1 && n_rollouts >= 1 && horizon >= 1 && x_init && K && k && xu && z, "bad argument");
+  REQUIRE((expert_mu == nullptr) == (expert_lam == nullptr), "expert policy needs both mu and lam");
+  const EnvDims& d = kEnv[env];
+  REQUIRE(d.np == 0 || env_par, "this env needs env_par");
+  REQUIRE(eta || sig_eta, "give either the disturbances eta or sig_eta for the device RNG (zero matrix = noise free)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_err(-2, "no CUDA device available: the i2c hot path has no CPU fallback");
+  CUDA_OK(cudaSetDevice(device));
+  const size_t B = n_problems, R = n_rollouts, T = horizon, dx = d.dx, du = d.du, n = dx + du, dz = d.dz, dzt = d.dzt;
+  const size_t np = d.np > 0 ? d.np : 0;
+  RolloutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = n_problems, a.R = n_rollouts, a.T = horizon, a.soft_expert = soft_expert, a.seed = seed;
+  a.hard_threshold = 3.0;  // ExpertTimeIndexedLinearGaussianPolicy.hard_exp_threshold (policy/linear.py:48)
+  if (!eta) {
+    std::vector<double> L(sig_eta, sig_eta + dx * dx);
+    bool zero = true;
+    for (double v : L) zero = zero && v == 0.0;
+    a.noise_free = zero;
+    if (!zero) {
+      REQUIRE(host_chol(L, (int)dx), "sig_eta must be positive definite");
+      for (size_t i = 0; i < dx; ++i)
+        for (size_t j = 0; j <= i; ++j) a.chol_eta[i * (i + 1) / 2 + j] = L[i * dx + j];
+    }
+  }
+  struct Buf { const double* host; size_t elems; const double** dev; };
+  const size_t sizes_in[9] = {B * R * dx, B * T * du * dx, B * T * du, sigK ? B * T * du * du : 0, expert_mu ? B * T * dx : 0,
+                              expert_lam ? B * T * dx * dx : 0, eta ? B * R * T * dx : 0, eps_u ? B * R * T * du : 0, B * np};
+  const double* hosts[9] = {x_init, K, k, sigK, expert_mu, expert_lam, eta, eps_u, env_par};
+  const double** devs[9] = {&a.x_init, &a.K, &a.k, &a.sigK, &a.ex_mu, &a.ex_lam, &a.eta, &a.eps_u, &a.envpar};
+  const size_t n_xu = B * R * T * n, n_z = B * R * T * dz, n_zt = B * R * dzt, n_xf = B * R * dx;
+  size_t total = n_xu + n_z + n_zt + n_xf;
+  for (size_t v : sizes_in) total += v;
+  double* buf = nullptr;
+  CUDA_OK(cudaMalloc((void**)&buf, total * 8));
+  size_t off = 0;
+  int rc = 0;
+  for (int i = 0; i < 9 && rc == 0; ++i) {
+    if (sizes_in[i] == 0) continue;
+    *devs[i] = buf + off;
+    if (cudaMemcpy(buf + off, hosts[i], sizes_in[i] * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = set_err(-3, "H2D copy failed");
+    off += sizes_in[i];
+  }
+  a.xu = buf + off, a.z = a.xu + n_xu, a.z_term = a.z + n_z, a.x_final = a.z_term + n_zt;
+  if (rc == 0) {
+    int lrc = launch_rollout(env, a, nullptr);
+    if (lrc != 0) rc = set_err(-100 - lrc, "rollout kernel launch failed");
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpy(xu, a.xu, n_xu * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(z, a.z, n_z * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && z_term && kHasTerm[env]) e = cudaMemcpy(z_term, a.z_term, n_zt * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && x_final) e = cudaMemcpy(x_final, a.x_final, n_xf * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = set_err(-100 - (int)e, std::string("rollout: ") + cudaGetErrorString(e));
+  }
+  cudaFree(buf);
+  return rc;
 }
 
 int i2c_dfma_peak(int32_t device, double* tflops) {

@@ -31,5 +31,8 @@ int I2C_CAT(launch_quad_env, I2C_ENV_ID)(int fn, const QuadArgs& a, void* stream
   return launch_quad_t<EnvT>(fn, a, (cudaStream_t)stream);
 }
 int I2C_CAT(launch_ckf_env, I2C_ENV_ID)(const CkfArgs& a, void* stream) { return launch_ckf_t<EnvT>(a, (cudaStream_t)stream); }
+int I2C_CAT(launch_rollout_env, I2C_ENV_ID)(const RolloutArgs& a, void* stream) {
+  return launch_rollout_t<EnvT>(a, (cudaStream_t)stream);
+}
 
 }  // namespace i2c

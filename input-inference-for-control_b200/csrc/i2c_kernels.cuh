@@ -16,6 +16,7 @@
 //   quadrature    i2c/inference/quadrature.py:15-58, i2c/exp_types.py:36-49
 #pragma once
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 #include <math.h>
 
 #include "envs.cuh"
@@ -2046,6 +2047,112 @@ static int launch_ckf_t(const CkfArgs& a, cudaStream_t s) {
   } else {
     return -2;  // only the quadrotor defines measure() (mpc_quad.py:371-383)
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched stochastic closed-loop evaluation of time-indexed linear-Gaussian controllers:
+// BaseSim.run / batch_eval (i2c/env.py:40-103) with BaseKnownSim.forward (:180-187) under
+// TimeIndexedLinearGaussianPolicy / ExpertTimeIndexedLinearGaussianPolicy (i2c/policy/linear.py:31-43, 73-90).
+// One thread per (problem, roll-out); SURVEY.md 8(f) row 1.
+template <class Env>
+__global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+  constexpr int DX = Env::DX, DU = Env::DU, N = DX + DU, DZ = Env::DZ, DZT = Env::DZT;
+  const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (id >= (long long)a.B * a.R) return;
+  const int b = (int)(id / a.R);
+  double par[Env::NP > 0 ? Env::NP : 1];
+#pragma unroll
+  for (int i = 0; i < Env::NP; ++i) par[i] = a.envpar[(size_t)b * Env::NP + i];
+  curandStatePhilox4_32_10_t rng;
+  const bool need_rng = (!a.eta && !a.noise_free) || (a.sigK && !a.eps_u);
+  if (need_rng) curand_init(a.seed, (unsigned long long)id, 0, &rng);
+  typename Env::TrigT ctx;
+  double xu[N];
+#pragma unroll
+  for (int i = 0; i < DX; ++i) xu[i] = a.x_init[(size_t)id * DX + i];
+  for (int t = 0; t < a.T; ++t) {
+    const size_t bt = (size_t)b * a.T + t;
+    const double* K = a.K + bt * DU * DX;
+    double gate = 1.0, d[DX];
+    if (a.ex_mu) {  // expert policy: u = k + p K (x - mu), p = exp(-e) or [|e| < threshold], e = 1/2 d^T lam d
+      double e = 0.0;
+#pragma unroll
+      for (int i = 0; i < DX; ++i) d[i] = xu[i] - a.ex_mu[bt * DX + i];
+#pragma unroll
+      for (int i = 0; i < DX; ++i)
+#pragma unroll
+        for (int j = 0; j < DX; ++j) e = fma(d[i] * a.ex_lam[(bt * DX + i) * DX + j], d[j], e);
+      e *= 0.5;
+      gate = a.soft_expert ? exp(-e) : (fabs(e) < a.hard_threshold ? 1.0 : 0.0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DX; ++i) d[i] = xu[i];
+    }
+    double u[DU];
+#pragma unroll
+    for (int r = 0; r < DU; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < DX; ++i) s = fma(K[r * DX + i], d[i], s);
+      u[r] = fma(gate, s, a.k[bt * DU + r]);
+    }
+    if (a.sigK) {  // sample the action: u += chol(sig_k) eps
+      double Ls[TRI(DU)], iv[DU], eps[DU];
+#pragma unroll
+      for (int r = 0; r < DU; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) Ls[tix(r, q)] = a.sigK[(bt * DU + r) * DU + q];
+      const bool pd = chol_rows<DU>(Ls, iv);
+#pragma unroll
+      for (int r = 0; r < DU; ++r) eps[r] = a.eps_u ? a.eps_u[((size_t)id * a.T + t) * DU + r] : curand_normal_double(&rng);
+      if (pd) {
+#pragma unroll
+        for (int r = 0; r < DU; ++r)
+#pragma unroll
+          for (int q = 0; q <= r; ++q) u[r] = fma(Ls[tix(r, q)], eps[q], u[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < DU; ++r) xu[DX + r] = u[r];
+    double* oxu = a.xu + ((size_t)id * a.T + t) * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) oxu[i] = xu[i];
+    double zz[DZ];
+    Env::obs(xu, 0, ctx, zz);
+#pragma unroll
+    for (int i = 0; i < DZ; ++i) a.z[((size_t)id * a.T + t) * DZ + i] = zz[i];
+    double xn[DX];
+    Env::dyn(xu, 0, ctx, par, xn);
+    if (a.eta) {
+#pragma unroll
+      for (int i = 0; i < DX; ++i) xn[i] += a.eta[((size_t)id * a.T + t) * DX + i];
+    } else if (!a.noise_free) {
+      double eps[DX];
+#pragma unroll
+      for (int i = 0; i < DX; ++i) eps[i] = curand_normal_double(&rng);
+#pragma unroll
+      for (int i = 0; i < DX; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) xn[i] = fma(a.chol_eta[tix(i, j)], eps[j], xn[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < DX; ++i) xu[i] = xn[i];
+  }
+#pragma unroll
+  for (int i = 0; i < DX; ++i) a.x_final[(size_t)id * DX + i] = xu[i];
+  if (Env::HAS_TERM) {
+    double zt[DZT];
+    Env::obs_term(xu, 0, ctx, zt);
+#pragma unroll
+    for (int i = 0; i < DZT; ++i) a.z_term[(size_t)id * DZT + i] = zt[i];
+  }
+}
+
+template <class Env>
+static int launch_rollout_t(const RolloutArgs& a, cudaStream_t s) {
+  const long long n = (long long)a.B * a.R;
+  rollout_kernel<Env><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+  return (int)cudaGetLastError();
 }
 
 }  // namespace i2c

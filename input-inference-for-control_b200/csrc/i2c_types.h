@@ -104,4 +104,26 @@ struct CkfArgs {
 };
 int launch_ckf(int env, const CkfArgs& a, void* stream);
 
+// batched closed-loop policy evaluation (canonical layouts, one thread per (problem, roll-out))
+struct RolloutArgs {
+  const double* x_init;  // [B][R][dx]
+  const double* K;       // [B][T][du][dx]
+  const double* k;       // [B][T][du]
+  const double* sigK;    // [B][T][du][du] or NULL (deterministic policy)
+  const double* ex_mu;   // [B][T][dx]     expert gating centre or NULL
+  const double* ex_lam;  // [B][T][dx][dx] expert gating precision or NULL
+  const double* eta;     // [B][R][T][dx]  process disturbances (already coloured) or NULL -> device RNG
+  const double* eps_u;   // [B][R][T][du]  standard normals for action sampling or NULL -> device RNG (if sigK)
+  const double* envpar;  // [B][NP] or NULL
+  double* xu;            // [B][R][T][n]
+  double* z;             // [B][R][T][dz]
+  double* z_term;        // [B][R][dzt]
+  double* x_final;       // [B][R][dx] state after the last step
+  int32_t B, R, T, soft_expert, noise_free;
+  uint64_t seed;
+  double hard_threshold;
+  double chol_eta[MAX_DX * (MAX_DX + 1) / 2];  // lower Cholesky factor of sig_eta (device RNG path)
+};
+int launch_rollout(int env, const RolloutArgs& a, void* stream);
+
 }  // namespace i2c

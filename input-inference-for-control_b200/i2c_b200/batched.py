@@ -357,3 +357,42 @@ def quadrature(env, fn, m, S, quad=(1.0, 0.0, 0.0), env_par=None, device=0):
     capi.check(L.i2c_quadrature(env_id, fn_id, B, capi.ptr(m), capi.ptr(S), *map(float, quad), capi.ptr(env_par),
                                 capi.ptr(my), capi.ptr(Sy), capi.ptr(Sxy), capi.ptr(st), device))
     return my, Sy, Sxy, st
+
+
+def rollout(env, x_init, K, k, sig_k=None, expert=None, soft_expert=True, eta=None, eps_u=None, sig_eta=None, seed=0,
+            env_par=None, device=0, return_final=False):
+    """Batched stochastic closed-loop evaluation of time-indexed linear-Gaussian controllers on the GPU
+    (BaseSim.run / batch_eval, i2c/env.py:40-103, for all problems and roll-outs in one launch).
+
+    x_init [B,R,dx]; K [B,T,du,dx], k [B,T,du]; sig_k [B,T,du,du] -> stochastic actions; expert = (mu [B,T,dx],
+    lam [B,T,dx,dx]) -> ExpertTimeIndexedLinearGaussianPolicy; eta [B,R,T,dx] disturbances to add (else drawn on the
+    device from N(0, sig_eta), default the env's); eps_u [B,R,T,du] standard normals for the action noise.
+    Returns xu [B,R,T,dx+du], z [B,R,T,dz], z_term [B,R,dzt]."""
+    L = capi.lib()
+    env_id = capi.ENV_IDS[env]
+    dx, du, dz, dzt, n_par, _ = capi.env_dims(env_id)
+    e = _envs.make(env)
+    x_init = capi.f64(x_init)
+    B, R = x_init.shape[:2]
+    K = capi.f64(K)
+    T = K.shape[1]
+    K = capi.f64(K, (B, T, du, dx))
+    k = capi.f64(k, (B, T, du))
+    x_init = capi.f64(x_init, (B, R, dx))
+    sig_k = None if sig_k is None else capi.f64(sig_k, (B, T, du, du))
+    mu = lam = None
+    if expert is not None:
+        mu, lam = capi.f64(expert[0], (B, T, dx)), capi.f64(expert[1], (B, T, dx, dx))
+    eta = None if eta is None else capi.f64(eta, (B, R, T, dx))
+    eps_u = None if eps_u is None else capi.f64(eps_u, (B, R, T, du))
+    sig_eta = capi.f64(e.sig_eta if sig_eta is None else sig_eta, (dx, dx))
+    if n_par:
+        if env_par is None:
+            env_par = _envs.linear_params(e.A, e.B, e.a)
+        env_par = capi.f64(np.broadcast_to(env_par, (B, n_par)).copy())
+    xu, z, zt = np.empty((B, R, T, dx + du)), np.empty((B, R, T, dz)), np.empty((B, R, dzt))
+    xf = np.empty((B, R, dx))
+    p = capi.ptr
+    capi.check(L.i2c_rollout(env_id, B, R, T, p(x_init), p(K), p(k), p(sig_k), p(mu), p(lam), int(bool(soft_expert)), p(eta),
+                             p(eps_u), p(sig_eta), int(seed), p(env_par), p(xu), p(z), p(zt), p(xf), device))
+    return (xu, z, zt, xf) if return_final else (xu, z, zt)

@@ -164,3 +164,44 @@ def test_mpc_quad_flow(mirror, mode):
         assert relerr(u[:, 0], g["u"][t]) < 1e-6, t
         assert relerr(policy.mus[-1][:, 0], g["mu"][t]) < 1e-7, t
         assert relerr(policy.xu_history[-1][:, :, 0], g["plan"][t]) < 1e-6, t
+
+
+def test_env_batch_eval_mirror(mirror):
+    """scripts/i2c_run.py:96-106: evaluate the extracted controllers in the simulator after every EM iteration."""
+    import types
+
+    from i2c.env import make_env
+
+    g = golden("pendulum_known_quad_seed0")
+    exp = types.SimpleNamespace(ENVIRONMENT="PendulumKnown", N_DURATION=100)
+    env = make_env(exp)
+    model = mirror.make_env_model("PendulumKnown", None)
+    i2c = mirror.I2cGraph(model, 100, g["Q"], g["R"], g["Qf"], 100, 0.0, g["mu_u"], g["sig_u"], None, None,
+                          mirror.CubatureQuadrature(1, 0, 0))
+    i2c.learn_msgs(60)
+    policy_linear = mirror.TimeIndexedLinearGaussianPolicy(0.0 * np.eye(1), 100, 1, 2)
+    policy_linear.write(*i2c.get_local_linear_policy())
+    np.random.seed(0)
+    xs, ys, zs, zs_term = env.batch_eval(policy_linear, 10)
+    assert len(xs) == 10 and xs[0].shape == (100, 3) and ys[0].shape == (100, 2) and zs[0].shape == (100, 4)
+    assert zs_term[0].shape == (1, 3)
+    # the closed loop follows the plan: realised trajectory close to the smoothed one
+    plan = i2c.get_marginal_trajectory()
+    assert np.max(np.abs(np.mean(xs, axis=0)[:, :2] - plan[:, :2])) < 0.5
+    # host loop over the same controller reproduces a roll-out (same disturbances via the seed)
+    np.random.seed(1)
+    x1, y1, z1, zt1 = env.run(policy_linear)
+    np.random.seed(1)
+    eta = np.random.multivariate_normal(np.zeros(2), env.sig_eta, (1, 1, 100))[0, 0]
+    x = np.asarray(model.x0, float)[:, 0].copy()
+    from oracle import envs as E
+
+    sys_ = E.Pendulum()
+    for t in range(100):
+        u = policy_linear(t, x[:, None])[:, 0]
+        assert np.allclose(x1[t], np.concatenate((x, u)), rtol=0, atol=1e-9)
+        x = sys_.dynamics(np.concatenate((x, u))) + eta[t]
+    policy = mirror.ExpertTimeIndexedLinearGaussianPolicy(0.0 * np.eye(1), 100, 1, 2, soft=False)
+    policy.write(*i2c.get_local_expert_linear_policy())
+    xs, ys, zs, zs_term = env.batch_eval(policy, 4, deterministic=False)
+    assert np.all(np.isfinite(np.asarray(xs)))
