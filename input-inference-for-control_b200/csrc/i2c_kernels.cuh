@@ -559,18 +559,27 @@ struct Worker {
 
   // exp(-1/2 d^T C^-1 d): the pdf ratio w/Z of i2c.py:369-374 (scipy multivariate_normal)
   __device__ __forceinline__ bool pdf_ratio(const double* C_in, const double* d_in, double& rho) {
-    double C[TRI(DX)], invd[DX], d[DX];
+    if constexpr (DX == 2) {
+      // closed form for 2x2 (one reciprocal instead of two dependent rsqrt pivots on the critical path)
+      const double c00 = C_in[0], c10 = C_in[1], c11 = C_in[2];
+      const double det = fma(c00, c11, -c10 * c10);
+      const double q = fma(c11 * d_in[0], d_in[0], fma(-2.0 * c10 * d_in[0], d_in[1], c00 * d_in[1] * d_in[1])) * fast_rcp(det);
+      rho = exp(-0.5 * q);
+      return (c00 > 0.0) && (det > 0.0) && (det < 1.0e300);
+    } else {
+      double C[TRI(DX)], invd[DX], d[DX];
 #pragma unroll
-    for (int i = 0; i < TRI(DX); ++i) C[i] = C_in[i];
+      for (int i = 0; i < TRI(DX); ++i) C[i] = C_in[i];
 #pragma unroll
-    for (int i = 0; i < DX; ++i) d[i] = d_in[i];
-    bool ok = chol_rows<DX>(C, invd);
-    fwd_subst<DX>(C, invd, d);
-    double q = 0.0;
+      for (int i = 0; i < DX; ++i) d[i] = d_in[i];
+      bool ok = chol_rows<DX>(C, invd);
+      fwd_subst<DX>(C, invd, d);
+      double q = 0.0;
 #pragma unroll
-    for (int i = 0; i < DX; ++i) q = fma(d[i], d[i], q);
-    rho = exp(-0.5 * q);
-    return ok;
+      for (int i = 0; i < DX; ++i) q = fma(d[i], d[i], q);
+      rho = exp(-0.5 * q);
+      return ok;
+    }
   }
 
   // Joint (x,u) Gaussian under a linear-Gaussian controller around the incoming state message:

@@ -127,9 +127,13 @@ struct LogAcc {
   int e;
   __device__ __forceinline__ void reset() { m = 1.0; e = 0; }
   __device__ __forceinline__ void mul(double x) {
-    int ex;
-    m = frexp(m * x, &ex);
-    e += ex;
+    m *= x;
+    // renormalise only when the running product leaves a safe range (pivots are ~1e-6 .. 1e3: rarely taken)
+    if (!(m > 1.0e-150 && m < 1.0e150)) {
+      int ex;
+      m = frexp(m, &ex);
+      e += ex;
+    }
   }
   __device__ __forceinline__ double value() const { return log(m) + 0.6931471805599453 * (double)e; }
 };
