@@ -207,21 +207,27 @@ def run_cuda(args, rank, world, local_rank):
     pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
     h_x0, h_s0 = pin(B, 2), pin(B, 2, 2)
     h_x0[:], h_s0[:] = g.x0, g.sig_x0
-    h_K, h_k, h_s, h_m = pin(B, T, 1, 2), pin(B, T, 1), pin(B, T, 1, 1), pin(1, B)
+    h_m = pin(1, B)
+    # double-buffered pinned result arrays: the controller copy of step i overlaps the sweep of step i+1
+    h_pol = [(pin(B, T, 1, 2), pin(B, T, 1), pin(B, T, 1, 1)) for _ in range(2)]
+    h_K, h_k, h_s = h_pol[0]
     L = g.lib
 
-    def e2e_step():
+    def e2e_step(i):
         capi.check(L.i2c_set_initial_state(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))
         capi.check(L.i2c_run(g._h, 1, capi.PH_LEARN))
         for m in ("alpha", "cost_m"):
             capi.check(L.i2c_get_metric(g._h, capi.METRICS[m], capi.ptr(h_m), 1))
-        capi.check(L.i2c_get_policy(g._h, capi.ptr(h_K), capi.ptr(h_k), capi.ptr(h_s)))
+        bK, bk, bs = h_pol[i & 1]
+        capi.check(L.i2c_get_policy_async(g._h, capi.ptr(bK), capi.ptr(bk), capi.ptr(bs)))
 
-    e2e_step()
+    e2e_step(0)
+    capi.check(L.i2c_copy_wait(g._h))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
+    for i in range(Ke):
+        e2e_step(i)
+    capi.check(L.i2c_copy_wait(g._h))
     if dist is not None:
         # the path's only collective: final gather of controllers and costs over NVLink
         from i2c_b200 import dist as idist
@@ -265,7 +271,9 @@ def run_cuda(args, rank, world, local_rank):
                    "failed_problems": n_fail},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "what": "per step: H2D start-state belief, one learn_msgs, D2H cost+alpha per problem and K,k,sigK"
+                "what": "per step: H2D start-state belief, one learn_msgs, D2H cost+alpha per problem (sync) and K,k,sigK "
+                        "(i2c_get_policy_async into double-buffered pinned arrays: the copy overlaps the next step; all "
+                        "copies complete inside the timed region)"
                         + ("; + final NCCL all_gather of controllers" if world > 1 else "")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

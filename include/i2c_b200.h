@@ -198,6 +198,11 @@ int i2c_field_shape(i2c_handle_t h, int32_t field, int32_t* rows, int32_t* cols)
 /* Controller extraction == I2cGraph.get_local_linear_policy (i2c.py:1253-1264):
  * K[B][H][du][dx], k[B][H][du], sigK[B][H][du][du]; any pointer may be NULL. */
 int i2c_get_policy(i2c_handle_t h, double* K, double* k, double* sigK);
+/* Asynchronous variant: the controllers of the latest sweep are converted on the compute stream and copied to
+ * (ideally pinned) host arrays on a separate copy stream, so the transfer overlaps the next i2c_run; the arrays are
+ * valid after i2c_copy_wait().  One transfer may be in flight per handle. */
+int i2c_get_policy_async(i2c_handle_t h, double* K, double* k, double* sigK);
+int i2c_copy_wait(i2c_handle_t h);
 /* Same, into DEVICE buffers in canonical layout (for the NCCL gather of controllers). */
 int i2c_get_policy_dev(i2c_handle_t h, double* K_dev, double* k_dev, double* sigK_dev);
 

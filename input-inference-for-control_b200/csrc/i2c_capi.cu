@@ -96,7 +96,7 @@ struct i2c_handle_s {
   size_t ws_bytes;
   // device buffers (inside ws)
   double *recA, *recB, *filt, *auxf, *auxb, *pf, *ric, *term, *x0, *sig_x0, *alpha, *alpha_cell, *z_cell, *z_term_pp, *envpar, *metrics,
-      *scratch;
+      *scratch, *policy_out;
   int32_t *cell_flags_dev, *cell_index_dev, *status, *info;
   size_t scratch_elems;
   // host state
@@ -109,7 +109,9 @@ struct i2c_handle_s {
   KParams kp;  // constants + pointers template
   int last_n_iter;
   long long launches;
-  cudaEvent_t ev0, ev1;
+  cudaEvent_t ev0, ev1, ev_unpacked, ev_copied;
+  cudaStream_t copy_stream;
+  bool copy_pending;
   bool problem_set;
   bool has_z_term_pp;
   std::vector<double> mu_u_init_last, sig_u_host;
@@ -221,7 +223,7 @@ static inline int nblocks(size_t total) {
 
 // ----------------------------------------------------------------------------------------- layout
 struct WsLayout {
-  size_t recA, recB, filt, auxf, auxb, pf, ric, term, x0, sig_x0, alpha, alpha_cell, z_cell, z_term_pp, envpar, metrics, scratch, flags,
+  size_t recA, recB, filt, auxf, auxb, pf, ric, term, x0, sig_x0, alpha, alpha_cell, z_cell, z_term_pp, envpar, metrics, scratch, policy_out, flags,
       index, status, info, total, scratch_elems;
 };
 
@@ -256,6 +258,7 @@ static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
   if ((size_t)(d.dz * d.dz) > big) big = d.dz * d.dz;
   w.scratch_elems = Bpad * T * big;
   w.scratch = take(w.scratch_elems, 8);
+  w.policy_out = take(Bpad * T * (size_t)(d.du * d.dx + d.du + d.du * d.du), 8);
   w.flags = take(T, 4);
   w.index = take(T, 4);
   w.status = take(Bpad, 4);
@@ -356,6 +359,7 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
   h->metrics = (double*)(h->ws + w.metrics);
   h->scratch = (double*)(h->ws + w.scratch);
   h->scratch_elems = w.scratch_elems;
+  h->policy_out = (double*)(h->ws + w.policy_out);
   h->cell_flags_dev = (int32_t*)(h->ws + w.flags);
   h->cell_index_dev = (int32_t*)(h->ws + w.index);
   h->status = (int32_t*)(h->ws + w.status);
@@ -366,6 +370,10 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
   h->cell_head = 0;
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  cudaEventCreateWithFlags(&h->ev_unpacked, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  h->copy_pending = false;
   CUDA_OK(cudaMemsetAsync(h->ws, 0, w.total, h->stream));
   *out = h;
   return 0;
@@ -374,8 +382,12 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
 int i2c_destroy(i2c_handle_t h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->copy_stream);
+  cudaStreamDestroy(h->copy_stream);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->ev_unpacked);
+  cudaEventDestroy(h->ev_copied);
   if (h->own_ws) cudaFree(h->ws);
   delete h;
   return 0;
@@ -900,6 +912,40 @@ int i2c_get_policy_dev(i2c_handle_t h, double* K_dev, double* k_dev, double* sig
     h->launches++;
     CUDA_OK(cudaGetLastError());
   }
+  return 0;
+}
+
+int i2c_get_policy_async(i2c_handle_t h, double* K, double* k, double* sigK) {
+  REQUIRE(h && K && k && sigK, "NULL argument");
+  const size_t BT = (size_t)h->B * h->T, nK = BT * h->d.du * h->d.dx, nk = BT * h->d.du, ns = BT * h->d.du * h->d.du;
+  // the previous asynchronous copy must have drained before its device staging buffer is overwritten
+  if (h->copy_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
+  double* outs[3] = {h->policy_out, h->policy_out + nK, h->policy_out + nK + nk};
+  const int fields[3] = {I2C_F_K, I2C_F_KK, I2C_F_SIGK};
+  for (int i = 0; i < 3; ++i) {
+    FieldMap f;
+    double* base;
+    int rc = field_map(h, fields[i], &f, &base);
+    if (rc) return rc;
+    size_t total = BT * f.rows * f.cols;
+    unpack_kernel<<<nblocks(total), 256, 0, h->stream>>>(base, f, 0, h->T, h->T, h->cell_head, h->B, h->ntiles, outs[i]);
+    h->launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(h->ev_unpacked, h->stream));
+  CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_unpacked, 0));
+  CUDA_OK(cudaMemcpyAsync(K, outs[0], nK * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_OK(cudaMemcpyAsync(k, outs[1], nk * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_OK(cudaMemcpyAsync(sigK, outs[2], ns * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_OK(cudaEventRecord(h->ev_copied, h->copy_stream));
+  h->copy_pending = true;
+  return 0;
+}
+
+int i2c_copy_wait(i2c_handle_t h) {
+  REQUIRE(h, "NULL handle");
+  if (h->copy_pending) CUDA_OK(cudaEventSynchronize(h->ev_copied));
+  h->copy_pending = false;
   return 0;
 }
 

@@ -240,6 +240,14 @@ class BatchedI2c:
         capi.check(self.lib.i2c_get_policy(self._h, capi.ptr(K), capi.ptr(k), capi.ptr(s)))
         return K, k, s
 
+    def get_local_linear_policy_async(self, K, k, sigK):
+        """Start the device->host copy of the controllers into the given (pinned) arrays on the copy stream; it
+        overlaps later sweeps.  Call wait_copies() before reading the arrays."""
+        capi.check(self.lib.i2c_get_policy_async(self._h, capi.ptr(K), capi.ptr(k), capi.ptr(sigK)))
+
+    def wait_copies(self):
+        capi.check(self.lib.i2c_copy_wait(self._h))
+
     def get_cell_flags(self):
         f = np.zeros(self.H, np.int32)
         capi.check(self.lib.i2c_get_cell_flags(self._h, capi.ptr(f)))

@@ -212,3 +212,25 @@ def test_mpc_batched_rollouts_vs_oracle(i2c_b200):
         x = sys_.dynamics(np.concatenate((x, ur), axis=-1)) + rng.multivariate_normal(np.zeros(6), sys_.sig_eta, B)
         u = ur
     assert np.all(G.status()[0] == 0)
+
+
+def test_async_policy_copy(i2c_b200):
+    """i2c_get_policy_async + i2c_copy_wait deliver the same controllers as the synchronous getter, also when a new
+    sweep is launched while the copy is in flight."""
+    import torch
+
+    Q, R = np.diag([1.0, 100.0, 1.0]), np.diag([2.0])
+    G, _ = make_pair(i2c_b200, "PendulumKnown", 300, 40, Q, R, Q, 100.0, 0.0, 7, np.array([0.3, 0.5]), 2.0 * np.eye(1),
+                     enable_aux=False)
+    G.learn(2)
+    K0, k0, s0 = G.get_local_linear_policy()
+    pin = lambda *s: torch.empty(s, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
+    K, k, s = pin(300, 40, 1, 2), pin(300, 40, 1), pin(300, 40, 1, 1)
+    G.get_local_linear_policy_async(K, k, s)
+    G.learn(1)  # overlaps the copy; must not disturb it
+    G.wait_copies()
+    assert np.array_equal(K, K0) and np.array_equal(k, k0) and np.array_equal(s, s0)
+    K1, k1, s1 = G.get_local_linear_policy()
+    G.get_local_linear_policy_async(K, k, s)
+    G.wait_copies()
+    assert np.array_equal(K, K1) and not np.array_equal(K1, K0)
