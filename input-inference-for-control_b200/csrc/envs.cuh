@@ -7,6 +7,7 @@
 // index a only need fresh sin/cos for columns j <= a.  Every map therefore takes the column index j
 // (compile-time after unrolling; j < 0 = centre) and a `Trig` cache evaluated once at the centre.
 #pragma once
+#include "dual.cuh"
 #include "linalg.cuh"
 
 namespace i2c {
@@ -31,6 +32,12 @@ struct EnvLinear {
   static constexpr int OBS_NL = 0, OBS_JMAX = -1;
   __host__ __device__ static constexpr int obs_src(int a) { return a; }
   __host__ __device__ static constexpr int term_src(int a) { return a; }
+  __host__ __device__ static constexpr int nl_angle(int) { return 0; }
+  template <class T>
+  __device__ static void dyn_g(const T* xu, const double* par, T* y) {
+    y[0] = par[0] * xu[0] + par[1] * xu[1] + par[4] * xu[2] + par[6];
+    y[1] = par[2] * xu[0] + par[3] * xu[1] + par[5] * xu[2] + par[7];
+  }
   __device__ static void trig_nl(const double*, int, const TrigT&, double*) {}
   __device__ static void center(const double*, TrigT&) {}
   __device__ static void dyn(const double* xu, int, const TrigT&, const double* par, double* y) {
@@ -66,6 +73,18 @@ struct EnvPendulum {
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
     if (j != 0) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[0], &s, &co); }
   }
+  // scalar-generic dynamics (double or Dual): used by the Linearize inference to get value + Jacobian in one pass
+  template <class T>
+  __device__ static void dyn_g(const T* xu, const double*, T* y) {
+    const double dt = 0.05, d = 1e-2, g = 9.80665;
+    T u = t_clip(xu[2], -2.0, 2.0);
+    T acc = (-3.0 * g / 2.0) * t_sin(xu[0] + 3.141592653589793) - d * xu[1];
+    acc = acc + 3.0 * u;
+    T xd = xu[1] + acc * dt;
+    y[0] = xu[0] + xd * dt;
+    y[1] = xd;
+  }
+  __host__ __device__ static constexpr int nl_angle(int) { return 0; }
   static constexpr int OBS_NL = 2, OBS_JMAX = 0;  // z = [sin th, cos th | thd, u]
   __host__ __device__ static constexpr int obs_src(int a) { return a < 2 ? -1 - a : a - 1; }
   __host__ __device__ static constexpr int term_src(int a) { return a < 2 ? -1 - a : a - 1; }
@@ -119,6 +138,22 @@ struct EnvCartpole {
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
     if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[1], &s, &co); }
   }
+  template <class T>
+  __device__ static void dyn_g(const T* xu, const double*, T* y) {
+    const double g = 9.81, Mc = 0.37, Mp = 0.127, Mt = Mc + Mp, l = 0.3365, dt = 1.0 / 250.0;
+    T u = t_clip(xu[4], -5.0, 5.0);
+    T sth = t_sin(xu[1]), cth = t_cos(xu[1]);
+    T dth2 = xu[3] * xu[3];
+    T num = (-Mp * l) * sth * cth * dth2 + (Mt * g) * sth - u * cth;
+    T den = l * ((4.0 / 3.0) * Mt - Mp * (cth * cth));
+    T th_acc = num / den;
+    T x_acc = ((Mp * l) * sth * dth2 - (Mp * l) * th_acc * cth + u) / Mt;
+    y[0] = xu[0] + dt * xu[2];
+    y[1] = xu[1] + dt * xu[3];
+    y[2] = xu[2] + dt * x_acc;
+    y[3] = xu[3] + dt * th_acc;
+  }
+  __host__ __device__ static constexpr int nl_angle(int) { return 1; }
   static constexpr int OBS_NL = 2, OBS_JMAX = 1;  // z = [x, sin th, cos th, xd, thd, u]
   __host__ __device__ static constexpr int obs_src(int a) { return a == 0 ? 0 : (a <= 2 ? -a : a - 1); }
   __host__ __device__ static constexpr int term_src(int a) { return a == 0 ? 0 : (a <= 2 ? -a : a - 1); }
@@ -170,6 +205,41 @@ struct EnvDoubleCartpole {
   __device__ static void trig2(const double* x, int j, const TrigT& c, double& s, double& co) {
     if (j < 0 || j > 2) { s = c.s[1]; co = c.c[1]; } else { fast_sincos(x[2], &s, &co); }
   }
+  template <class T>
+  __device__ static void dyn_g(const T* xu, const double*, T* y) {
+    const double dt = 1.0 / 125.0, g = 9.81, Mc = 0.37, Mp1 = 0.127, Mp2 = 0.127, Mt = Mc + Mp1 + Mp2;
+    const double L1 = 0.3365, L2 = 0.3365, l1 = L1 / 2, l2 = L2 / 2, J1 = Mp1 * L1 / 12, J2 = Mp2 * L2 / 12;
+    const double a12 = Mp1 * l1 + Mp2 * L2, a13 = Mp2 * l2, a23 = L1 * l2 * Mp2;
+    const double M22 = l1 * l1 * Mp1 + L1 * L1 * Mp2 + J1, M33 = l2 * l2 * Mp2 + J2;
+    T s1 = t_sin(xu[1]), c1 = t_cos(xu[1]), s2 = t_sin(xu[2]), c2 = t_cos(xu[2]);
+    T sd = t_sin(xu[1] - xu[2]), cd = t_cos(xu[1] - xu[2]);
+    T M12 = a12 * c1, M13 = a13 * c2, M23 = a23 * cd;
+    T td1 = xu[4], td2 = xu[5];
+    T C12 = (-a12) * td1 * s1, C13 = (-a13) * td2 * s2, C23 = a23 * td2 * sd, C32 = (-a23) * td1 * sd;
+    T G2 = (-(Mp1 * l1 + Mp2 * L1) * g) * s1, G3 = (-Mp2 * l2 * g) * s2;
+    T u = 3.0 * t_clip(xu[6], -10.0, 10.0);
+    T r1 = u - (C12 * td1 + C13 * td2);
+    T r2 = -(C23 * td2) - G2;
+    T r3 = -(C32 * td1) - G3;
+    // Cholesky solve of the SPD mass matrix [[Mt, M12, M13], [M12, M22, M23], [M13, M23, M33]]
+    const double l11 = sqrt(Mt);
+    T l21 = M12 / l11, l31 = M13 / l11;
+    T l22 = t_sqrt(M22 - l21 * l21);
+    T l32 = (M23 - l31 * l21) / l22;
+    T l33 = t_sqrt(M33 - l31 * l31 - l32 * l32);
+    T y1 = r1 / l11;
+    T y2 = (r2 - l21 * y1) / l22;
+    T y3 = (r3 - l31 * y1 - l32 * y2) / l33;
+    T a3 = y3 / l33;
+    T a2 = (y2 - l32 * a3) / l22;
+    T a1 = (y1 - l21 * a2 - l31 * a3) / l11;
+    T v1 = xu[3] + a1 * dt, v2 = xu[4] + a2 * dt, v3 = xu[5] + a3 * dt;
+    y[0] = xu[0] + v1 * dt;
+    y[1] = xu[1] + v2 * dt;
+    y[2] = xu[2] + v3 * dt;
+    y[3] = v1; y[4] = v2; y[5] = v3;
+  }
+  __host__ __device__ static constexpr int nl_angle(int k) { return k < 2 ? 1 : 2; }
   static constexpr int OBS_NL = 4, OBS_JMAX = 2;  // z = [x, s1, c1, s2, c2, xd, thd1, thd2, u]
   __host__ __device__ static constexpr int obs_src(int a) { return a == 0 ? 0 : (a <= 4 ? -a : a - 2); }
   __host__ __device__ static constexpr int term_src(int a) { return a == 0 ? 0 : (a <= 4 ? -a : a - 2); }
@@ -245,6 +315,22 @@ struct EnvQuadrotor {
   __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
     if (j < 0 || j > 2) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[2], &s, &co); }
   }
+  template <class T>
+  __device__ static void dyn_g(const T* xu, const double*, T* y) {
+    const double h = 0.1;
+    T u1 = t_clip(xu[6], 0.0, 30.0), u2 = t_clip(xu[7], 0.0, 30.0);
+    T s = t_sin(xu[2]), co = t_cos(xu[2]);
+    T f = u1 + u2;
+    T vx = xu[3] + h * ((-s * f) * (1.0 / MASS));
+    T vy = xu[4] + h * (-9.81 + (co * f) * (1.0 / MASS));
+    T w = xu[5] + (h * VDX / INERTIA) * (u2 - u1);
+    w = w * (1.0 / (1.0 + h * 0.5));
+    y[0] = xu[0] + h * vx;
+    y[1] = xu[1] + h * vy;
+    y[2] = xu[2] + h * w;
+    y[3] = vx; y[4] = vy; y[5] = w;
+  }
+  __host__ __device__ static constexpr int nl_angle(int) { return 2; }
   static constexpr int OBS_NL = 0, OBS_JMAX = -1;  // observe / observe_terminal are identities
   __host__ __device__ static constexpr int obs_src(int a) { return a; }
   __host__ __device__ static constexpr int term_src(int a) { return a; }

@@ -243,7 +243,8 @@ static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
   w.auxf = take(c.enable_aux ? T * nt * r.e_auxf() * TILE : 0, 8);
   w.auxb = take(c.enable_aux ? T * nt * r.e_auxb() * TILE : 0, 8);
   w.pf = take(c.enable_aux ? T * nt * r.e_pf() * TILE : 0, 8);
-  w.ric = take((c.enable_aux && c.inference == I2C_INF_LINEARIZE) ? T * nt * r.e_ric() * TILE : 0, 8);
+  const bool ric = c.enable_aux && c.inference == I2C_INF_LINEARIZE && (c.env == I2C_ENV_LINEAR || c.env == I2C_ENV_LINEAR_MIN_ENERGY);
+  w.ric = take(ric ? T * nt * r.e_ric() * TILE : 0, 8);
   w.term = take(nt * r.e_term() * TILE, 8);
   w.x0 = take(nt * d.dx * TILE, 8);
   w.sig_x0 = take(nt * tri(d.dx) * TILE, 8);
@@ -272,8 +273,7 @@ static int check_cfg(const i2c_config_t* cfg) {
   REQUIRE(cfg->abi_version == I2C_ABI_VERSION, "ABI version mismatch");
   REQUIRE(cfg->env >= 0 && cfg->env < I2C_ENV_COUNT, "unknown env id (no CPU fallback for unregistered envs)");
   REQUIRE(cfg->inference == I2C_INF_CUBATURE || cfg->inference == I2C_INF_LINEARIZE, "unknown inference kind");
-  REQUIRE(cfg->inference == I2C_INF_CUBATURE || cfg->env == I2C_ENV_LINEAR || cfg->env == I2C_ENV_LINEAR_MIN_ENERGY,
-          "Linearize inference is only available for the linear environments (nonlinear Jacobians: not built)");
+
   REQUIRE(cfg->n_problems >= 1 && cfg->horizon >= 1 && cfg->horizon < 65536, "bad B or H");
   REQUIRE(cfg->max_iters >= 1, "max_iters must be >= 1");
   REQUIRE(cfg->quad_alpha > 0.0, "cubature alpha must be > 0");
@@ -347,7 +347,8 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
   h->auxf = cfg->enable_aux ? (double*)(h->ws + w.auxf) : nullptr;
   h->auxb = cfg->enable_aux ? (double*)(h->ws + w.auxb) : nullptr;
   h->pf = cfg->enable_aux ? (double*)(h->ws + w.pf) : nullptr;
-  h->ric = (cfg->enable_aux && cfg->inference == I2C_INF_LINEARIZE) ? (double*)(h->ws + w.ric) : nullptr;
+  h->ric = (cfg->enable_aux && cfg->inference == I2C_INF_LINEARIZE && (cfg->env == I2C_ENV_LINEAR || cfg->env == I2C_ENV_LINEAR_MIN_ENERGY))
+               ? (double*)(h->ws + w.ric) : nullptr;
   h->term = (double*)(h->ws + w.term);
   h->x0 = (double*)(h->ws + w.x0);
   h->sig_x0 = (double*)(h->ws + w.sig_x0);
@@ -751,7 +752,7 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "n_iter must be in [1, max_iters]");
   REQUIRE(!(phases & I2C_PH_STORE_AUX) || h->cfg.enable_aux, "I2C_PH_STORE_AUX needs enable_aux=1");
   REQUIRE(!(phases & I2C_PH_CALIBRATE) || (phases & I2C_PH_PROPAGATE), "CALIBRATE needs PROPAGATE");
-  REQUIRE(!(phases & I2C_PH_RICCATI) || (h->ric != nullptr), "RICCATI needs Linearize inference and enable_aux=1");
+  REQUIRE(!(phases & I2C_PH_RICCATI) || (h->ric != nullptr), "RICCATI needs Linearize inference on a linear environment and enable_aux=1");
   KParams kp = h->kp;
   kp.prior = rec_prior(h);
   kp.post = rec_post(h);

@@ -619,52 +619,60 @@ struct Worker {
   }
 
   // ---------------------------------------------------------------------------------- Linearize moments
-  // Exact moments of the linear cost-feature map z = E x + F u (observe_linearize, env_def.py:171-181)
-  // and of the linear dynamics x' = A x + B u + a (LinearBase.forward_linearize, model.py:240-242):
-  // what _forward_msgs_linearize (i2c.py:297-306, 322-340) feeds its Kalman update / RTS gain.
+  // First-order moments of the cost-feature map around the mean (observe_linearize, env_def.py:171-181, 278-298,
+  // 541-570, 700-761): every feature is either the identity of component idx or sin / cos of the angle at idx, so
+  // H = d z / d xu has one non-zero per row: z_a ~ h_a * xu[idx_a].  What _forward_msgs_linearize (i2c.py:297-306)
+  // feeds its Kalman update:  mz = observe(mu), Sxy = Sigma H^T, Sz = H Sigma H^T (noise added by the caller).
+  // CROSS = false drops the x-u cross terms: sig_z0_m = C sig_x C^T + D sig_u D^T of the backward pass (i2c.py:538-540).
+  template <int D, int DY, bool TERM, bool CROSS>
   __device__ __forceinline__ void lin_obs_moments(const double* mu, const double* Sig, double* mz, double* Sz, double* Sxy) {
+    int idx[DY];
+    double h[DY];
 #pragma unroll
-    for (int a = 0; a < DZ; ++a) {
-      double s = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; ++i) s = fma(i < DX ? Env::obsE(a, i) : Env::obsF(a, i - DX), mu[i], s);
-      mz[a] = s;
+    for (int a = 0; a < DY; ++a) {
+      const int sa = TERM ? Env::term_src(a) : Env::obs_src(a);
+      if (sa >= 0) {
+        idx[a] = sa;
+        h[a] = 1.0;
+        mz[a] = mu[sa];
+      } else {
+        const int k = -1 - sa, ang = Env::nl_angle(k);
+        double sn, cs;
+        sincos(mu[ang], &sn, &cs);
+        idx[a] = ang;
+        mz[a] = (k & 1) ? cs : sn;  // nonlinear features come in (sin, cos) pairs
+        h[a] = (k & 1) ? -sn : cs;
+      }
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+    for (int a = 0; a < DY; ++a) {
+      if (Sxy) {
 #pragma unroll
-      for (int a = 0; a < DZ; ++a) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; ++k) s = fma(Sig[six(i, k)], k < DX ? Env::obsE(a, k) : Env::obsF(a, k - DX), s);
-        Sxy[i * DZ + a] = s;
+        for (int i = 0; i < D; ++i) Sxy[i * DY + a] = h[a] * Sig[six(i, idx[a])];
       }
-#pragma unroll
-    for (int a = 0; a < DZ; ++a)
 #pragma unroll
       for (int bb = 0; bb <= a; ++bb) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) s = fma(i < DX ? Env::obsE(a, i) : Env::obsF(a, i - DX), Sxy[i * DZ + bb], s);
-        Sz[tix(a, bb)] = s;
+        const bool same_block = CROSS || ((idx[a] < DX) == (idx[bb] < DX));
+        Sz[tix(a, bb)] = same_block ? h[a] * h[bb] * Sig[six(idx[a], idx[bb])] : 0.0;
       }
-  }
-  __device__ __forceinline__ double ABel(int r, int i) const { return i < DX ? par[r * DX + i] : par[DX * DX + r * DU + (i - DX)]; }
-  __device__ __forceinline__ void lin_dyn_moments(const double* mu, const double* Sig, double* m3, double* S3, double* Sxy) {
-#pragma unroll
-    for (int r = 0; r < DX; ++r) {
-      double s = par[DX * DX + DX * DU + r];
-#pragma unroll
-      for (int i = 0; i < N; ++i) s = fma(ABel(r, i), mu[i], s);
-      m3[r] = s;
     }
+  }
+  // Linearised dynamics around mu (forward_linearize, model.py:158-164 / 240-242): m3 = f(mu), AB = df/dxu by
+  // forward-mode AD on the in-kernel dynamics (the reference uses autograd), Sxy = Sigma AB^T, S3 = AB Sigma AB^T.
+  __device__ __forceinline__ void lin_dyn_moments(const double* mu, const double* Sig, double* m3, double* S3, double* Sxy) {
+    Dual<N> x[N], y[DX];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = dvar<N>(mu[i], i);
+    Env::template dyn_g<Dual<N>>(x, par, y);
+#pragma unroll
+    for (int r = 0; r < DX; ++r) m3[r] = y[r].v;
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
       for (int r = 0; r < DX; ++r) {
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < N; ++k) s = fma(Sig[six(i, k)], ABel(r, k), s);
+        for (int k = 0; k < N; ++k) s = fma(Sig[six(i, k)], y[r].d[k], s);
         Sxy[i * DX + r] = s;
       }
 #pragma unroll
@@ -673,11 +681,11 @@ struct Worker {
       for (int q = 0; q <= r; ++q) {
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) s = fma(ABel(r, i), Sxy[i * DX + q], s);
+        for (int i = 0; i < N; ++i) s = fma(y[r].d[i], Sxy[i * DX + q], s);
         S3[tix(r, q)] = s;
       }
   }
-  __device__ __forceinline__ bool lin() const { return Env::LINEAR && p.linearize; }
+  __device__ __forceinline__ bool lin() const { return p.linearize; }
 
   // ---------------------------------------------------------------------------------- forward cell
   // I2cCell._forward_msgs_quadrature (i2c.py:350-447); with p.linearize (linear envs) the same cell with exact
@@ -761,7 +769,7 @@ struct Worker {
     {
       double mz[DZ], Sz[TRI(DZ)], Sxy[N * DZ], z[DZ];
       if (lin()) {
-        lin_obs_moments(mu, Sig, mz, Sz, Sxy);
+        lin_obs_moments<N, DZ, false, true>(mu, Sig, mz, Sz, Sxy);
       } else if (p.fast_obs) {
         structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Sxy);
       } else {
@@ -971,28 +979,7 @@ struct Worker {
       double mz[DZ], Sz[TRI(DZ)], z[DZ];
       if (lin()) {
         // mu_z0_m = observe(mu_xu0_m); sig_z0_m = C sig_x0_m C^T + D sig_u0_m D^T (no cross term, i2c.py:538-540)
-#pragma unroll
-        for (int a = 0; a < DZ; ++a) {
-          double s = 0.0;
-#pragma unroll
-          for (int i = 0; i < N; ++i) s = fma(i < DX ? Env::obsE(a, i) : Env::obsF(a, i - DX), mu[i], s);
-          mz[a] = s;
-        }
-#pragma unroll
-        for (int a = 0; a < DZ; ++a)
-#pragma unroll
-          for (int bb = 0; bb <= a; ++bb) {
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < DX; ++i)
-#pragma unroll
-              for (int k = 0; k < DX; ++k) s = fma(Env::obsE(a, i) * Env::obsE(bb, k), Sig[six(i, k)], s);
-#pragma unroll
-            for (int i = 0; i < DU; ++i)
-#pragma unroll
-              for (int k = 0; k < DU; ++k) s = fma(Env::obsF(a, i) * Env::obsF(bb, k), Sig[six(DX + i, DX + k)], s);
-            Sz[tix(a, bb)] = s;
-          }
+        lin_obs_moments<N, DZ, false, false>(mu, Sig, mz, Sz, nullptr);
       } else if (p.fast_obs) {
         double Cxy[N * DZ];
         structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Cxy);
@@ -1014,8 +1001,13 @@ struct Worker {
       if (lin()) {
         // calc_cost goes through the graph's cubature transform of the joint posterior (i2c.py:1034-1043), which
         // is exact for a linear map: full E F Sigma (E F)^T including the x-u cross terms
+        // (for the nonlinear envs the graph's cubature transform is used, as in the reference)
         double mzf[DZ], Szf[TRI(DZ)], Sxyf[N * DZ];
-        lin_obs_moments(mu, Sig, mzf, Szf, Sxyf);
+        if (Env::OBS_NL == 0) {
+          lin_obs_moments<N, DZ, false, true>(mu, Sig, mzf, Szf, Sxyf);
+        } else {
+          structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mzf, Szf, Sxyf);
+        }
         cost_stats<DZ>(p, mzf, Szf, p.z_graph, cm, cv);
       } else {
         cost_stats<DZ>(p, mz, Sz, p.z_graph, cm, cv);
@@ -1038,51 +1030,46 @@ struct Worker {
   // the terminal cost-feature moments for the alpha update.  c holds (mu_x3_f, sig_x3_f, chol).
   __device__ __forceinline__ void backward_terminal(int it, int t, double temp, double a_cell, const Carry<DX>& c,
                                                     double* m3m, double* S3m, double& tr_term) {
-    if constexpr (Env::LINEAR) {
-      if (p.linearize) {
-        // _backward_msgs_linearize, end of chain (i2c.py:450-501); observe_terminal is the identity for the linear envs
-        static_assert(!Env::LINEAR || Env::DZT == Env::DX, "linear envs observe the full state at the end");
-        tr_term = 0.0;
+    if (p.linearize) {
+      // _backward_msgs_linearize, end of chain (i2c.py:450-501)
+      tr_term = 0.0;
 #pragma unroll
-        for (int i = 0; i < DX; ++i) m3m[i] = c.m[i];
+      for (int i = 0; i < DX; ++i) m3m[i] = c.m[i];
 #pragma unroll
-        for (int i = 0; i < TRI(DX); ++i) S3m[i] = c.S[i];
-        if (p.cov_ctrl) {
+      for (int i = 0; i < TRI(DX); ++i) S3m[i] = c.S[i];
+      if (p.cov_ctrl) {
 #pragma unroll
-          for (int i = 0; i < DX; ++i) m3m[i] = p.mu_xt[i];
+        for (int i = 0; i < DX; ++i) m3m[i] = p.mu_xt[i];
 #pragma unroll
-          for (int i = 0; i < TRI(DX); ++i) S3m[i] = p.sxt[i];
-        } else if (p.has_qf) {
-          double Sz[TRI(DX)], Sxy[DX * DX];
+        for (int i = 0; i < TRI(DX); ++i) S3m[i] = p.sxt[i];
+      } else if (Env::HAS_TERM && p.has_qf) {
+        // terminal cost as a Kalman update through observe_terminal_linearize at mu_x3_f (i2c.py:474-492)
+        double mz[DZT], Sz[TRI(DZT)], Sxy[DX * DZT], zt[DZT];
+        lin_obs_moments<DX, DZT, true, true>(c.m, c.S, mz, Sz, Sxy);
 #pragma unroll
-          for (int i = 0; i < DX; ++i)
+        for (int i = 0; i < DZT; ++i)
 #pragma unroll
-            for (int j = 0; j < DX; ++j) Sxy[i * DX + j] = c.S[six(i, j)];
-#pragma unroll
-          for (int i = 0; i < DX; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) Sz[tix(i, j)] = fma(a_cell, p.Qfinv[i * DX + j], c.S[tix(i, j)]);
-          double zt[DZT];
-          load_zterm(zt);
-          if (!condition<DX, DX>(m3m, S3m, Sz, Sxy, c.m, zt)) fail(I2C_FAIL_CHOL_TERMINAL, it, t);
-        }
-        if (p.has_qf) {
-          double Sz3[TRI(DX)];
-#pragma unroll
-          for (int i = 0; i < DX; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) Sz3[tix(i, j)] = fma(a_cell, p.Qfinv[i * DX + j], S3m[tix(i, j)]);
-          double* tm = p.term + ((size_t)tile * LY::E_TERM) * TILE + lane;
-#pragma unroll
-          for (int i = 0; i < DX; ++i) tm[(LY::TM_MU + i) * TILE] = m3m[i];
-#pragma unroll
-          for (int i = 0; i < TRI(DX); ++i) tm[(LY::TM_SIG + i) * TILE] = Sz3[i];
-          double zt[DZT];
-          load_zterm(zt);
-          tr_term = alpha_trace<DX>(p.Qf, 0, m3m, Sz3, zt);
-        }
-        return;
+          for (int j = 0; j <= i; ++j) Sz[tix(i, j)] = fma(a_cell, p.Qfinv[i * DZT + j], Sz[tix(i, j)]);
+        load_zterm(zt);
+        if (!condition<DX, DZT>(m3m, S3m, Sz, Sxy, mz, zt)) fail(I2C_FAIL_CHOL_TERMINAL, it, t);
       }
+      if (Env::HAS_TERM && p.has_qf) {
+        // mu_z3_m = observe_terminal(mu_x3_m); sig_z3_m = E sig_x3_m E^T + sig_xi_terminal (i2c.py:500-501)
+        double mz3[DZT], Sz3[TRI(DZT)], zt[DZT];
+        lin_obs_moments<DX, DZT, true, true>(m3m, S3m, mz3, Sz3, nullptr);
+#pragma unroll
+        for (int i = 0; i < DZT; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j) Sz3[tix(i, j)] = fma(a_cell, p.Qfinv[i * DZT + j], Sz3[tix(i, j)]);
+        double* tm = p.term + ((size_t)tile * LY::E_TERM) * TILE + lane;
+#pragma unroll
+        for (int i = 0; i < DZT; ++i) tm[(LY::TM_MU + i) * TILE] = mz3[i];
+#pragma unroll
+        for (int i = 0; i < TRI(DZT); ++i) tm[(LY::TM_SIG + i) * TILE] = Sz3[i];
+        load_zterm(zt);
+        tr_term = alpha_trace<DZT>(p.Qf, 0, mz3, Sz3, zt);
+      }
+      return;
     }
     double Lm[TRI(DX)], invm[DX];
     if (p.cov_ctrl) {

@@ -29,6 +29,34 @@ class EnvSpec:
     def observe_terminal_x(self, x):  # model.py:100-101
         return self.observe_terminal(x)
 
+    # ---- linearisations for the Linearize inference on nonlinear envs.  The reference takes the dynamics Jacobian
+    # with autograd (env_autograd.py:22,57,170; model.py:158-164) -- absent from this image, PARITY UNPINNED -- here:
+    # central differences of the restated dynamics (relative accuracy ~1e-9); the cost-feature Jacobians are the
+    # analytic ones of env_def.py:278-298, 541-570, 700-761 written generically from the feature structure.
+    def _obs_jac(self, z_fn, x, dim_in):
+        z = z_fn(x)
+        H = np.zeros(x.shape[:-1] + (z.shape[-1], dim_in))
+        eye = np.eye(dim_in)
+        for a in range(z.shape[-1]):
+            H[..., a, :] = self._feature_row(a, x, dim_in, eye)
+        return z, H
+
+    def observe_jac(self, xu):
+        """z, H = [C D] with z ~ z(mu) + H (xu - mu)."""
+        return self._obs_jac(self.observe, xu, self.dim_xu)
+
+    def observe_terminal_jac(self, x):
+        return self._obs_jac(self.observe_terminal, x, self.dim_x)
+
+    def forward_jac(self, xu, h=1e-6):
+        f0 = self.dynamics(xu)
+        J = np.zeros(xu.shape[:-1] + (self.dim_x, self.dim_xu))
+        for i in range(self.dim_xu):
+            d = np.zeros(self.dim_xu)
+            d[i] = h
+            J[..., :, i] = (self.dynamics(xu + d) - self.dynamics(xu - d)) / (2 * h)
+        return f0, J
+
 
 class Linear(EnvSpec):
     """LinearDef + LinearBase: env_def.py:139-191, model.py:226-242."""
@@ -128,6 +156,14 @@ class Pendulum(EnvSpec):
         x_pos = th + x_dot * dt
         return np.stack((x_pos, x_dot), axis=-1)
 
+    def _feature_row(self, a, x, dim_in, eye):
+        # z = [sin th, cos th, thd, (u)]
+        if a == 0:
+            return np.cos(x[..., 0])[..., None] * eye[0]
+        if a == 1:
+            return -np.sin(x[..., 0])[..., None] * eye[0]
+        return np.broadcast_to(eye[a - 1], x.shape[:-1] + (dim_in,))
+
     @staticmethod
     def observe(xu):  # env_def.py:273-276
         return np.stack((np.sin(xu[..., 0]), np.cos(xu[..., 0]), xu[..., 1], xu[..., 2]), axis=-1)
@@ -187,6 +223,16 @@ class Cartpole(EnvSpec):
         return np.stack(
             (xu[..., 0] + dt * xu[..., 2], xu[..., 1] + dt * xu[..., 3],
              xu[..., 2] + dt * x_acc, xu[..., 3] + dt * th_acc), axis=-1)
+
+    def _feature_row(self, a, x, dim_in, eye):
+        # z = [x, sin th, cos th, xd, thd, (u)]
+        if a == 0:
+            return np.broadcast_to(eye[0], x.shape[:-1] + (dim_in,))
+        if a == 1:
+            return np.cos(x[..., 1])[..., None] * eye[1]
+        if a == 2:
+            return -np.sin(x[..., 1])[..., None] * eye[1]
+        return np.broadcast_to(eye[a - 1], x.shape[:-1] + (dim_in,))
 
     @staticmethod
     def observe(xu):
@@ -255,6 +301,18 @@ class DoubleCartpole(EnvSpec):
         x_dot = xu[..., 3:6] + x_dot_dot * dt
         x_pos = xu[..., :3] + x_dot * dt
         return np.concatenate((x_pos, x_dot), axis=-1)
+
+    def _feature_row(self, a, x, dim_in, eye):
+        # z = [x, s1, c1, s2, c2, xd, thd1, thd2, (u)]
+        if a == 0:
+            return np.broadcast_to(eye[0], x.shape[:-1] + (dim_in,))
+        if a in (1, 3):
+            ang = 1 if a == 1 else 2
+            return np.cos(x[..., ang])[..., None] * eye[ang]
+        if a in (2, 4):
+            ang = 1 if a == 2 else 2
+            return -np.sin(x[..., ang])[..., None] * eye[ang]
+        return np.broadcast_to(eye[a - 2], x.shape[:-1] + (dim_in,))
 
     @staticmethod
     def observe(xu):

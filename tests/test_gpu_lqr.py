@@ -126,3 +126,34 @@ def test_linear_covariance_control_linearize(i2c_b200):
                 assert relerr(G.field(a)[0], g[f"it{it}/{a}"], floor=1e-9) < 1e-7, (it, a)
     assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-7
     assert relerr(np.array(G.metrics["kl_term"])[:, 0], g["kl_terms"]) < 1e-6
+
+
+@pytest.mark.parametrize("env,Q,R,alpha,xs,T", [
+    ("PendulumKnown", np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), 100.0, [0.3, 0.5], 40),
+    ("CartpoleKnown", np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0]), 80.0, 0.05, 40),
+    ("DoubleCartpoleKnown", 1e-3 * np.diag([1.0, 1.0, 100.0, 1.0, 100.0, 10.0, 1.0, 1.0]), 1e-4 * np.eye(1), 0.05, 0.02, 30),
+])
+def test_linearize_nonlinear_envs(i2c_b200, env, Q, R, alpha, xs, T):
+    """Linearize inference on the nonlinear envs (experiments pendulum_known.py,
+    cartpole_known.py, double_cartpole_known(_lin).py).  PARITY UNPINNED against the reference (its dynamics
+    Jacobians come from autograd, absent here): the oracle takes them by central differences, the kernel by
+    forward-mode AD, so agreement is limited by the finite-difference error (~1e-8 relative)."""
+    from oracle import i2c_oracle as O
+
+    rng = np.random.default_rng(4)
+    e = i2c_b200.envs.make(env)
+    B = 16
+    x0 = e.x0 + np.asarray(xs) * rng.normal(size=(B, e.dim_x))
+    mu_u = 1e-2 * rng.normal(size=(B, T, e.dim_u))
+    G = i2c_b200.BatchedI2c(env, B, T, Q, R, Q, alpha, 0.5, mu_u, np.eye(e.dim_u), x0=x0, inference="linearize",
+                            enable_aux=True)
+    ref = O.make_graph(env, T, Q, R, Q, alpha, 0.5, mu_u, np.eye(e.dim_u), inference=O.Linearize(), B=B, x0=x0)
+    for it in range(3):
+        G.learn(1)
+        ref.learn_msgs()
+        assert np.all(G.status()[0] == 0), (it, G.status())
+        for a, tol in [("mu_xu1_f", 1e-6), ("sig_xu1_f", 1e-5), ("mu_x3_f", 1e-6), ("sig_x3_f", 1e-5), ("mu_xu0_m", 1e-6),
+                       ("sig_xu0_m", 1e-5), ("mu_z0_m", 1e-6), ("sig_z0_m", 1e-5), ("K", 1e-4), ("k", 1e-4), ("sigK", 1e-5)]:
+            assert relerr(G.field(a), ref.stack(a), floor=1e-6) < tol, (it, a)
+        assert relerr(G.alpha, ref.alpha) < 1e-6
+    assert relerr(np.array(G.metrics["cost_m"]), np.array(ref.costs_m)) < 1e-6
