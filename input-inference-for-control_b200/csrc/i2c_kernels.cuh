@@ -392,7 +392,8 @@ struct Carry {
 // META = latency-regime variant: per-cell targets / flags are staged with the records and the records move with
 // per-thread cp.async (lowest latency); throughput variant (META = false): records move with one TMA bulk copy per
 // warp and cell (fewest instructions), targets / flags are plain cached loads.
-template <class Env, bool META>
+// LIN = Linearize inference compiled in (separate instantiation: keeps the cubature kernels small).
+template <class Env, bool META, bool LIN = false>
 struct Worker {
   static constexpr bool BULK = kUseBulk && !META;
   using LY = Lay<Env>;
@@ -685,7 +686,7 @@ struct Worker {
         S3[tix(r, q)] = s;
       }
   }
-  __device__ __forceinline__ bool lin() const { return p.linearize; }
+  __device__ __forceinline__ static constexpr bool lin() { return LIN; }
 
   // ---------------------------------------------------------------------------------- forward cell
   // I2cCell._forward_msgs_quadrature (i2c.py:350-447); with p.linearize (linear envs) the same cell with exact
@@ -768,7 +769,7 @@ struct Worker {
     // ---- cost observation update (i2c.py:390-404)
     {
       double mz[DZ], Sz[TRI(DZ)], Sxy[N * DZ], z[DZ];
-      if (lin()) {
+      if constexpr (LIN) {
         lin_obs_moments<N, DZ, false, true>(mu, Sig, mz, Sz, Sxy);
       } else if (p.fast_obs) {
         structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Sxy);
@@ -805,7 +806,7 @@ struct Worker {
     if (!chol_rows<N>(L, invd)) fail(I2C_FAIL_CHOL_FILTERED, it, t);
     {
       double Sxy[N * DX];
-      if (lin()) {
+      if constexpr (LIN) {
         lin_dyn_moments(mu, Sig, c.m, c.S, Sxy);
       } else {
         TrigT ctx;
@@ -977,7 +978,7 @@ struct Worker {
     // marginal cost-feature moments (i2c.py:594-596) -> alpha / cost statistics
     {
       double mz[DZ], Sz[TRI(DZ)], z[DZ];
-      if (lin()) {
+      if constexpr (LIN) {
         // mu_z0_m = observe(mu_xu0_m); sig_z0_m = C sig_x0_m C^T + D sig_u0_m D^T (no cross term, i2c.py:538-540)
         lin_obs_moments<N, DZ, false, false>(mu, Sig, mz, Sz, nullptr);
       } else if (p.fast_obs) {
@@ -998,7 +999,7 @@ struct Worker {
         for (int i = 0; i < TRI(DZ); ++i) ab[(LY::AB_SIGZ + i) * TILE] = Sz[i];
       }
       double cm, cv;
-      if (lin()) {
+      if constexpr (LIN) {
         // calc_cost goes through the graph's cubature transform of the joint posterior (i2c.py:1034-1043), which
         // is exact for a linear map: full E F Sigma (E F)^T including the x-u cross terms
         // (for the nonlinear envs the graph's cubature transform is used, as in the reference)
@@ -1030,7 +1031,7 @@ struct Worker {
   // the terminal cost-feature moments for the alpha update.  c holds (mu_x3_f, sig_x3_f, chol).
   __device__ __forceinline__ void backward_terminal(int it, int t, double temp, double a_cell, const Carry<DX>& c,
                                                     double* m3m, double* S3m, double& tr_term) {
-    if (p.linearize) {
+    if constexpr (LIN) {
       // _backward_msgs_linearize, end of chain (i2c.py:450-501)
       tr_term = 0.0;
 #pragma unroll
@@ -1841,7 +1842,7 @@ struct Worker {
 // MINB = minimum resident 128-thread blocks per SM: 1 lets ptxas use up to 255 registers (best per-warp latency,
 // used when the batch cannot fill the machine anyway); 4 caps the kernel at 128 registers so that 16 warps per SM
 // are resident (throughput regime, small envs only).
-template <class Env, int MINB, bool LAT>
+template <class Env, int MINB, bool LAT, bool LIN>
 __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ KParams pin) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / TILE;
   const int lane = threadIdx.x % TILE;
@@ -1849,7 +1850,7 @@ __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ K
   extern __shared__ __align__(128) double stage_smem[];
   constexpr int PER_WARP = 2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars;  // staging buffers + mbarriers
   double* base = stage_smem + (size_t)(threadIdx.x / TILE) * PER_WARP;
-  Worker<Env, LAT> w(pin, warp, lane, base + lane, reinterpret_cast<uint64_t*>(base + 2 * Lay<Env>::E_STAGE_TOT * TILE));
+  Worker<Env, LAT, LIN> w(pin, warp, lane, base + lane, reinterpret_cast<uint64_t*>(base + 2 * Lay<Env>::E_STAGE_TOT * TILE));
   w.run();
 }
 
@@ -1879,14 +1880,14 @@ static int launch_em_team(const KParams& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-template <class Env, int MINB, bool LAT>
+template <class Env, int MINB, bool LAT, bool LIN = false>
 static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
   int wpb = threads / TILE;
   int blocks = (p.ntiles + wpb - 1) / wpb;
   const size_t smem = Lay<Env>::STAGED ? (size_t)wpb * (2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars) * sizeof(double) : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env, MINB, LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env, MINB, LAT, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -1894,7 +1895,7 @@ static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
   // staging the per-cell targets / flags removes their exposed load latency when a warp is alone on its
   // sub-partition; in the throughput regime the extra LDGSTS instructions cost more than they hide
   q.stage_meta = Lay<Env>::STAGED && LAT;
-  em_kernel<Env, MINB, LAT><<<blocks, threads, smem, s>>>(q);
+  em_kernel<Env, MINB, LAT, LIN><<<blocks, threads, smem, s>>>(q);
   return (int)cudaGetLastError();
 }
 
@@ -1904,6 +1905,8 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   int threads = 32;
   if (p.ntiles >= 148 * 8) threads = 64;
   if (p.ntiles >= 148 * 32) threads = 128;
+  // Linearize inference: one (latency-style) variant only -- not a throughput path
+  if (p.linearize) return launch_em_v<Env, 1, true, true>(p, s, threads);
   // fewer tiles than SMs: spread each tile's backward pass over the 8 warps of a block (one block per SM)
   if (p.ntiles <= 148 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 8>(p, s);
   if (p.ntiles <= 296 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 4>(p, s);  // two blocks per SM
