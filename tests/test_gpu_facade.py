@@ -205,3 +205,24 @@ def test_env_batch_eval_mirror(mirror):
     policy.write(*i2c.get_local_expert_linear_policy())
     xs, ys, zs, zs_term = env.batch_eval(policy, 4, deterministic=False)
     assert np.all(np.isfinite(np.asarray(xs)))
+
+
+def test_linearize_pendulum_flow(mirror):
+    """scripts/i2c_run.py with experiments/pendulum_known.py (Linearize inference on a nonlinear env):
+    the mirror runs the same calls; compared with the oracle (finite-difference Jacobians)."""
+    from oracle import i2c_oracle as O
+
+    rng = np.random.default_rng(2)
+    T = 50
+    mu_u = 1e-2 * rng.normal(size=(T, 1))
+    Q, R = np.diag([1.0, 100.0, 1.0]), np.diag([2.0])
+    model = mirror.make_env_model("PendulumKnown", None)
+    i2c = mirror.I2cGraph(model, T, Q, R, Q, 100.0, 0.5, mu_u, 2.0 * np.eye(1), None, None, mirror.Linearize())
+    ref = O.make_graph("PendulumKnown", T, Q, R, Q, 100.0, 0.5, mu_u, 2.0 * np.eye(1), inference=O.Linearize())
+    for _ in range(4):
+        i2c.learn_msgs()
+        ref.learn_msgs()
+    assert relerr(np.array(i2c.alphas), np.array([a[0] for a in ref.alphas])) < 1e-6
+    K, k, s = i2c.get_local_linear_policy()
+    Kr, kr, sr = ref.get_local_linear_policy()
+    assert relerr(K, Kr[0]) < 1e-4 and relerr(k, kr[0]) < 1e-4 and relerr(s, sr[0]) < 1e-5

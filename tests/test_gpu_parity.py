@@ -184,3 +184,26 @@ def test_em_against_reference_golden(i2c_b200, name, tol_s, tol_g):
     assert relerr(k[0], g["final/k"], 1e-6) < 10 * tol_g
     assert relerr(sk[0], g["final/sigK"]) < 10 * tol_s
     assert relerr(G.field("mu_xu0_m")[0], g["final/mu_xu0_m"]) < 100 * tol_s
+
+
+def test_em_general_cubature_parameters(i2c_b200):
+    """CubatureQuadrature(alpha, beta, kappa) != (1, 0, 0): non-zero centre weight, so the kernels take the generic
+    sigma-point path (centre point evaluated, no structured shortcut).  (1, 0, 1) is the unscented rule with kappa = 1."""
+    from oracle import i2c_oracle as O
+
+    quad = (1.0, 0.0, 1.0)
+    rng = np.random.default_rng(8)
+    B, T = 40, 30
+    e = i2c_b200.envs.make("CartpoleKnown")
+    Q, R = np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0])
+    x0 = e.x0 + 0.05 * rng.normal(size=(B, 4))
+    mu_u = 1e-2 * rng.normal(size=(B, T, 1))
+    G = i2c_b200.BatchedI2c("CartpoleKnown", B, T, Q, R, Q, 80.0, 0.0, mu_u, np.eye(1), x0=x0, quadrature=quad,
+                            enable_aux=True)
+    ref = O.make_graph("CartpoleKnown", T, Q, R, Q, 80.0, 0.0, mu_u, np.eye(1), inference=O.Cubature(*quad), B=B, x0=x0)
+    for it in range(3):
+        G.learn(1)
+        ref.learn_msgs()
+        assert np.all(G.status()[0] == 0)
+        compare_cells(G, ref, FIELDS_F + FIELDS_B, 1e-9, 1e-6, tag=f"it{it}")
+    assert relerr(G.alpha, ref.alpha) < 1e-10
