@@ -215,6 +215,11 @@ int i2c_shift_horizon(i2c_handle_t h, const double* z_new, const double* mu_u_in
  * handle's belief (x0, sig_x0): predict through the dynamics with u fixed, update on measure(x).
  * y[B][dy], u[B][du], sig_zeta[dy][dy]. */
 int i2c_ckf_step(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta);
+/* One whole control step of PartiallyObservedMpcPolicy.__call__ (policy/mpc.py:156-182) with a single host
+ * synchronisation: [do_filter: i2c_ckf_step(y, u_prev)] -> n_iter x (forward, backward, _update_priors) ->
+ * u_out[B][du] = cells[0].mu_u0_m -> horizon shift with the new last cell's target z_new[dz]. */
+int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const double* u_prev, const double* sig_zeta,
+                 int32_t n_iter, const double* z_new, const double* mu_u_init, double alpha_init, double* u_out);
 int i2c_get_initial_state(i2c_handle_t h, double* x0, double* sig_x0);
 /* First action of the plan: cells[0].mu_u0_m / sig_u0_m (policy/mpc.py:166-167). */
 int i2c_get_first_action(i2c_handle_t h, double* mu_u /*[B][du]*/, double* sig_u /*[B][du][du]*/);

@@ -212,6 +212,17 @@ __global__ void dfma_peak_kernel(double* out, int iters, double b, double c) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// tiny by-value setters: let the MPC step update one cell's metadata without host staging / synchronisation
+struct SmallVals {
+  double v[16];
+};
+__global__ void set_vals_kernel(double* dst, SmallVals s, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = s.v[threadIdx.x];
+}
+__global__ void set_cell_meta_kernel(int32_t* flags, int32_t* index, int slot, int32_t f, int32_t ix) {
+  flags[slot] = f;
+  index[slot] = ix;
+}
 __global__ void fill_kernel(double* p, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -995,6 +1006,52 @@ int i2c_shift_horizon(i2c_handle_t h, const double* z_new, const double* mu_u_in
     CUDA_OK(cudaStreamSynchronize(h->stream));
   }
   return rc;
+}
+
+// One closed-loop MPC step with a single synchronisation: PartiallyObservedMpcPolicy.__call__
+// (policy/mpc.py:156-182) = [filter] -> n_iter x (forward, backward, _update_priors) -> first action -> horizon shift.
+int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const double* u_prev, const double* sig_zeta,
+                 int32_t n_iter, const double* z_new, const double* mu_u_init, double alpha_init, double* u_out) {
+  REQUIRE(h && z_new && mu_u_init && u_out, "NULL argument");
+  REQUIRE(!h->cfg.z_per_problem, "i2c_mpc_step expects shared cell targets (z_per_problem = 0)");
+  const int dx = h->d.dx, du = h->d.du, n = dx + du, dz = h->d.dz, T = h->T;
+  REQUIRE(dz <= 16 && du <= 16, "internal: by-value setter too small");
+  int rc = 0;
+  if (do_filter) {
+    REQUIRE(y && u_prev && sig_zeta, "filter step needs y, u_prev, sig_zeta");
+    rc = i2c_ckf_step(h, y, u_prev, sig_zeta);  // enqueues + one sync (staging buffer reuse)
+    if (rc) return rc;
+  }
+  rc = i2c_run(h, n_iter, I2C_PH_FORWARD | I2C_PH_BACKWARD | I2C_PH_UPDATE_PRIORS);
+  if (rc) return rc;
+  // first action = cells[0].mu_u0_m (policy/mpc.py:166) -> scratch -> host (async)
+  {
+    FieldMap f{h->r.e_post(), dx, 0, du, 1, 0, 0, 1};
+    size_t total = (size_t)h->B * du;
+    unpack_kernel<<<nblocks(total), 256, 0, h->stream>>>(rec_latest(h), f, 0, 1, h->T, h->cell_head, h->B, h->ntiles, h->scratch);
+    CUDA_OK(cudaMemcpyAsync(u_out, h->scratch, total * 8, cudaMemcpyDeviceToHost, h->stream));
+    h->launches++;
+  }
+  // horizon shift (policy/mpc.py:174-181) without host staging
+  h->cell_head = (h->cell_head + 1) % T;
+  const int slot = (T - 1 + h->cell_head) % T;
+  h->flags[slot] = I2C_CELL_INDEPENDENT | I2C_CELL_EXPERT | I2C_CELL_OWN_ALPHA;
+  h->index[slot] = 0;
+  set_cell_meta_kernel<<<1, 1, 0, h->stream>>>(h->cell_flags_dev, h->cell_index_dev, slot, h->flags[slot], 0);
+  SmallVals sv;
+  for (int i = 0; i < du; ++i) sv.v[i] = mu_u_init[i];
+  double* mu_dev = h->scratch + (size_t)h->B * du + 64;  // behind the first-action staging
+  set_vals_kernel<<<1, 32, 0, h->stream>>>(mu_dev, sv, du);
+  InitArgs ia{dx, du, n, h->r.e_post(), T, h->cell_head, h->Bpad, h->ntiles, 1, {0, 0, 0}};
+  for (int i = 0; i < tri(du); ++i) ia.sig_u[i] = h->sig_u_host[i];
+  init_cells_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->recA, h->recB, ia, T - 1, 1, h->x0, h->sig_x0, mu_dev, h->B);
+  fill_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->alpha_cell + (size_t)slot * h->Bpad, (size_t)h->Bpad, alpha_init);
+  for (int i = 0; i < dz; ++i) sv.v[i] = z_new[i];
+  set_vals_kernel<<<1, 32, 0, h->stream>>>(h->z_cell + (size_t)slot * dz, sv, dz);
+  h->launches += 5;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 int i2c_ckf_step(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta) {

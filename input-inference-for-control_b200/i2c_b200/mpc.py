@@ -55,20 +55,35 @@ class BatchedPartiallyObservedMpc:
     def belief(self):
         return self.i2c.get_initial_state()
 
-    def __call__(self, i, y, u):
-        """policy/mpc.py:156-182 with deterministic=True: returns the first planned action [B, du]."""
-        if i > 0:
-            self.filter(y, u)
-        self.optimize(self.n_iter)
-        ctrl, _ = self.i2c.first_action()
+    def _next_target(self, i):
         g = self.i2c
-        if self.z_traj is not None:
-            if (i + g.H) < self.z_traj.shape[0]:
-                z_new = self.z_traj[i + g.H]
-            else:
-                z_new = self._z_last
-            self._z_last = np.array(z_new, float)
-        else:
-            z_new = g.z_graph
-        g.shift_horizon(z_new, self._mu_u_init, self._alpha_init)
+        if self.z_traj is None:
+            return g.z_graph
+        z_new = self.z_traj[i + g.H] if (i + g.H) < self.z_traj.shape[0] else self._z_last
+        self._z_last = np.array(z_new, float)
+        return z_new
+
+    def __call__(self, i, y, u, fused=True):
+        """policy/mpc.py:156-182 with deterministic=True: returns the first planned action [B, du].
+        fused=True runs filter, sweeps, action read-out and horizon shift as ONE library call with a single
+        synchronisation (i2c_mpc_step); fused=False issues the individual calls (same numbers)."""
+        g = self.i2c
+        z_new = capi.f64(self._next_target(i), (g.dims[2],))
+        if not fused:
+            if i > 0:
+                self.filter(y, u)
+            self.optimize(self.n_iter)
+            ctrl, _ = g.first_action()
+            g.shift_horizon(z_new, self._mu_u_init, self._alpha_init)
+            return ctrl
+        ctrl = np.empty((g.B, g.dims[1]))
+        yy = uu = sz = None
+        if i > 0:
+            yy = capi.f64(np.broadcast_to(y, (g.B, g.env.dim_y)))
+            uu = capi.f64(np.broadcast_to(u, (g.B, g.dims[1])))
+            sz = capi.f64(self.sig_zeta, (g.env.dim_y, g.env.dim_y))
+        capi.check(g.lib.i2c_set_tau(g._h, int(g.tau)))
+        capi.check(g.lib.i2c_mpc_step(g._h, int(i > 0), capi.ptr(yy), capi.ptr(uu), capi.ptr(sz), self.n_iter,
+                                      capi.ptr(z_new), capi.ptr(capi.f64(self._mu_u_init)), self._alpha_init,
+                                      capi.ptr(ctrl)))
         return ctrl

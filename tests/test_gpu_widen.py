@@ -202,15 +202,22 @@ def test_mpc_batched_rollouts_vs_oracle(i2c_b200):
     x = np.broadcast_to(sys_.x0, (B, 6)).copy()
     u = np.zeros((B, 2))
     ur = np.zeros((B, 2))
+    G2, pol2 = quad_setup(i2c_b200, g, B, sig_zeta)  # same roll-outs through the un-fused call sequence
+    G2.calibrate_alpha()
+    pol2.optimize(25)
+    G2.calibrate_alpha()
+    u2 = np.zeros((B, 2))
     for t in range(n_steps):
         y = sys_.measure(x) + rng.multivariate_normal(np.zeros(8), sig_zeta, B)
+        u2 = np.clip(pol2(t, y, u2, fused=False), 0.0, 30.0)
         u = np.clip(pol(t, y, u), 0.0, 30.0)
+        assert np.array_equal(u, u2), t
         ur = np.clip(rp(t, y, ur), 0.0, 30.0)
         assert relerr(u, ur) < 1e-6, t
         mu, cov = pol.belief
         assert relerr(mu, rp.mu) < 1e-7 and relerr(cov, rp.covar) < 1e-6, t
         x = sys_.dynamics(np.concatenate((x, ur), axis=-1)) + rng.multivariate_normal(np.zeros(6), sys_.sig_eta, B)
-        u = ur
+        u = u2 = ur
     assert np.all(G.status()[0] == 0)
 
 
