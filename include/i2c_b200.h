@@ -183,6 +183,16 @@ int i2c_get_temp(i2c_handle_t h, double* temp);
  * MpcPolicy.optimize (policy/mpc.py:147-154).  Asynchronous on the handle's stream. */
 int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases);
 
+/* Parallel-in-time variant of i2c_run for long horizons (not in the reference, whose sweeps are sequential loops over the
+ * cells, i2c.py:876-886): the horizon is cut into chunks of `chunk_cells` cells; per sweep (1) every chunk composes the
+ * Kalman filtering / RTS smoothing elements of its cells (associative operators), (2) the boundary messages are pushed
+ * through the chunk aggregates, (3) every chunk runs the ordinary cell recursion from its exact boundary message, so the
+ * records, metrics and alpha schedule are those of i2c_run up to round-off.  Sequential depth 2*chunk_cells + H/chunk_cells
+ * cells instead of H.  Exact only where the cell map is linear-Gaussian in the state message: I2C_INF_LINEARIZE on
+ * I2C_ENV_LINEAR / I2C_ENV_LINEAR_MIN_ENERGY with cells that are independent or non-expert feedback cells; anything else
+ * is refused (no fallback).  phases: I2C_PH_FORWARD | I2C_PH_BACKWARD [| I2C_PH_MSTEP | I2C_PH_UPDATE_PRIORS | I2C_PH_STORE_AUX]. */
+int i2c_run_scan(i2c_handle_t h, int32_t n_iter, int32_t phases, int32_t chunk_cells);
+
 /* Wait for the stream; number of metric rows written by the last i2c_run. */
 int i2c_synchronize(i2c_handle_t h);
 

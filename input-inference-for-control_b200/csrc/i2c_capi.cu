@@ -20,7 +20,8 @@ namespace i2c {
   int launch_em_env##k(const KParams& p, void* stream);                   \
   int launch_quad_env##k(int fn, const QuadArgs& a, void* stream);        \
   int launch_ckf_env##k(const CkfArgs& a, void* stream);              \
-  int launch_rollout_env##k(const RolloutArgs& a, void* stream);
+  int launch_rollout_env##k(const RolloutArgs& a, void* stream);       \
+  int launch_scan_env##k(int stage, const KParams& p, const ScanArgs& a, void* stream);
 I2C_DECL_ENV(0) I2C_DECL_ENV(1) I2C_DECL_ENV(2) I2C_DECL_ENV(3) I2C_DECL_ENV(4) I2C_DECL_ENV(5) I2C_DECL_ENV(6)
 #undef I2C_DECL_ENV
 
@@ -53,6 +54,11 @@ int launch_ckf(int env, const CkfArgs& a, void* stream) {
 }
 int launch_rollout(int env, const RolloutArgs& a, void* stream) {
 #define CALL(k) launch_rollout_env##k(a, stream)
+  I2C_SWITCH_ENV(env, CALL)
+#undef CALL
+}
+int launch_scan(int env, int stage, const KParams& p, const ScanArgs& a, void* stream) {
+#define CALL(k) launch_scan_env##k(stage, p, a, stream)
   I2C_SWITCH_ENV(env, CALL)
 #undef CALL
 }
@@ -757,13 +763,7 @@ int i2c_get_temp(i2c_handle_t h, double* temp) {
   return 0;
 }
 
-int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
-  REQUIRE(h, "NULL handle");
-  REQUIRE(h->problem_set, "i2c_set_problem has not been called");
-  REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "n_iter must be in [1, max_iters]");
-  REQUIRE(!(phases & I2C_PH_STORE_AUX) || h->cfg.enable_aux, "I2C_PH_STORE_AUX needs enable_aux=1");
-  REQUIRE(!(phases & I2C_PH_CALIBRATE) || (phases & I2C_PH_PROPAGATE), "CALIBRATE needs PROPAGATE");
-  REQUIRE(!(phases & I2C_PH_RICCATI) || (h->ric != nullptr), "RICCATI needs Linearize inference on a linear environment and enable_aux=1");
+static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   KParams kp = h->kp;
   kp.prior = rec_prior(h);
   kp.post = rec_post(h);
@@ -800,6 +800,17 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   kp.z_per_problem = h->cfg.z_per_problem;
   kp.temp0 = h->temp;
   kp.dtemp = h->dtemp;
+  return kp;
+}
+
+int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
+  REQUIRE(h, "NULL handle");
+  REQUIRE(h->problem_set, "i2c_set_problem has not been called");
+  REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "n_iter must be in [1, max_iters]");
+  REQUIRE(!(phases & I2C_PH_STORE_AUX) || h->cfg.enable_aux, "I2C_PH_STORE_AUX needs enable_aux=1");
+  REQUIRE(!(phases & I2C_PH_CALIBRATE) || (phases & I2C_PH_PROPAGATE), "CALIBRATE needs PROPAGATE");
+  REQUIRE(!(phases & I2C_PH_RICCATI) || (h->ric != nullptr), "RICCATI needs Linearize inference on a linear environment and enable_aux=1");
+  KParams kp = run_params(h, n_iter, phases);
   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
   int rc = launch_em(h->cfg.env, kp, (void*)h->stream);
   if (rc != 0) return set_err(-100 - rc, std::string("EM kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
@@ -826,6 +837,93 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
     }
     CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
   }
+  return 0;
+}
+
+// Parallel-in-time variant of i2c_run (csrc/i2c_scan.cuh): the horizon is cut into chunks of `chunk_cells` cells that are
+// processed concurrently; exact for Linearize inference on the linear environments.  Same records, metrics and state
+// machine as i2c_run(FORWARD | BACKWARD [| MSTEP] [| UPDATE_PRIORS] [| STORE_AUX]).
+int i2c_run_scan(i2c_handle_t h, int32_t n_iter, int32_t phases, int32_t chunk_cells) {
+  REQUIRE(h, "NULL handle");
+  REQUIRE(h->problem_set, "i2c_set_problem has not been called");
+  REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "n_iter must be in [1, max_iters]");
+  REQUIRE(!(phases & I2C_PH_STORE_AUX) || h->cfg.enable_aux, "I2C_PH_STORE_AUX needs enable_aux=1");
+  REQUIRE(h->cfg.inference == I2C_INF_LINEARIZE && (h->cfg.env == I2C_ENV_LINEAR || h->cfg.env == I2C_ENV_LINEAR_MIN_ENERGY),
+          "the parallel-in-time sweep is exact only for Linearize inference on the linear environments (no fallback)");
+  const int32_t allowed = I2C_PH_FORWARD | I2C_PH_BACKWARD | I2C_PH_MSTEP | I2C_PH_UPDATE_PRIORS | I2C_PH_STORE_AUX;
+  REQUIRE((phases & ~allowed) == 0, "i2c_run_scan supports FORWARD, BACKWARD, MSTEP, UPDATE_PRIORS, STORE_AUX");
+  REQUIRE((phases & I2C_PH_BACKWARD) || !(phases & I2C_PH_MSTEP), "MSTEP needs BACKWARD");
+  REQUIRE((phases & I2C_PH_FORWARD) || !(phases & I2C_PH_MSTEP), "MSTEP needs FORWARD");
+  const int T = h->T, dx = h->d.dx;
+  REQUIRE(chunk_cells >= 8 && chunk_cells <= T, "chunk_cells must be in [8, horizon]");
+  const int n_chunks = (T + chunk_cells - 1) / chunk_cells;
+  ScanArgs a{};
+  {
+    size_t per = (size_t)h->ntiles * TILE, off = 0;
+    auto take = [&](size_t e) {
+      double* q = h->scratch + off;
+      off += (size_t)n_chunks * e * per;
+      return q;
+    };
+    a.fagg = take(3 * dx * dx + 2 * dx);
+    a.cin = take(dx + tri(dx));
+    a.bagg = take(2 * dx * dx + dx);
+    a.bin = take(dx + tri(dx));
+    a.part = take(SCAN_PARTS);
+    a.tail = h->scratch + off;
+    off += per;
+    REQUIRE(off <= h->scratch_elems, "internal: scan scratch does not fit");
+  }
+  a.n_chunks = n_chunks;
+  a.chunk = chunk_cells;
+  CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  for (int it = 0; it < n_iter; ++it) {
+    for (int s = 0; s < T; ++s)
+      REQUIRE((h->flags[s] & I2C_CELL_INDEPENDENT) || !(h->flags[s] & I2C_CELL_EXPERT),
+              "parallel-in-time sweep: a feedback cell with use_expert_controller weights K by a pdf ratio of the incoming "
+              "message (i2c.py:259-265), which is not linear-Gaussian; clear I2C_CELL_EXPERT or use i2c_run");
+    KParams kp = run_params(h, 1, phases);
+    a.it = it;
+    a.temp = h->temp;
+    auto go = [&](int stage) -> int {
+      int rc = launch_scan(h->cfg.env, stage, kp, a, (void*)h->stream);
+      h->launches++;
+      return rc;
+    };
+    int rc = 0;
+    if (phases & I2C_PH_FORWARD) {
+      if (n_chunks > 1 && !rc) rc = go(SCAN_FWD_LOCAL);
+      if (!rc) rc = go(SCAN_FWD_PREFIX);
+      if (!rc) rc = go(SCAN_FWD_CELLS);
+    }
+    if (phases & I2C_PH_BACKWARD) {
+      if (n_chunks > 1 && !rc) rc = go(SCAN_BWD_LOCAL);
+      if (!rc) rc = go(SCAN_BWD_SUFFIX);
+      if (!rc) rc = go(SCAN_BWD_CELLS);
+      h->latest_is_A = h->prior_is_A ? 0 : 1;  // backward wrote `post`
+      if (h->kp.cov_ctrl) h->temp += h->dtemp;
+    }
+    if ((phases & I2C_PH_MSTEP) && !rc) rc = go(SCAN_MSTEP);
+    if (rc != 0) return set_err(-100 - rc, std::string("scan kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    bool flags_dirty = false;
+    if (phases & I2C_PH_UPDATE_PRIORS) {
+      if (h->latest_is_A != h->prior_is_A) h->prior_is_A = h->latest_is_A;  // swap prior/post
+      for (int s = 0; s < T; ++s)
+        if (h->tau > 0 && h->index[s] <= h->tau && (h->flags[s] & I2C_CELL_INDEPENDENT)) {
+          h->flags[s] &= ~I2C_CELL_INDEPENDENT;
+          flags_dirty = true;
+        }
+    }
+    if (phases & I2C_PH_MSTEP)
+      for (int s = 0; s < T; ++s)
+        if (h->flags[s] & I2C_CELL_OWN_ALPHA) {
+          h->flags[s] &= ~I2C_CELL_OWN_ALPHA;
+          flags_dirty = true;
+        }
+    if (flags_dirty) CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), T * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+  h->last_n_iter = n_iter;
   return 0;
 }
 

@@ -1,5 +1,6 @@
 // One translation unit per environment: compiled with -DI2C_ENV_ID=<enum i2c_env> (see __graft_entry__.build()).
 #include "i2c_kernels.cuh"
+#include "i2c_scan.cuh"
 
 #ifndef I2C_ENV_ID
 #error "compile with -DI2C_ENV_ID=<0..6>"
@@ -33,6 +34,10 @@ int I2C_CAT(launch_quad_env, I2C_ENV_ID)(int fn, const QuadArgs& a, void* stream
 int I2C_CAT(launch_ckf_env, I2C_ENV_ID)(const CkfArgs& a, void* stream) { return launch_ckf_t<EnvT>(a, (cudaStream_t)stream); }
 int I2C_CAT(launch_rollout_env, I2C_ENV_ID)(const RolloutArgs& a, void* stream) {
   return launch_rollout_t<EnvT>(a, (cudaStream_t)stream);
+}
+
+int I2C_CAT(launch_scan_env, I2C_ENV_ID)(int stage, const KParams& p, const ScanArgs& a, void* stream) {
+  return launch_scan_t<EnvT>(stage, p, a, (cudaStream_t)stream);
 }
 
 }  // namespace i2c

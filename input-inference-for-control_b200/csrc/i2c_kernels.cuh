@@ -1598,6 +1598,32 @@ struct Worker {
     p.metrics[((size_t)m * p.max_iters + it) * p.Bpad + b] = v;
   }
 
+  // compute_update_alpha(update_alpha=True) (i2c.py:921-963): alpha_hat from the summed traces, ratio clip, metrics
+  __device__ __forceinline__ double mstep_alpha(int it, double tr, double tr_term, double alpha) {
+    double sf = (double)(DZ * p.T);
+    if (Env::HAS_TERM && p.has_qf) {
+      tr += tr_term;
+      sf += (double)DZT;
+    }
+    double a_new = tr / sf;
+    metric(I2C_M_ALPHA_DESIRED, it, a_new);
+    if (a_new != a_new) {
+      fail(I2C_FAIL_NAN_ALPHA, it, 0);
+      a_new = alpha;
+    } else if (p.alpha_tol >= 0.0) {
+      const double ratio = a_new / alpha;
+      const double upper = 2.0 - p.alpha_tol;
+      double upd = a_new;
+      if (ratio < p.alpha_tol) upd = p.alpha_tol * alpha;
+      if (ratio > upper) upd = upper * alpha;
+      a_new = upd;
+    } else {
+      a_new = alpha;
+    }
+    metric(I2C_M_ALPHA, it, a_new);
+    return a_new;
+  }
+
   // ---------------------------------------------------------------------------------- the EM loop
   // TEAM = false: one warp does everything for its tile.  TEAM = true (latency regime, one block of W warps per
   // tile): warp 0 runs the sequential recursions (forward sweep, RTS heads, propagate); the per-cell work of the
@@ -1792,31 +1818,8 @@ struct Worker {
         flipped = true;
       }
       if (main_warp && (p.phases & I2C_PH_MSTEP)) {
-        // compute_update_alpha(update_alpha=True) (i2c.py:921-963)
-        double sf = (double)(DZ * T);
-        double tr = st.tr;
-        if (Env::HAS_TERM && p.has_qf) {
-          tr += tr_term;
-          sf += (double)DZT;
-        }
-        double a_new = tr / sf;
-        metric(I2C_M_ALPHA_DESIRED, it, a_new);
-        if (a_new != a_new) {
-          fail(I2C_FAIL_NAN_ALPHA, it, 0);
-          a_new = alpha;
-        } else if (p.alpha_tol >= 0.0) {
-          const double ratio = a_new / alpha;
-          const double upper = 2.0 - p.alpha_tol;
-          double upd = a_new;
-          if (ratio < p.alpha_tol) upd = p.alpha_tol * alpha;
-          if (ratio > upper) upd = upper * alpha;
-          a_new = upd;
-        } else {
-          a_new = alpha;
-        }
-        alpha = a_new;
+        alpha = mstep_alpha(it, st.tr, tr_term, alpha);
         own_alpha_valid = false;  // update_xi pushes the new sig_xi to every cell (i2c.py:976-981)
-        metric(I2C_M_ALPHA, it, alpha);
       }
       if (main_warp && (p.phases & I2C_PH_CALIBRATE)) {
         // calibrate_alpha (i2c.py:895-911): alpha from the propagated cost features, no terminal term

@@ -126,4 +126,20 @@ struct RolloutArgs {
 };
 int launch_rollout(int env, const RolloutArgs& a, void* stream);
 
+// chunked parallel-in-time sweep (i2c_scan.cuh); linear environments + Linearize inference only
+struct ScanArgs {
+  double* fagg;  // [n_chunks][ntiles][E_FAGG][32]  forward chunk aggregates (A, b, C, eta, J)
+  double* cin;   // [n_chunks][ntiles][E_MSG][32]   state message entering each chunk from the left
+  double* bagg;  // [n_chunks][ntiles][E_BAGG][32]  backward chunk aggregates (E, g, L)
+  double* bin;   // [n_chunks][ntiles][E_MSG][32]   smoothed message entering each chunk from the right
+  double* part;  // [n_chunks][SCAN_PARTS][Bpad]    per-chunk partial statistics
+  double* tail;  // [Bpad]                          terminal trace term of the alpha update
+  int32_t n_chunks, chunk, it;
+  double temp;
+};
+int launch_scan(int env, int stage, const KParams& p, const ScanArgs& a, void* stream);
+enum { SCAN_FWD_LOCAL = 0, SCAN_FWD_PREFIX, SCAN_FWD_CELLS, SCAN_BWD_LOCAL, SCAN_BWD_SUFFIX, SCAN_BWD_CELLS, SCAN_MSTEP };
+enum { SP_ENTX_M = 0, SP_ENTX_E, SP_COST, SP_COST_VAR, SP_TR, SP_ENTU_M, SP_ENTU_E, SCAN_PARTS };
+
+
 }  // namespace i2c

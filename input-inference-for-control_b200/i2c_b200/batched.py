@@ -95,6 +95,7 @@ class BatchedI2c:
         self.dtemp = float(dtemp)
         self._propagate = False
         self.tau = T - 1
+        self.time_parallel_chunk = None  # cells per chunk of the parallel-in-time sweep (None = sequential kernel)
         self.reset()
 
     # ------------------------------------------------------------------ lifecycle
@@ -131,7 +132,11 @@ class BatchedI2c:
         while done < n_iter:
             n = min(self.max_iters, n_iter - done)
             capi.check(self.lib.i2c_set_tau(self._h, int(self.tau)))
-            capi.check(self.lib.i2c_run(self._h, n, phases))
+            if self.time_parallel_chunk:
+                # parallel-in-time sweep (csrc/i2c_scan.cuh): Linearize inference on linear systems only, refused otherwise
+                capi.check(self.lib.i2c_run_scan(self._h, n, phases, int(self.time_parallel_chunk)))
+            else:
+                capi.check(self.lib.i2c_run(self._h, n, phases))
             if collect and (phases & (capi.PH_MSTEP | capi.PH_CALIBRATE | capi.PH_PROPAGATE)):
                 self._collect(n, phases)
             done += n
