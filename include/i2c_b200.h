@@ -45,7 +45,8 @@ enum i2c_env {
 };
 
 /* Inference kinds: i2c/exp_types.py:25-49 */
-enum i2c_inference { I2C_INF_CUBATURE = 0, I2C_INF_LINEARIZE = 1 };
+/* I2C_INF_GAUSS_HERMITE: GaussHermiteQuadrature(degree) (exp_types.py:52-68), degree passed in i2c_config.quad_alpha */
+enum i2c_inference { I2C_INF_CUBATURE = 0, I2C_INF_LINEARIZE = 1, I2C_INF_GAUSS_HERMITE = 2 };
 
 /* Per-problem status words (replace the reference's exceptions) */
 enum i2c_status {
@@ -241,6 +242,11 @@ int i2c_get_first_action(i2c_handle_t h, double* mu_u /*[B][du]*/, double* sig_u
 int i2c_quadrature(int32_t env, int32_t fn, int32_t n_problems, const double* m, const double* S,
                    double quad_alpha, double quad_beta, double quad_kappa, const double* env_par,
                    double* m_y, double* S_y, double* S_xy, int32_t* status, int32_t device);
+/* Same transform with GaussHermiteQuadrature(degree) (exp_types.py:52-68; quadrature.py:132): degree^D tensor grid. */
+int i2c_quadrature_gh(int32_t env, int32_t fn, int32_t n_problems, const double* m, const double* S, int32_t degree,
+                      const double* env_par, double* m_y, double* S_y, double* S_xy, int32_t* status, int32_t device);
+/* 1-D Gauss-Hermite rule used by the library: nodes[degree], weights[degree] = hermgauss weights / sqrt(pi). */
+int i2c_gauss_hermite(int32_t degree, double* nodes, double* weights);
 
 /* Batched stochastic closed-loop evaluation of the extracted controllers == BaseSim.run / batch_eval
  * (i2c/env.py:40-103; BaseKnownSim.forward :180-187) under TimeIndexedLinearGaussianPolicy /

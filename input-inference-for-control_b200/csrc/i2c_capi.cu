@@ -289,7 +289,11 @@ static int check_cfg(const i2c_config_t* cfg) {
   REQUIRE(cfg != nullptr, "cfg is NULL");
   REQUIRE(cfg->abi_version == I2C_ABI_VERSION, "ABI version mismatch");
   REQUIRE(cfg->env >= 0 && cfg->env < I2C_ENV_COUNT, "unknown env id (no CPU fallback for unregistered envs)");
-  REQUIRE(cfg->inference == I2C_INF_CUBATURE || cfg->inference == I2C_INF_LINEARIZE, "unknown inference kind");
+  REQUIRE(cfg->inference == I2C_INF_CUBATURE || cfg->inference == I2C_INF_LINEARIZE || cfg->inference == I2C_INF_GAUSS_HERMITE,
+          "unknown inference kind");
+  REQUIRE(cfg->inference != I2C_INF_GAUSS_HERMITE ||
+              (cfg->quad_alpha == floor(cfg->quad_alpha) && cfg->quad_alpha >= 1.0 && cfg->quad_alpha <= MAX_GH),
+          "Gauss-Hermite degree (passed in quad_alpha) must be an integer in [1, 8]");
 
   REQUIRE(cfg->n_problems >= 1 && cfg->horizon >= 1 && cfg->horizon < 65536, "bad B or H");
   REQUIRE(cfg->max_iters >= 1, "max_iters must be >= 1");
@@ -551,6 +555,62 @@ static void cubature_rule(double a, double b, double k, int dim, double* sf, dou
   *w0 = 2.0 * lam * (*wi) + (1.0 - a * a + b);
 }
 
+// Gauss-Hermite nodes / weights (np.polynomial.hermite.hermgauss in exp_types.py:57): roots of the physicists' Hermite
+// polynomial H_n by interlacing bisection on the orthonormal recurrence + Newton polish; w_i = 1 / (n p_{n-1}(x_i)^2).
+// The weights are returned divided by sqrt(pi), i.e. normalised to sum to one per dimension (exp_types.py:66).
+static double hermite_orthonormal(int n, double x, double* pnm1) {
+  double p0 = 0.7511255444649425, pm = 0.0;  // pi^(-1/4)
+  for (int j = 0; j < n; ++j) {
+    double pn = x * sqrt(2.0 / (j + 1)) * p0 - sqrt((double)j / (j + 1)) * pm;
+    pm = p0;
+    p0 = pn;
+  }
+  if (pnm1) *pnm1 = pm;
+  return p0;
+}
+static void gauss_hermite_rule(int n, double* x, double* w) {
+  std::vector<double> roots, prev;
+  for (int k = 1; k <= n; ++k) {
+    const double R = sqrt(2.0 * k + 1.0) + 1.0;
+    std::vector<double> br;
+    br.push_back(-R);
+    for (double r : prev) br.push_back(r);
+    br.push_back(R);
+    roots.assign(k, 0.0);
+    for (int i = 0; i < k; ++i) {
+      double lo = br[i], hi = br[i + 1];
+      double flo = hermite_orthonormal(k, lo, nullptr);
+      for (int it = 0; it < 200; ++it) {
+        double mid = 0.5 * (lo + hi), fm = hermite_orthonormal(k, mid, nullptr);
+        if ((fm > 0) == (flo > 0)) {
+          lo = mid;
+          flo = fm;
+        } else {
+          hi = mid;
+        }
+      }
+      double r = 0.5 * (lo + hi);
+      for (int it = 0; it < 3; ++it) {  // Newton: p_k' = sqrt(2k) p_{k-1}
+        double pm, pk = hermite_orthonormal(k, r, &pm);
+        r -= pk / (sqrt(2.0 * k) * pm);
+      }
+      roots[i] = r;
+    }
+    prev = roots;
+  }
+  for (int i = 0; i < n; ++i) {
+    x[i] = 0.5 * (roots[i] - roots[n - 1 - i]);  // enforce exact symmetry of the node set (middle node = 0)
+    double pm;
+    hermite_orthonormal(n, x[i], &pm);
+    w[i] = 1.0 / (n * pm * pm) / 1.7724538509055159;
+  }
+}
+static void fill_gh(GhRule* g, int degree) {
+  memset(g, 0, sizeof(*g));
+  g->degree = degree;
+  if (degree > 0) gauss_hermite_rule(degree, g->x, g->w);
+}
+
 static int upload_flags(i2c_handle_t h) {
   CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemcpyAsync(h->cell_index_dev, h->index.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
@@ -640,7 +700,9 @@ int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, cons
   kp.alpha_tol = alpha_update_tol;
   cubature_rule(h->cfg.quad_alpha, h->cfg.quad_beta, h->cfg.quad_kappa, n, &kp.sf_n, &kp.w0_n, &kp.wi_n);
   cubature_rule(h->cfg.quad_alpha, h->cfg.quad_beta, h->cfg.quad_kappa, dx, &kp.sf_x, &kp.w0_x, &kp.wi_x);
-  kp.fast_obs = kp.w0_n == 0.0 && kp.w0_x == 0.0 && fabs(2.0 * n * kp.wi_n - 1.0) < 1e-15 &&
+  fill_gh(&kp.gh, h->cfg.inference == I2C_INF_GAUSS_HERMITE ? (int)h->cfg.quad_alpha : 0);
+  if (kp.gh.degree > 0) cubature_rule(1.0, 0.0, 0.0, n, &kp.sf_n, &kp.w0_n, &kp.wi_n), cubature_rule(1.0, 0.0, 0.0, dx, &kp.sf_x, &kp.w0_x, &kp.wi_x);
+  kp.fast_obs = kp.gh.degree == 0 && kp.w0_n == 0.0 && kp.w0_x == 0.0 && fabs(2.0 * n * kp.wi_n - 1.0) < 1e-15 &&
                 fabs(2.0 * dx * kp.wi_x - 1.0) < 1e-15 && fabs(kp.sf_n * kp.sf_n - n) < 1e-12 && getenv("I2C_B200_GENERIC_OBS") == nullptr;
   // ---- graph state
   h->cell_head = 0;
@@ -1187,9 +1249,31 @@ int i2c_ckf_step(i2c_handle_t h, const double* y, const double* u, const double*
   return 0;
 }
 
+int i2c_gauss_hermite(int32_t degree, double* nodes, double* weights) {
+  REQUIRE(degree >= 1 && degree <= MAX_GH && nodes && weights, "degree must be in [1, 8]");
+  gauss_hermite_rule(degree, nodes, weights);
+  return 0;
+}
+
+static int quadrature_impl(int32_t env, int32_t fn, int32_t n_problems, const double* m, const double* S, double quad_alpha,
+                           double quad_beta, double quad_kappa, int gh_degree, const double* env_par, double* m_y, double* S_y,
+                           double* S_xy, int32_t* status, int32_t device);
+
 int i2c_quadrature(int32_t env, int32_t fn, int32_t n_problems, const double* m, const double* S, double quad_alpha,
                    double quad_beta, double quad_kappa, const double* env_par, double* m_y, double* S_y, double* S_xy,
                    int32_t* status, int32_t device) {
+  return quadrature_impl(env, fn, n_problems, m, S, quad_alpha, quad_beta, quad_kappa, 0, env_par, m_y, S_y, S_xy, status, device);
+}
+
+int i2c_quadrature_gh(int32_t env, int32_t fn, int32_t n_problems, const double* m, const double* S, int32_t degree,
+                      const double* env_par, double* m_y, double* S_y, double* S_xy, int32_t* status, int32_t device) {
+  REQUIRE(degree >= 1 && degree <= MAX_GH, "Gauss-Hermite degree must be in [1, 8]");
+  return quadrature_impl(env, fn, n_problems, m, S, 1.0, 0.0, 0.0, degree, env_par, m_y, S_y, S_xy, status, device);
+}
+
+static int quadrature_impl(int32_t env, int32_t fn, int32_t n_problems, const double* m, const double* S, double quad_alpha,
+                           double quad_beta, double quad_kappa, int gh_degree, const double* env_par, double* m_y, double* S_y,
+                           double* S_xy, int32_t* status, int32_t device) {
   REQUIRE(env >= 0 && env < I2C_ENV_COUNT, "unknown env id (no CPU fallback for unregistered callables)");
   REQUIRE(fn >= 0 && fn <= 3 && n_problems >= 1 && m && S && m_y && S_y && S_xy, "bad argument");
   const EnvDims& d = kEnv[env];
@@ -1235,6 +1319,7 @@ int i2c_quadrature(int32_t env, int32_t fn, int32_t n_problems, const double* m,
     a.m = t_m, a.S = t_S, a.envpar = t_par, a.my = t_my, a.Sy = t_Sy, a.Sxy = t_Sxy, a.status = st;
     a.B = B, a.ntiles = nt;
     cubature_rule(quad_alpha, quad_beta, quad_kappa, D, &a.sf, &a.w0, &a.wi);
+    fill_gh(&a.gh, gh_degree);
     int lrc = launch_quadrature(env, fn, a, (void*)s);
     if (lrc != 0) {
       rc = set_err(-100 - lrc, "quadrature kernel launch failed");

@@ -182,6 +182,70 @@ __device__ __forceinline__ void cross_cov(const double* L, double* DmSxy) {
     }
 }
 
+// Gauss-Hermite rule (exp_types.py:52-68, GaussHermiteQuadrature): the degree^D tensor grid of 1-D Gauss-Hermite nodes,
+//   x_p = m + sqrt(2) L xi_p,   w_p = prod_i w[d_i] / pi^(D/2)       (g.w holds the 1-D weights already divided by sqrt(pi))
+// Same outputs as sigma_transform: my, Syy (no noise), and Dm[j][:] = sqrt(2) sum_p w_p xi_pj y_p so that S_xy = L * Dm
+// (equal to the reference's sum_p w_p x_p y_p^T - m my^T because the nodes are symmetric and the weights sum to one).
+// The point loop is a run-time odometer: degree^D evaluations (27 for the pendulum at degree 3, 16 384 at d = 7, degree 4).
+template <int D, int DY, class Eval>
+__device__ __forceinline__ void grid_transform(const double* m, const double* L, const GhRule& g, Eval&& eval, double* my,
+                                               double* Syy, double* Dm) {
+  const double sf = 1.4142135623730951;
+  double sy[DY], syy[TRI(DY)];
+#pragma unroll
+  for (int a = 0; a < DY; ++a) sy[a] = 0.0;
+#pragma unroll
+  for (int a = 0; a < TRI(DY); ++a) syy[a] = 0.0;
+#pragma unroll
+  for (int a = 0; a < D * DY; ++a) Dm[a] = 0.0;
+  int dig[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) dig[i] = 0;
+  int total = 1;
+#pragma unroll
+  for (int i = 0; i < D; ++i) total *= g.degree;
+  for (int pt = 0; pt < total; ++pt) {
+    double xi[D], x[D], y[DY], w = 1.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      xi[i] = g.x[dig[i]];
+      w *= g.w[dig[i]];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k <= i; ++k) sacc = fma(L[tix(i, k)], xi[k], sacc);
+      x[i] = fma(sf, sacc, m[i]);
+    }
+    eval(x, 0, y);  // column index 0: every angle is evaluated afresh (no centre cache applies on a full grid)
+#pragma unroll
+    for (int a = 0; a < DY; ++a) {
+      const double wy = w * y[a];
+      sy[a] += wy;
+#pragma unroll
+      for (int b = 0; b <= a; ++b) syy[tix(a, b)] = fma(wy, y[b], syy[tix(a, b)]);
+#pragma unroll
+      for (int j = 0; j < D; ++j) Dm[j * DY + a] = fma(sf * xi[j], wy, Dm[j * DY + a]);
+    }
+    bool carry = true;  // odometer increment
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (carry) {
+        dig[i] += 1;
+        carry = dig[i] >= g.degree;
+        if (carry) dig[i] = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < DY; ++a) my[a] = sy[a];
+#pragma unroll
+  for (int a = 0; a < DY; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) Syy[tix(a, b)] = fma(-sy[a], sy[b], syy[tix(a, b)]);
+}
+
 // Gaussian conditioning on an observation with moments (my, Sy incl. noise, Sxy) and target z:
 //   G = Sxy Sy^{-1};  mu += G (z - my);  Sig -= G Sxy^T      (i2c.py:398-403 / :438-443)
 // done through the Cholesky factor of Sy: W_i = Ly^{-1} Sxy[i,:]^T, r = Ly^{-1}(z - my).
@@ -393,7 +457,8 @@ struct Carry {
 // per-thread cp.async (lowest latency); throughput variant (META = false): records move with one TMA bulk copy per
 // warp and cell (fewest instructions), targets / flags are plain cached loads.
 // LIN = Linearize inference compiled in (separate instantiation: keeps the cubature kernels small).
-template <class Env, bool META, bool LIN = false>
+// GH = Gauss-Hermite tensor-grid rule instead of the cubature points (separate instantiation as well).
+template <class Env, bool META, bool LIN = false, bool GH = false>
 struct Worker {
   static constexpr bool BULK = kUseBulk && !META;
   using LY = Lay<Env>;
@@ -687,6 +752,13 @@ struct Worker {
       }
   }
   __device__ __forceinline__ static constexpr bool lin() { return LIN; }
+  // sigma-point transform with the graph's rule: cubature points (sf, w0, wi) or the Gauss-Hermite grid
+  template <int D_, int DY_, class Eval>
+  __device__ __forceinline__ void xform(const double* m, const double* L, double sf, double w0, double wi, Eval&& eval,
+                                        double* my, double* Syy, double* Dm) const {
+    if constexpr (GH) grid_transform<D_, DY_>(m, L, p.gh, eval, my, Syy, Dm);
+    else sigma_transform<D_, DY_>(m, L, sf, w0, wi, eval, my, Syy, Dm);
+  }
 
   // ---------------------------------------------------------------------------------- forward cell
   // I2cCell._forward_msgs_quadrature (i2c.py:350-447); with p.linearize (linear envs) the same cell with exact
@@ -776,7 +848,7 @@ struct Worker {
       } else {
         TrigT ctx;
         Env::center(mu, ctx);
-        sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+        xform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                                [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Sxy);
         cross_cov<N, DZ>(L, Sxy);
       }
@@ -811,7 +883,7 @@ struct Worker {
       } else {
         TrigT ctx;
         Env::center(mu, ctx);
-        sigma_transform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+        xform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                                [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Sxy);
         cross_cov<N, DX>(L, Sxy);
       }
@@ -841,7 +913,7 @@ struct Worker {
       } else {
         TrigT ctx;
         Env::center(c.m, ctx);
-        sigma_transform<DX, DZT>(c.m, c.L, p.sf_x, p.w0_x, p.wi_x,
+        xform<DX, DZT>(c.m, c.L, p.sf_x, p.w0_x, p.wi_x,
                                  [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Sxy);
         cross_cov<DX, DZT>(c.L, Sxy);
       }
@@ -988,7 +1060,7 @@ struct Worker {
         double Dm[N * DZ];
         TrigT ctx;
         Env::center(mu, ctx);
-        sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+        xform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                                [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
       }
       if (aux) {
@@ -1136,7 +1208,7 @@ struct Worker {
       double mz[DZT], Sz[TRI(DZT)], Dm[DX * DZT];
       TrigT ctx;
       Env::center(m3m, ctx);
-      sigma_transform<DX, DZT>(m3m, Lm, p.sf_x, p.w0_x, p.wi_x,
+      xform<DX, DZT>(m3m, Lm, p.sf_x, p.w0_x, p.wi_x,
                                [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Dm);
       double* tm = p.term + ((size_t)tile * LY::E_TERM) * TILE + lane;
 #pragma unroll
@@ -1231,7 +1303,7 @@ struct Worker {
       } else {
         TrigT ctx;
         Env::center(mu, ctx);
-        sigma_transform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+        xform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                                [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
       }
       if (aux) {
@@ -1252,7 +1324,7 @@ struct Worker {
       double Dm[N * DX];
       TrigT ctx;
       Env::center(mu, ctx);
-      sigma_transform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
+      xform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                              [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Dm);
 #pragma unroll
       for (int i = 0; i < TRI(DX); ++i) {
@@ -1845,7 +1917,7 @@ struct Worker {
 // MINB = minimum resident 128-thread blocks per SM: 1 lets ptxas use up to 255 registers (best per-warp latency,
 // used when the batch cannot fill the machine anyway); 4 caps the kernel at 128 registers so that 16 warps per SM
 // are resident (throughput regime, small envs only).
-template <class Env, int MINB, bool LAT, bool LIN>
+template <class Env, int MINB, bool LAT, bool LIN, bool GH>
 __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ KParams pin) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / TILE;
   const int lane = threadIdx.x % TILE;
@@ -1853,7 +1925,7 @@ __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ K
   extern __shared__ __align__(128) double stage_smem[];
   constexpr int PER_WARP = 2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars;  // staging buffers + mbarriers
   double* base = stage_smem + (size_t)(threadIdx.x / TILE) * PER_WARP;
-  Worker<Env, LAT, LIN> w(pin, warp, lane, base + lane, reinterpret_cast<uint64_t*>(base + 2 * Lay<Env>::E_STAGE_TOT * TILE));
+  Worker<Env, LAT, LIN, GH> w(pin, warp, lane, base + lane, reinterpret_cast<uint64_t*>(base + 2 * Lay<Env>::E_STAGE_TOT * TILE));
   w.run();
 }
 
@@ -1883,14 +1955,14 @@ static int launch_em_team(const KParams& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-template <class Env, int MINB, bool LAT, bool LIN = false>
+template <class Env, int MINB, bool LAT, bool LIN = false, bool GH = false>
 static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
   int wpb = threads / TILE;
   int blocks = (p.ntiles + wpb - 1) / wpb;
   const size_t smem = Lay<Env>::STAGED ? (size_t)wpb * (2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars) * sizeof(double) : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env, MINB, LAT, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env, MINB, LAT, LIN, GH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -1898,7 +1970,7 @@ static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
   // staging the per-cell targets / flags removes their exposed load latency when a warp is alone on its
   // sub-partition; in the throughput regime the extra LDGSTS instructions cost more than they hide
   q.stage_meta = Lay<Env>::STAGED && LAT;
-  em_kernel<Env, MINB, LAT, LIN><<<blocks, threads, smem, s>>>(q);
+  em_kernel<Env, MINB, LAT, LIN, GH><<<blocks, threads, smem, s>>>(q);
   return (int)cudaGetLastError();
 }
 
@@ -1910,6 +1982,8 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   if (p.ntiles >= 148 * 32) threads = 128;
   // Linearize inference: one (latency-style) variant only -- not a throughput path
   if (p.linearize) return launch_em_v<Env, 1, true, true>(p, s, threads);
+  // Gauss-Hermite grids: degree^n points per transform, one variant as well
+  if (p.gh.degree > 0) return launch_em_v<Env, 1, true, false, true>(p, s, threads);
   // fewer tiles than SMs: spread each tile's backward pass over the 8 warps of a block (one block per SM)
   if (p.ntiles <= 148 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 8>(p, s);
   if (p.ntiles <= 296 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 4>(p, s);  // two blocks per SM
@@ -1950,14 +2024,14 @@ __global__ void __launch_bounds__(64) quad_kernel(const __grid_constant__ QuadAr
   double my[DY], Sy[TRI(DY)], Sxy[D * DY];
   typename Env::TrigT ctx;
   Env::center(m, ctx);
-  sigma_transform<D, DY>(m, L, a.sf, a.w0, a.wi,
-                         [&](const double* x, int j, double* y) {
-                           if (FN == 0) Env::obs(x, j, ctx, y);
-                           else if (FN == 1) Env::obs_term(x, j, ctx, y);
-                           else if (FN == 2) Env::dyn(x, j, ctx, par, y);
-                           else Env::measure(x, j, ctx, y);
-                         },
-                         my, Sy, Sxy);
+  auto ev = [&](const double* x, int j, double* y) {
+    if (FN == 0) Env::obs(x, j, ctx, y);
+    else if (FN == 1) Env::obs_term(x, j, ctx, y);
+    else if (FN == 2) Env::dyn(x, j, ctx, par, y);
+    else Env::measure(x, j, ctx, y);
+  };
+  if (a.gh.degree > 0) grid_transform<D, DY>(m, L, a.gh, ev, my, Sy, Sxy);
+  else sigma_transform<D, DY>(m, L, a.sf, a.w0, a.wi, ev, my, Sy, Sxy);
   cross_cov<D, DY>(L, Sxy);
 #pragma unroll
   for (int i = 0; i < DY; ++i) a.my[((size_t)tile * DY + i) * TILE + lane] = my[i];

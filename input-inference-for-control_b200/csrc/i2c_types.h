@@ -7,6 +7,12 @@
 namespace i2c {
 
 constexpr int TILE = 32;       // problems per tile == one warp; innermost (contiguous) axis of every record
+// Gauss-Hermite rule (exp_types.py:52-68): 1-D nodes and weights / sqrt(pi); degree 0 = not in use
+constexpr int MAX_GH = 8;
+struct GhRule {
+  int32_t degree, pad;
+  double x[MAX_GH], w[MAX_GH];
+};
 constexpr int MAX_DX = 6, MAX_DU = 2, MAX_N = 8, MAX_DZ = 9, MAX_DZT = 8, MAX_DY = 8;
 
 // Device layout ("AoSoA"): a per-cell record with E fp64 elements per problem is stored as
@@ -59,6 +65,7 @@ struct KParams {
   double sxt_inv_mu[MAX_DX];                     // sig_x_terminal^{-1} mu_x_terminal
   double mu_xt[MAX_DX];
   double sxt_logdet;                             // log det sig_x_terminal (KL term)
+  GhRule gh;                                     // Gauss-Hermite inference (I2C_INF_GAUSS_HERMITE), else degree 0
 };
 
 // element counts of the records for given dims
@@ -87,6 +94,7 @@ struct QuadArgs {
   int32_t* status;   // [Bpad]
   int32_t B, ntiles;
   double sf, w0, wi;
+  GhRule gh;         // degree > 0: Gauss-Hermite grid instead of the cubature points
 };
 int launch_quadrature(int env, int fn, const QuadArgs& a, void* stream);
 

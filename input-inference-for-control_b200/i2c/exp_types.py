@@ -50,9 +50,24 @@ class CubatureQuadrature(object):
 
 @dataclass
 class GaussHermiteQuadrature(object):
-    """Declared for import compatibility; degree**dim point rules are not built for the CUDA path."""
+    """Tensor-product Gauss-Hermite rule with degree**dim points (exp_types.py:52-68).  The 1-D nodes / weights come
+    from the CUDA library (i2c_gauss_hermite), the same rule its kernels integrate with."""
 
     degree: int
 
     def __post_init__(self):
-        raise NotImplementedError("Gauss-Hermite quadrature is not available on the CUDA path (no CPU fallback)")
+        if self.degree < 1:
+            raise AssertionError("degree must be >= 1")
+        import i2c_b200
+
+        x, w = i2c_b200.batched.gauss_hermite(self.degree)
+        self.gh_pts, self.gh_weights = x, w * np.sqrt(np.pi)  # hermgauss convention: weights sum to sqrt(pi)
+
+    def pts(self, dim):
+        axes = np.meshgrid(*([self.gh_pts] * dim))
+        return np.stack([a.ravel() for a in axes], axis=1)
+
+    def weights(self, dim):
+        axes = np.meshgrid(*([self.gh_weights] * dim))
+        w = np.prod(np.stack([a.ravel() for a in axes], axis=1), axis=1) / np.pi ** (dim / 2)
+        return np.sqrt(2), w, w

@@ -14,7 +14,7 @@ import numpy as np
 
 import i2c_b200
 from i2c_b200 import capi
-from i2c.exp_types import CubatureQuadrature, Linearize
+from i2c.exp_types import CubatureQuadrature, GaussHermiteQuadrature, Linearize
 from i2c.inference.quadrature import QuadratureInference
 
 # cell attribute -> (device field, slicer); x = state block, u = action block of a joint quantity
@@ -187,6 +187,9 @@ class I2cGraph(object):
         if isinstance(inference, CubatureQuadrature):
             kind, quad = "cubature", (inference.alpha, inference.beta, inference.kappa)
             self.obs_inf = QuadratureInference(inference, sys.dim_xu)
+        elif isinstance(inference, GaussHermiteQuadrature):  # i2c.py:116, 839
+            kind, quad = "gauss_hermite", (int(inference.degree), 0.0, 0.0)
+            self.obs_inf = QuadratureInference(inference, sys.dim_xu)
         elif isinstance(inference, Linearize):
             kind, quad = "linearize", (1.0, 0.0, 0.0)
             self.obs_inf = QuadratureInference(CubatureQuadrature(1, 0, 0), sys.dim_xu)
@@ -261,6 +264,8 @@ class I2cGraph(object):
             self._x0_pushed = x0
         g.tau = self.tau
         g._propagate = self._propagate
+        # extension (not in the reference): cells per chunk of the parallel-in-time sweep, None = sequential kernel
+        g.time_parallel_chunk = getattr(self, "time_parallel_chunk", None)
 
     def _after(self, phases):
         self._cache = {}

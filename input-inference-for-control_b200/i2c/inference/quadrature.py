@@ -5,7 +5,7 @@ arbitrary Python callables cannot be evaluated in-kernel and raise (no CPU fallb
 import numpy as np
 
 import i2c_b200
-from i2c.exp_types import CubatureQuadrature
+from i2c.exp_types import CubatureQuadrature, GaussHermiteQuadrature
 
 _FN = {"observe": "observe", "observe_terminal": "observe_terminal", "observe_terminal_x": "observe_terminal",
        "forward": "forward", "dynamics": "forward", "measure": "measure"}
@@ -13,8 +13,8 @@ _FN = {"observe": "observe", "observe_terminal": "observe_terminal", "observe_te
 
 class QuadratureInference(object):
     def __init__(self, params, dim):
-        if not isinstance(params, CubatureQuadrature):
-            raise NotImplementedError("only CubatureQuadrature is available on the CUDA path")
+        if not isinstance(params, (CubatureQuadrature, GaussHermiteQuadrature)):  # quadrature.py:9
+            raise AssertionError("params must be CubatureQuadrature or GaussHermiteQuadrature")
         self.params = params
         self.dim = dim
         self.base_pts = params.pts(dim)
@@ -33,9 +33,12 @@ class QuadratureInference(object):
     def _run(self, f, m_x, sig_x):
         model, env, fn = self._resolve(f)
         m = np.asarray(m_x, float).reshape(1, self.dim)
-        quad = (self.params.alpha, self.params.beta, self.params.kappa)
-        my, Sy, Sxy, st = i2c_b200.quadrature(env, fn, m, np.asarray(sig_x, float)[None], quad=quad,
-                                              env_par=model._b200_env_par(), device=getattr(model, "device", 0))
+        if isinstance(self.params, GaussHermiteQuadrature):
+            kw = dict(gh_degree=int(self.params.degree))
+        else:
+            kw = dict(quad=(self.params.alpha, self.params.beta, self.params.kappa))
+        my, Sy, Sxy, st = i2c_b200.quadrature(env, fn, m, np.asarray(sig_x, float)[None], env_par=model._b200_env_par(),
+                                              device=getattr(model, "device", 0), **kw)
         if st[0] != 0:
             raise np.linalg.LinAlgError("Matrix is not positive definite")  # quadrature.py:17-24
         self.m_y, self.sig_y, self.sig_xy = my, Sy[0], Sxy[0]

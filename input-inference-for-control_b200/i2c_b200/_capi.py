@@ -25,7 +25,7 @@ ENV_IDS = {
 # enum i2c_phase
 PH_FORWARD, PH_BACKWARD, PH_PROPAGATE, PH_MSTEP, PH_UPDATE_PRIORS = 1, 2, 4, 8, 16
 PH_CALIBRATE, PH_ONLY_DECREASE, PH_STORE_AUX, PH_RICCATI = 32, 64, 128, 256
-INF_CUBATURE, INF_LINEARIZE = 0, 1
+INF_CUBATURE, INF_LINEARIZE, INF_GAUSS_HERMITE = 0, 1, 2
 PH_LEARN = PH_FORWARD | PH_BACKWARD | PH_MSTEP | PH_UPDATE_PRIORS
 # enum i2c_cell_flag
 CELL_INDEPENDENT, CELL_TERMINAL, CELL_EXPERT, CELL_OWN_ALPHA = 1, 2, 4, 8
@@ -65,7 +65,7 @@ EXPORTS = [
     "i2c_set_cell_targets",
     "i2c_set_alpha", "i2c_get_alpha", "i2c_set_temp", "i2c_get_temp", "i2c_run", "i2c_run_scan", "i2c_synchronize", "i2c_get_metric",
     "i2c_get_status", "i2c_get_field", "i2c_set_field", "i2c_field_shape", "i2c_get_policy", "i2c_get_policy_async", "i2c_copy_wait", "i2c_get_policy_dev",
-    "i2c_shift_horizon", "i2c_ckf_step", "i2c_mpc_step", "i2c_get_initial_state", "i2c_get_first_action", "i2c_quadrature",
+    "i2c_shift_horizon", "i2c_ckf_step", "i2c_mpc_step", "i2c_get_initial_state", "i2c_get_first_action", "i2c_quadrature", "i2c_quadrature_gh", "i2c_gauss_hermite",
     "i2c_rollout", "i2c_snapshot_bytes", "i2c_snapshot", "i2c_restore", "i2c_kernel_launches", "i2c_last_run_ms", "i2c_dfma_peak",
     "i2c_last_error",
     "i2c_build_info",
@@ -123,6 +123,9 @@ def lib():
     L.i2c_mpc_step.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                C.c_double, C.c_void_p]
     L.i2c_get_first_action.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.i2c_quadrature_gh.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    L.i2c_gauss_hermite.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
     L.i2c_quadrature.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                  C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     L.i2c_rollout.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 6 + [C.c_int32] + [C.c_void_p] * 3 + [C.c_uint64] + \

@@ -41,7 +41,11 @@ class BatchedI2c:
         self.enable_aux = bool(enable_aux)
         self.max_iters = int(max_iters)
         self.inference = inference
-        inf_id = {"cubature": capi.INF_CUBATURE, "linearize": capi.INF_LINEARIZE}[inference]
+        inf_id = {"cubature": capi.INF_CUBATURE, "linearize": capi.INF_LINEARIZE, "gauss_hermite": capi.INF_GAUSS_HERMITE}[inference]
+        if inference == "gauss_hermite":
+            # GaussHermiteQuadrature(degree) (exp_types.py:52-68): `quadrature` is the degree (int or 1-tuple)
+            deg = int(quadrature[0] if np.ndim(quadrature) else quadrature)
+            quadrature = (float(deg), 0.0, 0.0)
         cfg = capi.Config(capi.ABI_VERSION, self.env_id, inf_id, B, T, self.max_iters, device, int(bool(z_per_problem)),
                           int(self.enable_aux), *map(float, quadrature))
         self._cfg = cfg
@@ -345,10 +349,18 @@ class BatchedI2c:
         return K, k, s
 
 
-def quadrature(env, fn, m, S, quad=(1.0, 0.0, 0.0), env_par=None, device=0):
+def gauss_hermite(degree):
+    """The library's 1-D Gauss-Hermite rule: nodes, weights / sqrt(pi) (exp_types.py:57, 66)."""
+    x, w = np.empty(degree), np.empty(degree)
+    capi.check(capi.lib().i2c_gauss_hermite(int(degree), capi.ptr(x), capi.ptr(w)))
+    return x, w
+
+
+def quadrature(env, fn, m, S, quad=(1.0, 0.0, 0.0), env_par=None, device=0, gh_degree=None):
     """Stand-alone sigma-point transform on the GPU (QuadratureInference.forward / forward_gaussian,
     inference/quadrature.py:27-58) for a registered env map.  fn in {"observe", "observe_terminal", "forward",
-    "measure"}.  m [B,d], S [B,d,d] -> m_y [B,dy], S_y [B,dy,dy], S_xy [B,d,dy], status [B]."""
+    "measure"}.  m [B,d], S [B,d,d] -> m_y [B,dy], S_y [B,dy,dy], S_xy [B,d,dy], status [B].
+    gh_degree: GaussHermiteQuadrature(degree) grid instead of the CubatureQuadrature(*quad) points."""
     L = capi.lib()
     env_id = capi.ENV_IDS[env]
     fn_id = {"observe": 0, "observe_terminal": 1, "forward": 2, "measure": 3}[fn]
@@ -367,8 +379,12 @@ def quadrature(env, fn, m, S, quad=(1.0, 0.0, 0.0), env_par=None, device=0):
         env_par = capi.f64(np.broadcast_to(env_par, (B, n_par)).copy())
     my, Sy, Sxy = np.empty((B, DY)), np.empty((B, DY, DY)), np.empty((B, D, DY))
     st = np.zeros(B, np.int32)
-    capi.check(L.i2c_quadrature(env_id, fn_id, B, capi.ptr(m), capi.ptr(S), *map(float, quad), capi.ptr(env_par),
-                                capi.ptr(my), capi.ptr(Sy), capi.ptr(Sxy), capi.ptr(st), device))
+    if gh_degree:
+        capi.check(L.i2c_quadrature_gh(env_id, fn_id, B, capi.ptr(m), capi.ptr(S), int(gh_degree), capi.ptr(env_par),
+                                       capi.ptr(my), capi.ptr(Sy), capi.ptr(Sxy), capi.ptr(st), device))
+    else:
+        capi.check(L.i2c_quadrature(env_id, fn_id, B, capi.ptr(m), capi.ptr(S), *map(float, quad), capi.ptr(env_par),
+                                    capi.ptr(my), capi.ptr(Sy), capi.ptr(Sxy), capi.ptr(st), device))
     return my, Sy, Sxy, st
 
 

@@ -124,11 +124,11 @@ def quad_kat():
 
 # ----------------------------------------------------------------------------- 2. EM runs
 def em_run(name, env_key, T, Q, R, Qf, alpha, tol, mu_u, sig_u, n_dump, n_total, mu_x_term=None, sig_x_term=None,
-           propagate=False, expert=True, x0=None):
+           propagate=False, expert=True, x0=None, inference=None):
     sys_ = ns.model.make_env_model(env_key, None)
     if x0 is not None:
         sys_.x0 = np.asarray(x0, float).reshape(-1, 1)
-    g = I2cGraph(sys_, T, Q, R, Qf, alpha, tol, mu_u, sig_u, mu_x_term, sig_x_term, Cub(1, 0, 0))
+    g = I2cGraph(sys_, T, Q, R, Qf, alpha, tol, mu_u, sig_u, mu_x_term, sig_x_term, inference or Cub(1, 0, 0))
     d = dict(env=env_key, T=T, Q=np.zeros(0) if Q is None else Q, R=R, Qf=np.zeros(0) if Qf is None else Qf,
              alpha0=alpha, tol=tol, mu_u=mu_u, sig_u=sig_u, x0=sys_.x0[:, 0],
              mu_x_term=np.zeros(0) if mu_x_term is None else np.asarray(mu_x_term, float).reshape(-1),
@@ -187,6 +187,45 @@ def em_runs():
     # linear minimum-energy system with cubature (well conditioned linear case)
     em_run("linear_minenergy_cubature_T40", "LinearKnownMinimumEnergy", 40, None, np.diag([1.0]), None, 10.0, 0.5,
            1e-2 * rng.normal(size=(40, 1)), 1e1 * np.eye(1), n_dump=2, n_total=6)
+
+
+def gauss_hermite():
+    """GaussHermiteQuadrature (exp_types.py:52-68) through the unmodified reference."""
+    GH = ns.exp_types.GaussHermiteQuadrature
+    d = {}
+    # the reference's own demo (inference/quadrature.py:86-104, 132): 2-D, degree 4
+    th = np.pi / 4
+    T = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    cov = T @ np.diag([0.5, 0.05]) @ T.T
+    rng = np.random.default_rng(17)
+    for key, deg in [("PendulumKnown", 4), ("PendulumKnown", 3), ("LinearKnown", 5), ("CartpoleKnown", 3)]:
+        sys_ = ns.model.make_env_model(key, None)
+        n, dx = sys_.dim_xu, sys_.dim_x
+        A = rng.normal(size=(n, n))
+        S_in = 0.05 * (A @ A.T) / n + 1e-3 * np.eye(n)
+        m_in = np.concatenate((sys_.x0[:, 0], [0.0] * sys_.dim_u)) + 0.3 * rng.normal(size=n)
+        qo = ns.quadrature.QuadratureInference(GH(deg), n)
+        mz, Sz = qo.forward(sys_.observe, m_in[:, None], S_in)
+        qd = ns.quadrature.QuadratureInference(GH(deg), n)
+        mx, Sx, Sn = qd.forward_gaussian(sys_.forward, m_in[:, None], S_in)
+        qt = ns.quadrature.QuadratureInference(GH(deg), dx)
+        mt, St = qt.forward(sys_.observe_terminal_x, m_in[:dx, None], S_in[:dx, :dx])
+        t = f"{key}/{deg}"
+        d[f"{t}/m_in"], d[f"{t}/S_in"] = m_in, S_in
+        d[f"{t}/obs_m"], d[f"{t}/obs_S"], d[f"{t}/obs_Sxy"] = mz[:, 0], Sz, qo.sig_xy
+        d[f"{t}/dyn_m"], d[f"{t}/dyn_S"], d[f"{t}/dyn_Sxy"], d[f"{t}/dyn_Sn"] = mx[:, 0], Sx, qd.sig_xy, Sn
+        d[f"{t}/term_m"], d[f"{t}/term_S"], d[f"{t}/term_Sxy"] = mt[:, 0], St, qt.sig_xy
+    for deg in (1, 2, 3, 4, 7):
+        sf, wm, ws = GH(deg).weights(2)
+        d[f"weights/{deg}"] = np.concatenate(([sf], wm))
+        d[f"pts/{deg}"] = GH(deg).pts(2)
+    save("gauss_hermite_kat", d)
+    exp = ref_shim.load_experiment("pendulum_known_quad", 0)
+    I = exp.INFERENCE
+    em_run("pendulum_gh3_T40", "PendulumKnown", 40, I.Q, I.R, I.Qf, 100.0, 0.0, 1e-2 * rng.normal(size=(40, 1)), I.sig_u,
+           n_dump=2, n_total=8, inference=GH(3))
+    em_run("pendulum_gh4_propagate_T20", "PendulumKnown", 20, I.Q, I.R, I.Qf, 100.0, 0.5, 1e-2 * rng.normal(size=(20, 1)),
+           I.sig_u, n_dump=2, n_total=4, inference=GH(4), propagate=True, expert=False)
 
 
 # ----------------------------------------------------------------------------- 3. LQR / Linearize
@@ -330,7 +369,7 @@ def mpc():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc"]
+    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc", "gh"]
     if "quad" in which:
         quad_kat()
     if "em" in which:
@@ -339,3 +378,5 @@ if __name__ == "__main__":
         lqr()
     if "mpc" in which:
         mpc()
+    if "gh" in which:
+        gauss_hermite()
