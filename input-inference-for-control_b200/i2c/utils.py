@@ -43,3 +43,80 @@ def finite_horizon_lqr(H, A, a, B, Q, R, x0, xg, ug, dim_x, dim_u):
         x = A @ x + B @ u + a
     cost += (x - xg) @ Q @ (x - xg)
     return x_lqr, u_lqr, K, k, cost, Ps, ps
+
+
+def _quadratic_traj_cost(W, Wf, zg, zg_term, dim_x, z, z_term):
+    """sum_{t < T-1} (z_t - zg)^T W (z_t - zg) [+ terminal (x_T - xg)^T Wf (x_T - xg)]: the last step of the trajectory is
+    dropped and only the first dim_x terminal features count, as in i2c/utils.py:116-121, 160-168."""
+    e = np.asarray(z, float).reshape(-1, W.shape[0])[:-1] - zg.reshape(1, -1)
+    cost = float(np.sum((e @ W) * e))
+    if z_term is not None:
+        et = (np.asarray(z_term, float).reshape(1, -1) - zg_term.reshape(1, -1))[-1, :dim_x]
+        cost += float(et @ Wf @ et)
+    return cost
+
+
+class TrajectoryEvaluator(object):
+    """Cost of one executed roll-out next to the planned one (interface of i2c/utils.py:103-148)."""
+
+    def __init__(self, W, Wf, sg, sg_term, dim_x):
+        self.W, self.Wf = np.asarray(W, float), np.asarray(Wf, float)
+        self.sg, self.sg_term = np.asarray(sg, float).reshape(-1, 1), np.asarray(sg_term, float).reshape(-1, 1)
+        self.dim_x = dim_x
+        self.actual_cost, self.planned_cost = [], []
+        if self.W.shape != (self.sg.shape[0],) * 2:
+            raise AssertionError("W must be square and match the feature goal")
+
+    def _eval_traj(self, s, s_terminal):
+        return _quadratic_traj_cost(self.W, self.Wf, self.sg, self.sg_term, self.dim_x, s, np.asarray(s_terminal)[-1])
+
+    def eval(self, actual_traj, actual_terminal, planned_traj, planned_terminal):
+        self.actual_cost.append(self._eval_traj(actual_traj, actual_terminal))
+        self.planned_cost.append(self._eval_traj(planned_traj, planned_terminal))
+
+    def plot(self, name, res_dir=None):
+        logging.info("TrajectoryEvaluator.plot: plotting is outside the CUDA path (SURVEY.md section 2)")
+
+    def save(self, name, res_dir):
+        import os
+
+        np.save(os.path.join(res_dir, f"cost_actual_{name}.npy"), np.asarray(self.actual_cost))
+        np.save(os.path.join(res_dir, f"cost_plan_{name}.npy"), np.asarray(self.planned_cost))
+
+
+class StochasticTrajectoryEvaluator(object):
+    """Cost statistics (mean, min, max, 10th / 90th percentile) over a batch of roll-outs, e.g. the output of
+    ``env.batch_eval`` (interface of i2c/utils.py:151-265; file names of ``save`` as read by process_results.py)."""
+
+    def __init__(self, W, Wf, sg, sg_term, dim_x):
+        self.W, self.Wf = np.asarray(W, float), np.asarray(Wf, float)
+        self.sg, self.sg_term = np.asarray(sg, float).reshape(-1, 1), np.asarray(sg_term, float).reshape(-1, 1)
+        self.dim_x, self.dim_s = dim_x, self.W.shape[0]
+        self.mu_actual_cost, self.max_actual_cost, self.min_actual_cost = [], [], []
+        self.actual_cost_10, self.actual_cost_90, self.planned_cost = [], [], []
+        if self.W.shape[1] != self.dim_s or self.sg.shape[0] != self.dim_s:
+            raise AssertionError(f"{self.sg.shape[0]} ~= {self.dim_s}")
+
+    def _eval_traj(self, s, s_term):
+        return _quadratic_traj_cost(self.W, self.Wf, self.sg, self.sg_term, self.dim_x, s, s_term)
+
+    def eval(self, actual_trajs, actual_trajs_term, planned_traj, planned_traj_term):
+        costs = np.array([self._eval_traj(z, zt) for z, zt in zip(actual_trajs, actual_trajs_term)])
+        self.mu_actual_cost.append(costs.mean())
+        self.min_actual_cost.append(costs.min())
+        self.max_actual_cost.append(costs.max())
+        lo, hi = np.percentile(costs, (10, 90))
+        self.actual_cost_10.append(lo)
+        self.actual_cost_90.append(hi)
+        self.planned_cost.append(self._eval_traj(planned_traj, planned_traj_term))
+
+    def plot(self, name, res_dir=None):
+        logging.info("StochasticTrajectoryEvaluator.plot: plotting is outside the CUDA path (SURVEY.md section 2)")
+
+    plot_sample = plot
+
+    def save(self, name, res_dir):
+        import os
+
+        np.save(os.path.join(res_dir, f"cost_actual_mean_{name}.npy"), np.asarray(self.mu_actual_cost))
+        np.save(os.path.join(res_dir, f"cost_plan_{name}.npy"), np.asarray(self.planned_cost))

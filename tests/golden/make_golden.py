@@ -368,8 +368,40 @@ def mpc():
             save(f"mpc_quadrotor_{'ff' if feedforward else 'fb'}_{'low' if low_noise else 'high'}", d)
 
 
+def evaluators():
+    """TrajectoryEvaluator / StochasticTrajectoryEvaluator (i2c/utils.py:103-265): the consumers of the roll-outs in
+    scripts/i2c_run.py:66-106, and the cost_*.npy files they write."""
+    import tempfile
+
+    rng = np.random.default_rng(5)
+    T, R, dz, dzt, dx = 30, 12, 4, 3, 2
+    A = rng.normal(size=(dz, dz))
+    W = A @ A.T
+    Af = rng.normal(size=(dx, dx))
+    Wf = Af @ Af.T
+    sg, sg_term = rng.normal(size=dz), rng.normal(size=dzt)
+    d = dict(W=W, Wf=Wf, sg=sg, sg_term=sg_term, dim_x=dx)
+    ev = ns.utils.StochasticTrajectoryEvaluator(W, Wf, sg, sg_term, dx)
+    det = ns.utils.TrajectoryEvaluator(W, Wf, sg, sg_term, dx)
+    for k in range(3):
+        trajs, terms = rng.normal(size=(R, T, dz)), rng.normal(size=(R, dzt))
+        plan, plan_term = rng.normal(size=(T, dz)), rng.normal(size=(1, dzt))
+        ev.eval(trajs, terms, plan, plan_term)
+        det.eval(trajs[0], terms[:1], plan, plan_term)
+        d[f"{k}/trajs"], d[f"{k}/terms"], d[f"{k}/plan"], d[f"{k}/plan_term"] = trajs, terms, plan, plan_term
+    for name in ["mu_actual_cost", "max_actual_cost", "min_actual_cost", "actual_cost_10", "actual_cost_90", "planned_cost"]:
+        d[f"stoch/{name}"] = np.asarray(getattr(ev, name), float)
+    d["det/actual_cost"], d["det/planned_cost"] = np.asarray(det.actual_cost, float), np.asarray(det.planned_cost, float)
+    with tempfile.TemporaryDirectory() as tmp:
+        ev.save("x", tmp)
+        det.save("y", tmp)
+        for f in sorted(os.listdir(tmp)):
+            d[f"file/{f}"] = np.load(os.path.join(tmp, f))
+    save("evaluator_kat", d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc", "gh"]
+    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc", "gh", "eval"]
     if "quad" in which:
         quad_kat()
     if "em" in which:
@@ -380,3 +412,5 @@ if __name__ == "__main__":
         mpc()
     if "gh" in which:
         gauss_hermite()
+    if "eval" in which:
+        evaluators()
