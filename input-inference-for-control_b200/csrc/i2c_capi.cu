@@ -837,6 +837,12 @@ static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   kp.ric = h->ric;
   kp.linearize = h->cfg.inference == I2C_INF_LINEARIZE;
   kp.no_team = getenv("I2C_B200_NO_TEAM") != nullptr;
+  {
+    const char* gm = getenv("I2C_B200_GROUP");
+    kp.group_mode = gm ? atoi(gm) : -1;
+    const char* gt = getenv("I2C_B200_GROUP_MAX_TILES");
+    kp.group_max_tiles = gt ? atoi(gt) : 0;
+  }
   kp.term = h->term;
   kp.x0 = h->x0;
   kp.sig_x0 = h->sig_x0;

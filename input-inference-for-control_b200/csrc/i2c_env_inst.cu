@@ -1,6 +1,7 @@
 // One translation unit per environment: compiled with -DI2C_ENV_ID=<enum i2c_env> (see __graft_entry__.build()).
 #include "i2c_kernels.cuh"
 #include "i2c_scan.cuh"
+#include "i2c_group.cuh"
 
 #ifndef I2C_ENV_ID
 #error "compile with -DI2C_ENV_ID=<0..6>"

@@ -1974,6 +1974,10 @@ static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
   return (int)cudaGetLastError();
 }
 
+constexpr int kGroupNotTaken = -12345;
+template <class Env>
+static int launch_em_group_maybe(const KParams& p, cudaStream_t s);  // i2c_group.cuh
+
 template <class Env>
 static int launch_em_t(const KParams& p, cudaStream_t s) {
   // one warp per tile of 32 problems; small blocks spread the warps over all SMs / sub-partitions
@@ -1984,6 +1988,11 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   if (p.linearize) return launch_em_v<Env, 1, true, true>(p, s, threads);
   // Gauss-Hermite grids: degree^n points per transform, one variant as well
   if (p.gh.degree > 0) return launch_em_v<Env, 1, true, false, true>(p, s, threads);
+  // small batches: G lanes per problem (i2c_group.cuh); the launcher there decides
+  {
+    const int rc = launch_em_group_maybe<Env>(p, s);
+    if (rc != kGroupNotTaken) return rc;
+  }
   // fewer tiles than SMs: spread each tile's backward pass over the 8 warps of a block (one block per SM)
   if (p.ntiles <= 148 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 8>(p, s);
   if (p.ntiles <= 296 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 4>(p, s);  // two blocks per SM

@@ -52,6 +52,8 @@ struct KParams {
   int32_t fast_obs;   // cubature rule has zero centre weight and unit weight sum: structured cost-feature moments
   int32_t no_team;    // debugging / A-B: force the one-warp-per-tile kernel
   int32_t stage_meta; // stage the cell targets / flags with the records (latency regime only; set by the launcher)
+  int32_t group_mode;      // -1 auto, 0 never, 1 always: G-lanes-per-problem kernel (i2c_group.cuh)
+  int32_t group_max_tiles; // auto: use it up to this many tiles
   int32_t linearize;  // Linearize inference (linear envs only): exact moments instead of sigma points
   double alpha_tol, temp0, dtemp;
   double sf_n, w0_n, wi_n;  // cubature rule in dim n = dx+du (exp_types.py:36-49)
