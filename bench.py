@@ -309,6 +309,9 @@ def run_cuda(args, rank, world, local_rank):
         del gs
     if mpc is not None:
         line["mpc"] = mpc
+    line["em_iterations_per_s"] = {"batch_sweeps_per_s": 1e3 * K / ms, "problem_iterations_per_s": world * B * K / (ms * 1e-3)}
+    if world == 1 and args.scan_horizon > 0:
+        line["time_parallel"] = scan_leg(args, dev)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_cpu_it = 24  # ~10-30 s of CPU work per core
@@ -319,6 +322,41 @@ def run_cuda(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def scan_leg(args, dev):
+    """Parallel-in-time variant (i2c_run_scan, csrc/i2c_scan.cuh) on a long-horizon linear-Gaussian problem: the horizon
+    is cut into chunks that are filtered / smoothed concurrently (associative Kalman / RTS elements).  Sequential kernel
+    beside it; both produce the same records (tests/test_gpu_scan.py)."""
+    import i2c_b200
+
+    B, T, chunk = 32, args.scan_horizon, 64
+    rng = np.random.default_rng(5)
+    A = np.array([[1.0, 0.1], [-0.05, 0.98]]) + 0.01 * rng.normal(size=(B, 2, 2))
+    xg = rng.normal(size=(B, 2))
+    par = i2c_b200.envs.linear_params(A, np.array([[0.0], [0.1]]), xg - np.einsum("bij,bj->bi", A, xg))
+    z = np.repeat(np.concatenate((xg, np.zeros((B, 1))), axis=1)[:, None, :], T, axis=1)
+    out = {"problems": B, "horizon": T, "chunk_cells": chunk, "inference": "Linearize, LinearKnown (exact scan)"}
+    ref = None
+    for name, ch in (("sequential", None), ("scan", chunk)):
+        G = i2c_b200.BatchedI2c("LinearKnown", B, T, np.diag([1.0, 2.0]), np.diag([0.5]), np.diag([1.0, 2.0]), 5.0, 0.5,
+                                1e-2 * rng.normal(size=(B, T, 1)) * 0, np.eye(1), x0=xg + 2.0, sig_x0=1e-2 * np.eye(2),
+                                sig_eta=1e-3 * np.eye(2), env_par=par, z=z, z_term=xg, z_per_problem=True, inference="linearize",
+                                device=dev, max_iters=8)
+        G.time_parallel_chunk = ch
+        G.forward_backward(2)
+        G.synchronize()
+        G.forward_backward(5)
+        G.synchronize()
+        out[f"{name}_ms_per_sweep_pair"] = G.last_run_ms() / 5
+        K = G.field("K")
+        if ref is None:
+            ref = K
+        else:
+            out["max_rel_diff_K"] = float(np.max(np.abs(K - ref)) / np.max(np.abs(ref)))
+        G.close()
+    out["speedup"] = out["sequential_ms_per_sweep_pair"] / out["scan_ms_per_sweep_pair"]
+    return out
 
 
 def mpc_leg(args, dev, rank, world, max_over_ranks, barrier):
@@ -385,6 +423,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--saturation", type=int, default=65536, help="extra large-batch measurement at N=1 (0 = off)")
     ap.add_argument("--mpc-rollouts", type=int, default=8192, help="roll-outs per GPU of the MPC leg (0 = off)")
+    ap.add_argument("--scan-horizon", type=int, default=4096, help="horizon of the parallel-in-time leg at N=1 (0 = off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

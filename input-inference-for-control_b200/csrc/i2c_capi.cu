@@ -1174,6 +1174,7 @@ int i2c_shift_horizon(i2c_handle_t h, const double* z_new, const double* mu_u_in
   return rc;
 }
 
+static int ckf_step_impl(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta, bool sync);
 // One closed-loop MPC step with a single synchronisation: PartiallyObservedMpcPolicy.__call__
 // (policy/mpc.py:156-182) = [filter] -> n_iter x (forward, backward, _update_priors) -> first action -> horizon shift.
 int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const double* u_prev, const double* sig_zeta,
@@ -1185,7 +1186,7 @@ int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const doubl
   int rc = 0;
   if (do_filter) {
     REQUIRE(y && u_prev && sig_zeta, "filter step needs y, u_prev, sig_zeta");
-    rc = i2c_ckf_step(h, y, u_prev, sig_zeta);  // enqueues + one sync (staging buffer reuse)
+    rc = ckf_step_impl(h, y, u_prev, sig_zeta, false);  // stream-ordered; the single synchronisation is at the end
     if (rc) return rc;
   }
   rc = i2c_run(h, n_iter, I2C_PH_FORWARD | I2C_PH_BACKWARD | I2C_PH_UPDATE_PRIORS);
@@ -1220,7 +1221,12 @@ int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const doubl
   return 0;
 }
 
+static int ckf_step_impl(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta, bool sync);
 int i2c_ckf_step(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta) {
+  return ckf_step_impl(h, y, u, sig_zeta, true);
+}
+// sync = false: the caller synchronises the stream before the borrowed host buffers go out of scope (i2c_mpc_step)
+static int ckf_step_impl(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta, bool sync) {
   REQUIRE(h && y && u && sig_zeta, "NULL argument");
   REQUIRE(h->d.dy > 0, "this env defines no measurement map (only the quadrotor does)");
   const int dx = h->d.dx, du = h->d.du, dy = h->d.dy;
@@ -1251,7 +1257,7 @@ int i2c_ckf_step(i2c_handle_t h, const double* y, const double* u, const double*
   int rc = launch_ckf(h->cfg.env, a, (void*)h->stream);
   h->launches += 3;
   if (rc != 0) return set_err(-100 - rc, "CKF kernel launch failed");
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (sync) CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
