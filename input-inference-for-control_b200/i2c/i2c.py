@@ -370,6 +370,84 @@ class I2cGraph(object):
                 self.costs_pf += [-1.0] * n
             done += n
 
+    # ---- alpha bookkeeping on the host (names of the reference; the sweeps update alpha on the device) ----------
+    def get_z_covar(self):
+        """sum_t E[(z_t - z)(z_t - z)^T] under the posterior (i2c.py:983-984)."""
+        return sum(c.expected_observation_covar() for c in self.cells)
+
+    def get_z_propagated_covar(self):
+        return sum(c.expected_propagated_observation_covar() for c in self.cells)
+
+    def get_z_terminal_covar(self):
+        c = self.cells[-1]
+        d = np.asarray(self.z_term, float).reshape(-1, 1) - np.asarray(c.mu_z3_m, float).reshape(-1, 1)
+        return d @ d.T + c.sig_z3_m
+
+    def calculate_alpha(self, z_covar, z_covar_term=None):
+        tr, sf = np.trace(self.QR @ z_covar), float(self.sys.dim_z * self.H)
+        if z_covar_term is not None:
+            tr += np.trace(self.Qf @ z_covar_term)
+            sf += float(self.sys.dim_z_term)
+        return tr / sf
+
+    def compute_update_alpha(self, update_alpha, *unused, **unused_kw):
+        """i2c.py:921-946 on the current device messages (extra arguments of the call in policy/mpc.py:59 are accepted
+        and ignored, the reference's own signature takes none)."""
+        term = self.get_z_terminal_covar() if self.sig_xi_terminal_base is not None else None
+        alpha_update = self.calculate_alpha(self.get_z_covar(), term)
+        if self._propagate:
+            self.alphas_pf.append(self.calculate_alpha(self.get_z_propagated_covar()))
+        self.alphas_desired.append(alpha_update)
+        if update_alpha:
+            self.update_alpha(alpha_update)
+        self.alphas.append(self.alpha)
+
+    def update_alpha(self, alpha_update):
+        if np.isnan(alpha_update):
+            raise ValueError("Alpha is NaN")
+        if self.alpha_update_tol >= 0.0:
+            ratio, upper = alpha_update / self.alpha, 2.0 - self.alpha_update_tol
+            if ratio < self.alpha_update_tol:
+                alpha_update = self.alpha_update_tol * self.alpha
+            if ratio > upper:
+                alpha_update = upper * self.alpha
+        else:
+            alpha_update = self.alpha
+        self._update_alpha(alpha_update)
+
+    def _update_alpha(self, update):
+        self.alpha = update  # i2c_set_alpha: sig_xi = alpha * QR^-1 is rebuilt by every cell on the device
+
+    def _override_alpha(self, update):
+        self.alphas[-1] = update
+        self.alpha = update
+
+    def update_xi(self, *unused):
+        pass  # cells read alpha * sig_xi0 from the graph (device scalar); nothing to broadcast
+
+    def update_models(self):
+        pass
+
+    @property
+    def propagate_cost_improved(self):
+        return self.costs_pf[-1] <= self.costs_pf[-2] if len(self.costs_pf) > 1 else True
+
+    def get_prior_state_action_distribution(self):
+        return self._g.field("mu_xu0_f")[0].copy(), self._g.field("sig_xu0_f")[0].copy()
+
+    def get_propagated_state(self):
+        dx = self.sys.dim_x
+        return self._field("mu_xu0_pf")[:, :dx].copy(), self._field("sig_xu0_pf")[:, :dx, :dx].copy()
+
+    def __getattr__(self, name):
+        # plot_traj / plot_metrics / plot_alphas / plot_cost / ... (i2c.py:1403-1818): figures are outside the CUDA path;
+        # the scripts' calls are accepted and logged so that they run unchanged
+        if name.startswith("plot_"):
+            def _no_plot(*a, **k):
+                logging.info(f"I2cGraph.{name}: plotting is not part of the CUDA path (skipped)")
+            return _no_plot
+        raise AttributeError(name)
+
     # ---- getters ----------------------------------------------------------------------------------------
     def get_local_linear_policy(self):
         K, k, s = self._g.get_local_linear_policy()

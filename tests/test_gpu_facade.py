@@ -226,3 +226,31 @@ def test_linearize_pendulum_flow(mirror):
     K, k, s = i2c.get_local_linear_policy()
     Kr, kr, sr = ref.get_local_linear_policy()
     assert relerr(K, Kr[0]) < 1e-4 and relerr(k, kr[0]) < 1e-4 and relerr(s, sr[0]) < 1e-5
+
+
+def test_alpha_helpers_match_device_update(mirror):
+    """compute_update_alpha / calculate_alpha / get_z_covar (i2c.py:913-992) recomputed on the host from the device
+    messages reproduce the alpha the M-step kernel produced; plot_* calls of the scripts are accepted."""
+    g = golden("pendulum_T200_x0pert")
+    T = 60
+    model = mirror.make_env_model("PendulumKnown", None)
+    model.x0 = g["x0"].reshape(-1, 1)
+    graph = mirror.I2cGraph(model, T, g["Q"], g["R"], g["Qf"], 100.0, 0.5, g["mu_u"][:T], g["sig_u"], None, None,
+                            mirror.CubatureQuadrature(1, 0, 0))
+    graph._forward_backward_msgs()
+    a0 = graph.alpha
+    desired = graph.calculate_alpha(graph.get_z_covar(), graph.get_z_terminal_covar())
+    graph.compute_update_alpha(True)  # host recomputation + i2c_set_alpha
+    host_alpha = graph.alpha
+    assert abs(graph.alphas_desired[-1] - desired) < 1e-12 * desired
+    # same sweep through the fused device path
+    graph2 = mirror.I2cGraph(model, T, g["Q"], g["R"], g["Qf"], 100.0, 0.5, g["mu_u"][:T], g["sig_u"], None, None,
+                             mirror.CubatureQuadrature(1, 0, 0))
+    graph2.learn_msgs()
+    assert abs(graph2.alphas_desired[-1] - desired) < 1e-10 * desired
+    assert abs(graph2.alpha - host_alpha) < 1e-10 * host_alpha and host_alpha != a0
+    assert graph.propagate_cost_improved is True
+    graph.plot_metrics(0, 0, None, "msg")  # scripts/i2c_run.py:123
+    graph.plot_traj(0, dir_name=None, filename="lqr")  # scripts/lqr_compare.py:172
+    with pytest.raises(AttributeError):
+        graph.no_such_attribute
