@@ -221,14 +221,7 @@ def run_cuda(args, rank, world, local_rank):
         bK, bk, bs = h_pol[i & 1]
         capi.check(L.i2c_get_policy_async(g._h, capi.ptr(bK), capi.ptr(bk), capi.ptr(bs)))
 
-    e2e_step(0)
-    capi.check(L.i2c_copy_wait(g._h))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        e2e_step(i)
-    capi.check(L.i2c_copy_wait(g._h))
-    if dist is not None:
+    def final_gather():
         # the path's only collective: final gather of controllers and costs over NVLink
         from i2c_b200 import dist as idist
 
@@ -236,6 +229,19 @@ def run_cuda(args, rank, world, local_rank):
         cost = torch.from_numpy(np.ascontiguousarray(h_m[0])).to(Kd.device)
         gathered = idist.gather_controllers(Kd, kd, sd, world * B, extra=(cost,))
         assert gathered[0].shape[0] == world * B
+        torch.cuda.synchronize(dev)
+
+    e2e_step(0)
+    capi.check(L.i2c_copy_wait(g._h))
+    if dist is not None:
+        final_gather()  # warm-up of the collective (communicator buffers, allocator), like the untimed first step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e_step(i)
+    capi.check(L.i2c_copy_wait(g._h))
+    if dist is not None:
+        final_gather()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * B * T * Ke / (e2e_ms * 1e-3)
