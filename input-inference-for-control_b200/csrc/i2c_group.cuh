@@ -125,28 +125,39 @@ struct GroupWorker {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     gsync();
   }
-  // Cholesky by columns J0 .. NN-1 of the lower triangle of A (leading dimension LD), rows below the pivot in
-  // parallel; columns < J0 are already final in every row.  The pivot is computed redundantly by every lane (no
-  // broadcast); the diagonal of L is written once at the end (one barrier per column).  Same operation order per
-  // entry as chol_rows.
+  // Cholesky of the lower triangle of A (leading dimension LD), rows >= J0 (rows < J0 already hold L and invd their
+  // reciprocal pivots), eliminated column by column with the rows below the pivot in parallel.  The pivot is computed
+  // redundantly by every lane (no broadcast); the diagonal of L is written once at the end (one barrier per column).
+  // Same operation order per entry as chol_rows.  (Tried and rejected: every lane factorising the whole matrix in
+  // registers -- the unrolled code of the five factorisations per cell no longer fits the instruction cache and the
+  // kernel became fetch-bound: 6.0k instead of 2.4k cycles for the 7x7 factorisation.)
   template <int NN, int LD, int J0>
-  __device__ __noinline__ bool chol_cols(double* A, double* invd) {
+  __device__ __noinline__ static bool chol_cols_impl(double* A, double* invd, const int r) {
+    // (static + explicit arguments: a non-inlined MEMBER function would take `this`, forcing the whole worker object
+    // into local memory and every shared-memory access through generic loads)
+    __builtin_assume(__isShared(A));
+    __builtin_assume(__isShared(invd));
     bool ok = true;
     double mydiag[(NN + G - 1) / G], myinv[(NN + G - 1) / G];
+    // rows J0.. first eliminate the columns < J0 against the finished rows (nothing to do for J0 = 0)
 #pragma unroll
-    for (int j = J0; j < NN; ++j) {
-      double d = A[j * LD + j];
+    for (int j = 0; j < NN; ++j) {
+      double d = A[j * LD + j], ri = 0.0;
+      if (j >= J0) {
 #pragma unroll
-      for (int k = 0; k < j; ++k) d = fma(-A[j * LD + k], A[j * LD + k], d);
-      ok = ok && (d > 0.0) && (d < 1.0e300);
-      const double ri = fast_rsqrt(d);
+        for (int k = 0; k < j; ++k) d = fma(-A[j * LD + k], A[j * LD + k], d);
+        ok = ok && (d > 0.0) && (d < 1.0e300);
+        ri = fast_rsqrt(d);
+      } else {
+        ri = invd[j];
+      }
       I2C_FOR_ROWS(i, NN) {
-        if (i > j) {
+        if (i > j && i >= J0) {
           double s = A[i * LD + j];
 #pragma unroll
           for (int k = 0; k < j; ++k) s = fma(-A[i * LD + k], A[j * LD + k], s);
           A[i * LD + j] = s * ri;
-        } else if (i == j) {
+        } else if (i == j && j >= J0) {
           mydiag[i_0 / G] = d * ri;
           myinv[i_0 / G] = ri;
         }
@@ -161,6 +172,10 @@ struct GroupWorker {
     }
     gsync();
     return ok;
+  }
+  template <int NN, int LD, int J0>
+  __device__ __forceinline__ bool chol_cols(double* A, double* invd) const {
+    return chol_cols_impl<NN, LD, J0>(A, invd, r);
   }
   // y <- L^-1 y / L^-T y for a register vector
   template <int NN, int LD>
@@ -187,9 +202,29 @@ struct GroupWorker {
   // Sigma-point transform around (m, L) in dimension D -> my[DY], Syy (lower, ld LDS, optionally + noise * Nz),
   // Sxy[D][DYM] = L * Dm.  Points +-j are spread over the lanes; then feature rows / state rows are.
   template <int D, int DY, int LDL, int LDS, class Eval>
-  __device__ __noinline__ void transform(const double* m, const double* L, double sf, double w0, double wi, Eval eval,
-                                         double* my, double* Syy, double* Sxy, bool want_sxy, double noise, const double* Nz) {
-    double* Y = sm + GL::O_Y;
+  __device__ __forceinline__ void transform(const double* m, const double* L, double sf, double w0, double wi, Eval eval,
+                                            double* my, double* Syy, double* Sxy, bool want_sxy, double noise, const double* Nz) {
+    transform_impl<D, DY, LDL, LDS, Eval>(m, L, sf, w0, wi, wk.par, sm + GL::O_Y, my, Syy, Sxy, want_sxy, r);
+    if (Nz) {  // observation noise on the rows this lane owns (it wrote them itself: no barrier needed)
+      I2C_FOR_ROWS(a, DY) {
+#pragma unroll
+        for (int b = 0; b < DY; ++b)
+          if (b <= a) Syy[a * LDS + b] = fma(noise, Nz[a * DY + b], Syy[a * LDS + b]);
+      }
+      gsync();
+    }
+  }
+  template <int D, int DY, int LDL, int LDS, class Eval>
+  __device__ __noinline__ static void transform_impl(const double* m, const double* L, double sf, double w0, double wi,
+                                                     const double* par, double* Y, double* my, double* Syy, double* Sxy,
+                                                     bool want_sxy, const int r) {
+    __builtin_assume(__isShared(m));
+    __builtin_assume(__isShared(L));
+    __builtin_assume(__isShared(Y));
+    __builtin_assume(__isShared(my));
+    __builtin_assume(__isShared(Syy));
+    if (want_sxy) __builtin_assume(__isShared(Sxy));
+    const Eval eval;
     TrigT ctx;
     Env::center(m, ctx);
     const bool centre = w0 != 0.0;
@@ -205,7 +240,7 @@ struct GroupWorker {
           x[i] = minus ? m[i] - d : m[i] + d;
         }
       }
-      eval(x, j, ctx, wk.par, y);
+      eval(x, j, ctx, par, y);
 #pragma unroll
       for (int a = 0; a < DY; ++a) Y[pt * DYM + a] = y[a];
     }
@@ -240,7 +275,6 @@ struct GroupWorker {
           s = wi * s;
           if (centre) s = fma(w0 * Y[(2 * D) * DYM + a], Y[(2 * D) * DYM + b], s);
           s = fma(-mine, mya[b], s);
-          if (Nz) s = fma(noise, Nz[a * DY + b], s);
           Syy[a * LDS + b] = s;
         }
       }
@@ -261,19 +295,181 @@ struct GroupWorker {
     gsync();
   }
 
+  // Structured moments of the cost-feature maps (same shortcut as structured_obs_moments of the per-thread kernels;
+  // valid for the cubature rule with zero centre weight): identity features have exact moments (copies of mu / Sigma),
+  // only the NL trigonometric features are integrated, and only the sigma-point columns j <= OBS_JMAX move them.
+  // Sig: the covariance the factor L belongs to (full, leading dimension LDL as L).
+  template <int D, int DY, int LDL, bool TERM>
+  __device__ __noinline__ static void structured_impl(const double* m, const double* Sig, const double* L, double sf, double wi,
+                                                      double* Y, double* my, double* Syy, double* Sxy, double* Cx,
+                                                      bool want_sxy, const int r) {
+    __builtin_assume(__isShared(m));
+    __builtin_assume(__isShared(Sig));
+    __builtin_assume(__isShared(L));
+    __builtin_assume(__isShared(Y));
+    __builtin_assume(__isShared(my));
+    __builtin_assume(__isShared(Syy));
+    __builtin_assume(__isShared(Cx));
+    if (want_sxy) __builtin_assume(__isShared(Sxy));
+    constexpr int NL = Env::OBS_NL, JM = Env::OBS_JMAX, NLs = NL > 0 ? NL : 1, NP = 2 * (JM + 1);
+    double mnl[NLs], Snl[TRI(NLs)];
+    if constexpr (NL > 0) {
+      double mc[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) mc[i] = m[i];
+      TrigT ctx;
+      Env::center(mc, ctx);
+      for (int pt = r; pt < NP; pt += G) {
+        const int j = pt >> 1;
+        const bool minus = pt & 1;
+        double x[D], y[NL];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          x[i] = mc[i];
+          if (i >= j) {
+            const double d = sf * L[i * LDL + j];
+            x[i] = minus ? mc[i] - d : mc[i] + d;
+          }
+        }
+        Env::trig_nl(x, j, ctx, y);
+#pragma unroll
+        for (int a = 0; a < NL; ++a) Y[pt * DYM + a] = y[a];
+      }
+      gsync();
+      double yc[NL], sy[NL], syy[TRI(NL)];
+      Env::trig_nl(mc, -1, ctx, yc);
+      constexpr double mult = 2.0 * (D - 1 - JM);
+#pragma unroll
+      for (int a = 0; a < NL; ++a) {
+        sy[a] = mult * yc[a];
+#pragma unroll
+        for (int b = 0; b <= a; ++b) syy[tix(a, b)] = mult * yc[a] * yc[b];
+      }
+#pragma unroll
+      for (int j = 0; j <= JM; ++j) {
+        const double* yp = Y + (2 * j) * DYM;
+        const double* ym = yp + DYM;
+#pragma unroll
+        for (int a = 0; a < NL; ++a) {
+          sy[a] += yp[a] + ym[a];
+#pragma unroll
+          for (int b = 0; b <= a; ++b) syy[tix(a, b)] = fma(yp[a], yp[b], fma(ym[a], ym[b], syy[tix(a, b)]));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NL; ++a) mnl[a] = wi * sy[a];
+#pragma unroll
+      for (int a = 0; a < NL; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) Snl[tix(a, b)] = fma(wi, syy[tix(a, b)], -mnl[a] * mnl[b]);
+      // cross covariance of the state rows with the nonlinear block: Cx[i][k] = sum_{j <= min(i, JM)} L[i][j] Dm[j][k]
+      const double wsf = wi * sf;
+      I2C_FOR_ROWS(i, D) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+          double v = 0.0;
+#pragma unroll
+          for (int j = 0; j <= JM; ++j)
+            if (j <= i) v = fma(L[i * LDL + j], wsf * (Y[(2 * j) * DYM + k] - Y[(2 * j + 1) * DYM + k]), v);
+          Cx[i * NLs + k] = v;
+        }
+      }
+      gsync();
+    }
+    // assemble: feature row a per lane (my, Syy lower), state row i per lane (Sxy)
+    I2C_FOR_ROWS(a, DY) {
+      const int sa = TERM ? Env::term_src(a) : Env::obs_src(a);
+      double v = 0.0;
+      if (sa >= 0) {
+        v = m[sa];
+      } else {
+#pragma unroll
+        for (int k = 0; k < NLs; ++k)
+          if (k == -1 - sa) v = mnl[k];
+      }
+      my[a] = v;
+#pragma unroll
+      for (int b = 0; b < DY; ++b) {
+        if (b <= a) {
+          const int sb = TERM ? Env::term_src(b) : Env::obs_src(b);  // (b is a compile-time constant here)
+          double w = 0.0;
+          if (sa >= 0 && sb >= 0) {
+            w = Sig[sa * LDL + sb];
+          } else if (sa < 0 && sb < 0) {
+#pragma unroll
+            for (int k = 0; k < NLs; ++k)
+#pragma unroll
+              for (int l = 0; l < NLs; ++l)
+                if (k == -1 - sa && l == -1 - sb) w = Snl[six(k, l)];
+          } else if (sa < 0) {
+            w = Cx[(sb >= 0 ? sb : 0) * NLs + (-1 - sa)];
+          } else {
+            w = Cx[sa * NLs + (sb < 0 ? -1 - sb : 0)];
+          }
+          Syy[a * DYM + b] = w;
+        }
+      }
+    }
+    if (want_sxy) {
+      I2C_FOR_ROWS(i, D) {
+#pragma unroll
+        for (int a = 0; a < DY; ++a) {
+          const int sa = TERM ? Env::term_src(a) : Env::obs_src(a);
+          Sxy[i * DYM + a] = sa >= 0 ? Sig[i * LDL + (sa >= 0 ? sa : 0)] : Cx[i * NLs + (sa < 0 ? -1 - sa : 0)];
+        }
+      }
+    }
+    gsync();
+  }
+  // cost-feature moments of (m, Sig, L): structured when the rule allows it, else the generic sigma-point transform
+  template <int D, int DY, int LDL, bool TERM>
+  __device__ __forceinline__ void obs_moments(const double* m, const double* Sig, const double* L, double sf, double w0, double wi,
+                                              bool want_sxy, double noise, const double* Nz) {
+    double* my = sm + GL::O_MY;
+    double* Syy = sm + GL::O_SYY;
+    double* Sxy = sm + GL::O_SXY;
+    if (p.fast_obs) {
+      structured_impl<D, DY, LDL, TERM>(m, Sig, L, sf, wi, sm + GL::O_Y, my, Syy, Sxy, sm + GL::O_TMP, want_sxy, r);
+      if (Nz) {
+        I2C_FOR_ROWS(a, DY) {
+#pragma unroll
+          for (int b = 0; b < DY; ++b)
+            if (b <= a) Syy[a * DYM + b] = fma(noise, Nz[a * DY + b], Syy[a * DYM + b]);
+        }
+        gsync();
+      }
+    } else if constexpr (TERM) {
+      transform<D, DY, LDL, DYM>(m, L, sf, w0, wi, EvalObsTerm<Env>(), my, Syy, Sxy, want_sxy, noise, Nz);
+    } else {
+      transform<D, DY, LDL, DYM>(m, L, sf, w0, wi, EvalObs<Env>(), my, Syy, Sxy, want_sxy, noise, Nz);
+    }
+  }
+
   // Gaussian conditioning of (mu[D], Sig[D][D] full, LD) on the observation whose moments sit in MY / SYY (noise added) /
   // SXY, with target z: W = Lz^-1 Sxy^T, mu += W^T Lz^-1 (z - my), Sig -= W^T W.
   template <int D, int DY, int LD>
-  __device__ __noinline__ bool condition(double* mu, double* Sig, const double* z) {
-    const double* my = sm + GL::O_MY;
-    double* Sz = sm + GL::O_SYY;
-    double* invz = sm + GL::O_INVZ;
-    double* W = sm + GL::O_SXY;
-    const bool ok = chol_cols<DY, DYM, 0>(Sz, invz);
+  __device__ __forceinline__ bool condition(double* mu, double* Sig, const double* z) {
+    // the residual z - my is formed here (z lives in registers), the rest in the shared non-inlined body
+    double* rz = sm + GL::O_RR;
+#pragma unroll
+    for (int a = 0; a < DY; ++a)
+      if ((a % G) == r) rz[a] = z[a] - sm[GL::O_MY + a];
+    return condition_impl<D, DY, LD>(mu, Sig, rz, sm + GL::O_SYY, sm + GL::O_INVZ, sm + GL::O_SXY, r);
+  }
+  template <int D, int DY, int LD>
+  __device__ __noinline__ static bool condition_impl(double* mu, double* Sig, const double* rz, double* Sz, double* invz, double* W,
+                                                     const int r) {
+    __builtin_assume(__isShared(mu));
+    __builtin_assume(__isShared(Sig));
+    __builtin_assume(__isShared(rz));
+    __builtin_assume(__isShared(Sz));
+    __builtin_assume(__isShared(invz));
+    __builtin_assume(__isShared(W));
+    const bool ok = chol_cols_impl<DY, DYM, 0>(Sz, invz, r);  // (its barriers also publish rz)
     // residual solve: every lane (DY^2 / 2 FMAs, no exchange)
     double rr[DY];
 #pragma unroll
-    for (int a = 0; a < DY; ++a) rr[a] = z[a] - my[a];
+    for (int a = 0; a < DY; ++a) rr[a] = rz[a];
     fsub<DY, DYM>(Sz, invz, rr);
     I2C_FOR_ROWS(c, D) {
       double w[DY];
@@ -310,7 +506,7 @@ struct GroupWorker {
 
   // quadratic-cost statistics / alpha trace of the feature moments in MY / SYY (lower), reduced over the group
   template <int DZ_>
-  __device__ __noinline__ void cost_stats(const double* zref, double& mean, double& var) {
+  __device__ __forceinline__ void cost_stats(const double* zref, double& mean, double& var) {
     const double* mz = sm + GL::O_MY;
     const double* Sz = sm + GL::O_SYY;
     double m = 0.0, t2 = 0.0, q4 = 0.0;
@@ -424,7 +620,6 @@ struct GroupWorker {
         for (int u = 0; u < DU; ++u) {
           if (u == i - DX) {
             MU[i] = mu_u[u];
-            double row[DX];
 #pragma unroll
             for (int j = 0; j < DX; ++j) {
               double s = 0.0;
@@ -434,19 +629,10 @@ struct GroupWorker {
               }
               SIG[i * N + j] = s;
               SIG[j * N + i] = s;
-              row[j] = s;
+              L[i * N + j] = s;  // raw: the factorisation below eliminates the rows >= DX
             }
 #pragma unroll
             for (int q = 0; q < DU; ++q) SIG[i * N + DX + q] = Suu[u >= q ? tix(u, q) : tix(q, u)];
-            // row of the factor against the carried block: L[i][j] = (Sig[i][j] - sum_k L[i][k] L0[j][k]) / L0[j][j]
-#pragma unroll
-            for (int j = 0; j < DX; ++j) {
-              double s = row[j];
-#pragma unroll
-              for (int k = 0; k < j; ++k) s = fma(-row[k], L0[j * DX + k], s);
-              row[j] = s * I0[j];
-              L[i * N + j] = row[j];
-            }
 #pragma unroll
             for (int q = 0; q <= u; ++q) L[i * N + DX + q] = Suu[tix(u, q)];
           }
@@ -533,9 +719,7 @@ struct GroupWorker {
     // ---- cost observation update (i2c.py:390-404)
     {
       const double a_cell = wk.cell_alpha(t, flags, alpha);
-      transform<N, DZ, N, DYM>(MU, L, p.sf_n, p.w0_n, p.wi_n,
-                               EvalObs<Env>(), sm + GL::O_MY,
-                               sm + GL::O_SYY, sm + GL::O_SXY, true, a_cell, p.QRinv);
+      obs_moments<N, DZ, N, false>(MU, SIG, L, p.sf_n, p.w0_n, p.wi_n, true, a_cell, p.QRinv);
       if (aux) {
         put_vec<DZ>(af, LY::AF_MUZ, sm + GL::O_MY);
         put_tri<DZ, DYM>(af, LY::AF_SIGZ, sm + GL::O_SYY);
@@ -593,9 +777,7 @@ struct GroupWorker {
     if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf) {
       const double a_cell = wk.cell_alpha(t, flags, alpha);
       gsync();  // the J rows above still read SXY
-      transform<DX, DZT, DX, DYM>(M0, L0, p.sf_x, p.w0_x, p.wi_x,
-                                  EvalObsTerm<Env>(),
-                                  sm + GL::O_MY, sm + GL::O_SYY, sm + GL::O_SXY, true, a_cell, p.Qfinv);
+      obs_moments<DX, DZT, DX, true>(M0, S0, L0, p.sf_x, p.w0_x, p.wi_x, true, a_cell, p.Qfinv);
       double zt[DZT];
       wk.load_zterm(zt);
       if (!condition<DX, DZT, DX>(M0, S0, zt)) wk.fail(I2C_FAIL_CHOL_TERMINAL, it, t);
@@ -714,9 +896,7 @@ struct GroupWorker {
       for (int u = 0; u < DU; ++u) st.ent_u.mul(Su[tix(u, u)]);
     }
     I2C_TICK(9)
-    transform<N, DZ, N, DYM>(MU, L, p.sf_n, p.w0_n, p.wi_n,
-                             EvalObs<Env>(), sm + GL::O_MY,
-                             sm + GL::O_SYY, nullptr, false, 0.0, nullptr);
+    obs_moments<N, DZ, N, false>(MU, SIG, L, p.sf_n, p.w0_n, p.wi_n, false, 0.0, nullptr);
     I2C_TICK(12)
     if (aux) {
       double* ab = wk.rec(p.auxb, t, LY::E_AUXB);
@@ -886,9 +1066,7 @@ struct GroupWorker {
       put_vec<N>(pf, LY::PF_MU, MU);
       put_tri<N, N>(pf, LY::PF_SIG, SIG);
     }
-    transform<N, DZ, N, DYM>(MU, L, p.sf_n, p.w0_n, p.wi_n,
-                             EvalObs<Env>(), sm + GL::O_MY,
-                             sm + GL::O_SYY, nullptr, false, 0.0, nullptr);
+    obs_moments<N, DZ, N, false>(MU, SIG, L, p.sf_n, p.w0_n, p.wi_n, false, 0.0, nullptr);
     if (aux) {
       put_vec<DZ>(pf, LY::PF_MUZ, sm + GL::O_MY);
       put_tri<DZ, DYM>(pf, LY::PF_SIGZ, sm + GL::O_SYY);
