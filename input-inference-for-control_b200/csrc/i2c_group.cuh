@@ -1309,15 +1309,20 @@ static int launch_em_group(const KParams& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-// Policy: the group kernel wins while the per-thread kernels cannot fill the machine (one warp per tile); beyond that
-// the per-thread kernels have the higher throughput (no exchange overhead).  I2C_B200_GROUP=0/1 forces the choice.
+// Policy (measured, profiles/r01h_group_vs_thread.txt): the group kernel wins where the per-thread kernel is issue-bound on
+// one sub-partition per tile AND heavy per problem -- the double cart-pole (n = 7: 5.7 KB of register spills per thread,
+// ~350 instructions per sigma-point evaluation): 1.54x at 512 / 2048 problems, 1.33x at 4096, slower from 8192 on.  For the
+// quadrotor, cart-pole and pendulum the per-thread kernels are 1.5-3x faster at every batch size (cheap dynamics, no
+// spills), so the variant is taken automatically only for n = 7 up to 160 tiles.  I2C_B200_GROUP=0/1 forces the choice,
+// I2C_B200_GROUP_MAX_TILES overrides the threshold.
 template <class Env>
 static int launch_em_group_maybe(const KParams& p, cudaStream_t s) {
   constexpr int N = Lay<Env>::N;
   constexpr int G = N >= 5 ? 8 : 4;
   if (p.linearize || p.gh.degree > 0 || (p.phases & I2C_PH_RICCATI)) return kGroupNotTaken;
   if (p.group_mode == 0) return kGroupNotTaken;
-  if (p.group_mode < 0 && p.ntiles > p.group_max_tiles) return kGroupNotTaken;
+  const int max_tiles = p.group_max_tiles > 0 ? p.group_max_tiles : (N == 7 ? 160 : 0);
+  if (p.group_mode < 0 && p.ntiles > max_tiles) return kGroupNotTaken;
   return launch_em_group<Env, G>(p, s);
 }
 
