@@ -52,8 +52,6 @@ struct KParams {
   int32_t fast_obs;   // cubature rule has zero centre weight and unit weight sum: structured cost-feature moments
   int32_t no_team;    // debugging / A-B: force the one-warp-per-tile kernel
   int32_t stage_meta; // stage the cell targets / flags with the records (latency regime only; set by the launcher)
-  int32_t group_mode;      // -1 auto, 0 never, 1 always: G-lanes-per-problem kernel (i2c_group.cuh)
-  int32_t group_max_tiles; // auto: use it up to this many tiles
   int32_t linearize;  // Linearize inference (linear envs only): exact moments instead of sigma points
   double alpha_tol, temp0, dtemp;
   double sf_n, w0_n, wi_n;  // cubature rule in dim n = dx+du (exp_types.py:36-49)
@@ -68,6 +66,9 @@ struct KParams {
   double mu_xt[MAX_DX];
   double sxt_logdet;                             // log det sig_x_terminal (KL term)
   GhRule gh;                                     // Gauss-Hermite inference (I2C_INF_GAUSS_HERMITE), else degree 0
+  // (new fields go at the END: the offsets of the hot fields above are part of the tuned code generation)
+  int32_t group_mode;      // -1 auto, 0 never, 1 always: G-lanes-per-problem kernel (i2c_group.cuh)
+  int32_t group_max_tiles; // auto: use it up to this many tiles (0 = built-in policy)
 };
 
 // element counts of the records for given dims
