@@ -1,0 +1,128 @@
+"""BASELINE configs 4 and 5 at their per-GPU shard sizes: the job shards along the independent problem axis,
+so one rank's work is exactly this.  A random subset of problems is checked against the oracle on the same inputs; the
+whole batch through size-independent properties (no failed problems, PD posteriors, permutation equivariance)."""
+import numpy as np
+import pytest
+
+from conftest import golden, relerr
+from test_gpu_parity import i2c_b200  # noqa: F401
+from test_gpu_widen import quad_setup
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config4_shard_double_cartpole_covariance_control(i2c_b200):
+    """Double cart-pole cubature i2c + covariance control, 2048 problems x T=500 (= 16384 / 8 GPUs).
+
+    Finding: with these inputs the reference algorithm itself cannot run the in-loop propagate -- the closed-loop
+    propagation of the FIRST posterior loses positive definiteness around cell 160 (LinAlgError in the reference /
+    oracle).  The sweeps without it are fine.  So (a) EM with covariance control, without the in-loop propagate, is checked
+    against the oracle on a subset, and (b) with propagate the CUDA path must report exactly that failure
+    (I2C_FAIL_CHOL_PROPAGATE, same first failing cell) for the problems where the oracle raises."""
+    from oracle import i2c_oracle as O
+
+    capi = i2c_b200.capi
+    B, T, iters = 2048, 500, 2
+    sf = 1e-3
+    Q = sf * np.diag([1.0, 1.0, 100.0, 1.0, 100.0, 10.0, 1.0, 1.0])
+    R = sf * np.diag([0.1])
+    mu_t, sig_t = np.zeros(6), np.diag([0.01, 0.005, 0.005, 0.05, 0.05, 0.05])
+    rng = np.random.default_rng(4321)
+    e = i2c_b200.envs.make("DoubleCartpoleKnown")
+    x0 = e.x0 + 0.05 * rng.normal(size=(B, 6))
+    mu_u = 1e-2 * rng.normal(size=(B, T, 1))
+
+    def make(x0_, mu_u_):
+        G = i2c_b200.BatchedI2c("DoubleCartpoleKnown", x0_.shape[0], T, Q, R, Q, 0.05, 0.99, mu_u_, np.eye(1), mu_t, sig_t,
+                                x0=x0_, max_iters=8)  # sig_x0 = sig_eta = 1e-6 I: env defaults (env_def.py:654-656)
+        G.set_cell_flag(capi.CELL_EXPERT, False)
+        return G
+
+    def make_ref(idx):
+        ref = O.make_graph("DoubleCartpoleKnown", T, Q, R, Q, 0.05, 0.99, mu_u[idx], np.eye(1), mu_t, sig_t, B=len(idx),
+                           x0=x0[idx])
+        for c in ref.cells:
+            c.use_expert_controller = False
+        return ref
+
+    # ---- (a) covariance-control EM without the in-loop propagate
+    G = make(x0, mu_u)
+    G.propagate()  # the initial propagate of nonlinear_covariance_control.py:105-113 works (prior controller)
+    G.learn(iters)
+    assert np.all(G.status()[0] == 0), np.unique(G.status()[0], return_counts=True)
+    idx = rng.choice(B, 6, replace=False)
+    ref = make_ref(idx)
+    for _ in range(iters):
+        ref.learn_msgs()
+    # T = 500 cells of a chaotic system: the noise floor of the reference itself is ~1e-9 after ONE sweep
+    assert relerr(G.field("mu_xu0_m")[idx], ref.stack("mu_xu0_m")) < 1e-6
+    assert relerr(G.field("sig_xu0_m")[idx], ref.stack("sig_xu0_m")) < 1e-5
+    assert relerr(G.alpha[idx], ref.alpha) < 1e-8  # the ratio clip binds (tol 0.99): schedules agree to round-off
+    assert relerr(np.array(G.metrics["cost_m"])[:, idx], np.array(ref.costs_m)) < 1e-6
+    sig = G.field("sig_xu0_m")
+    assert np.all(np.isfinite(sig)) and np.all(np.linalg.eigvalsh(sig.reshape(-1, 7, 7)) > 0)
+    K, k, sk = G.get_local_linear_policy()
+    assert np.all(np.isfinite(K)) and np.all(sk > 0)
+    perm = np.random.default_rng(1).permutation(B)[:256]  # independence of the problems: a re-ordered sub-batch
+    Gp = make(x0[perm], mu_u[perm])
+    Gp.learn(iters)
+    Kp, _, _ = Gp.get_local_linear_policy()
+    assert np.array_equal(Kp, K[perm])
+
+    # ---- (b) with the in-loop propagate: failure parity
+    Gf = make(x0, mu_u)
+    Gf._propagate = True
+    Gf.learn(1)
+    st, info = Gf.status()
+    for b in idx[:3]:
+        r1 = make_ref(np.array([b]))
+        r1._forward_backward_msgs()
+        mu, sg, fail_cell = r1.x0, r1.sig_x0, None
+        for i, c in enumerate(r1.cells):
+            try:
+                mu, sg = c.propagate_quadrature(mu, sg)
+            except np.linalg.LinAlgError:
+                fail_cell = i
+                break
+        if fail_cell is None:
+            assert st[b] == 0
+        else:
+            assert st[b] == capi.STATUS_IDS["CHOL_PROPAGATE"] if hasattr(capi, "STATUS_IDS") else st[b] == 10
+            assert (int(info[b]) & 0xFFFF) == fail_cell, (b, int(info[b]) & 0xFFFF, fail_cell)
+
+
+def test_config5_shard_quadrotor_mpc(i2c_b200):
+    """Quadrotor MPC with cubature Kalman filter, 8192 closed-loop roll-outs (= 65536 / 8 GPUs), a few control steps."""
+    from oracle import envs as E
+    from oracle import i2c_oracle as O
+
+    g = golden("mpc_quadrotor_fb_high")
+    B, n_steps, n_ref = 8192, 4, 6
+    sig_zeta = g["sig_zeta"]
+    G, pol = quad_setup(i2c_b200, g, B, sig_zeta)
+    sys_ = E.Quadrotor(sig_zeta=sig_zeta)
+    R = O.Graph(sys_, int(g["T_plan"]), g["Q"], g["R"], g["Qf"], 1.0, 1.0, g["u_init"], g["sig_u"], None, None,
+                O.Cubature(1, 0, 0), B=n_ref)
+    R._propagate = True
+    rp = O.PartiallyObservedMpc(R, int(g["mpc_iter"]), g["sig_u"], g["z_traj"].copy())
+    rp.set_control(bool(g["feedforward"]))
+    G.calibrate_alpha()
+    pol.optimize(25)
+    G.calibrate_alpha()
+    R.calibrate_alpha()
+    rp.optimize(25, R.x0, R.sig_x0)
+    R.calibrate_alpha()
+    rng = np.random.default_rng(11)
+    x = np.broadcast_to(sys_.x0, (B, 6)).copy()
+    u = np.zeros((B, 2))
+    ur = np.zeros((n_ref, 2))
+    for t in range(n_steps):
+        y = sys_.measure(x) + rng.multivariate_normal(np.zeros(8), sig_zeta, B)
+        u = np.clip(pol(t, y, u), 0.0, 30.0)
+        ur = np.clip(rp(t, y[:n_ref], ur), 0.0, 30.0)
+        assert relerr(u[:n_ref], ur) < 1e-6, t
+        assert np.all(np.isfinite(u))
+        x = sys_.dynamics(np.concatenate((x, u), axis=-1)) + rng.multivariate_normal(np.zeros(6), sys_.sig_eta, B)
+    assert np.all(G.status()[0] == 0)
+    mu, cov = pol.belief
+    assert relerr(mu[:n_ref], rp.mu) < 1e-6 and np.all(np.linalg.eigvalsh(cov) > 0)
