@@ -125,12 +125,13 @@ struct GroupWorker {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     gsync();
   }
-  // Cholesky of the lower triangle of A (leading dimension LD), rows >= J0 (rows < J0 already hold L and invd their
-  // reciprocal pivots), eliminated column by column with the rows below the pivot in parallel.  The pivot is computed
-  // redundantly by every lane (no broadcast); the diagonal of L is written once at the end (one barrier per column).
-  // Same operation order per entry as chol_rows.  (Tried and rejected: every lane factorising the whole matrix in
-  // registers -- the unrolled code of the five factorisations per cell no longer fits the instruction cache and the
-  // kernel became fetch-bound: 6.0k instead of 2.4k cycles for the 7x7 factorisation.)
+  // Cholesky of the lower triangle of A (leading dimension LD) by columns J0 .. NN-1, rows below the pivot in parallel.
+  // Rows < J0 already hold L (invd their reciprocal pivots) and the columns < J0 of the rows >= J0 have been eliminated
+  // by the caller (build_joint does it for the one or two action rows without any barrier).  Two columns are retired per
+  // barrier: every lane forms both pivots and the sub-diagonal entry L[j+1][j] redundantly, then updates its own rows in
+  // both columns.  The diagonal of L is written once at the end.  Same operation order per entry as chol_rows.
+  // (Tried and rejected: every lane factorising the whole matrix in registers -- the unrolled code of the five
+  // factorisations per cell no longer fits the instruction cache: 6.0k instead of 2.4k cycles for the 7x7 factorisation.)
   template <int NN, int LD, int J0>
   __device__ __noinline__ static bool chol_cols_impl(double* A, double* invd, const int r) {
     // (static + explicit arguments: a non-inlined MEMBER function would take `this`, forcing the whole worker object
@@ -138,28 +139,49 @@ struct GroupWorker {
     __builtin_assume(__isShared(A));
     __builtin_assume(__isShared(invd));
     bool ok = true;
-    double mydiag[(NN + G - 1) / G], myinv[(NN + G - 1) / G];
-    // rows J0.. first eliminate the columns < J0 against the finished rows (nothing to do for J0 = 0)
+    double mydiag[(NN + G - 1) / G], myinv[(NN + G - 1) / G], mysub[(NN + G - 1) / G];
 #pragma unroll
-    for (int j = 0; j < NN; ++j) {
-      double d = A[j * LD + j], ri = 0.0;
-      if (j >= J0) {
+    for (int j = J0; j < NN; j += 2) {
+      const bool two = j + 1 < NN;
+      // pivot j, entry (j+1, j), pivot j+1 -- redundantly in every lane
+      double d0 = A[j * LD + j];
 #pragma unroll
-        for (int k = 0; k < j; ++k) d = fma(-A[j * LD + k], A[j * LD + k], d);
-        ok = ok && (d > 0.0) && (d < 1.0e300);
-        ri = fast_rsqrt(d);
-      } else {
-        ri = invd[j];
+      for (int k = 0; k < j; ++k) d0 = fma(-A[j * LD + k], A[j * LD + k], d0);
+      ok = ok && (d0 > 0.0) && (d0 < 1.0e300);
+      const double r0 = fast_rsqrt(d0);
+      double l10 = 0.0, d1 = 1.0, r1 = 1.0;
+      if (two) {
+        l10 = A[(j + 1) * LD + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) l10 = fma(-A[(j + 1) * LD + k], A[j * LD + k], l10);
+        l10 *= r0;
+        d1 = A[(j + 1) * LD + j + 1];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d1 = fma(-A[(j + 1) * LD + k], A[(j + 1) * LD + k], d1);
+        d1 = fma(-l10, l10, d1);
+        ok = ok && (d1 > 0.0) && (d1 < 1.0e300);
+        r1 = fast_rsqrt(d1);
       }
       I2C_FOR_ROWS(i, NN) {
-        if (i > j && i >= J0) {
-          double s = A[i * LD + j];
+        if (i > j + 1 || (!two && i > j)) {
+          double s0 = A[i * LD + j], s1 = two ? A[i * LD + j + 1] : 0.0;
 #pragma unroll
-          for (int k = 0; k < j; ++k) s = fma(-A[i * LD + k], A[j * LD + k], s);
-          A[i * LD + j] = s * ri;
-        } else if (i == j && j >= J0) {
-          mydiag[i_0 / G] = d * ri;
-          myinv[i_0 / G] = ri;
+          for (int k = 0; k < j; ++k) {
+            const double aik = A[i * LD + k];
+            s0 = fma(-aik, A[j * LD + k], s0);
+            if (two) s1 = fma(-aik, A[(j + 1) * LD + k], s1);
+          }
+          s0 *= r0;
+          A[i * LD + j] = s0;
+          if (two) A[i * LD + j + 1] = fma(-s0, l10, s1) * r1;
+        } else if (i == j) {
+          mydiag[i_0 / G] = d0 * r0;
+          myinv[i_0 / G] = r0;
+        } else if (two && i == j + 1) {
+          mysub[i_0 / G] = l10;  // (stored at the end: the other lanes still read the raw entry in this phase, and
+                                 //  nobody reads L[j+1][j] again inside this function)
+          mydiag[i_0 / G] = d1 * r1;
+          myinv[i_0 / G] = r1;
         }
       }
       gsync();
@@ -168,6 +190,7 @@ struct GroupWorker {
       if (i >= J0) {
         A[i * LD + i] = mydiag[i_0 / G];
         invd[i] = myinv[i_0 / G];
+        if ((i - J0) & 1) A[i * LD + i - 1] = mysub[i_0 / G];
       }
     }
     gsync();
@@ -620,6 +643,7 @@ struct GroupWorker {
         for (int u = 0; u < DU; ++u) {
           if (u == i - DX) {
             MU[i] = mu_u[u];
+            double row[DX];
 #pragma unroll
             for (int j = 0; j < DX; ++j) {
               double s = 0.0;
@@ -629,10 +653,19 @@ struct GroupWorker {
               }
               SIG[i * N + j] = s;
               SIG[j * N + i] = s;
-              L[i * N + j] = s;  // raw: the factorisation below eliminates the rows >= DX
+              row[j] = s;
             }
 #pragma unroll
             for (int q = 0; q < DU; ++q) SIG[i * N + DX + q] = Suu[u >= q ? tix(u, q) : tix(q, u)];
+            // columns < DX of this row against the carried factor: L[i][j] = (Sig[i][j] - sum_k L[i][k] L0[j][k]) / L0[j][j]
+#pragma unroll
+            for (int j = 0; j < DX; ++j) {
+              double s = row[j];
+#pragma unroll
+              for (int k = 0; k < j; ++k) s = fma(-row[k], L0[j * DX + k], s);
+              row[j] = s * I0[j];
+              L[i * N + j] = row[j];
+            }
 #pragma unroll
             for (int q = 0; q <= u; ++q) L[i * N + DX + q] = Suu[tix(u, q)];
           }
