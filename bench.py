@@ -140,6 +140,26 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CUDA arm
+def bind_to_gpu_numa_node(dev):
+    """One process per GPU: run (and allocate pinned host buffers, first touch) on the CPUs NVML reports as local to this
+    GPU, so that the H2D / D2H copies of eight ranks do not cross the socket interconnect."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_cuda(args, rank, world, local_rank):
     import torch
     import __graft_entry__ as ge
@@ -159,6 +179,7 @@ def run_cuda(args, rank, world, local_rank):
 
     dev = local_rank
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(dev) if world > 1 else None
     B, T, K, W = args.problems, args.horizon, args.steps, args.warmup
     x0, mu_u = make_inputs(B, T, 1234 + rank)
     g = i2c_b200.BatchedI2c("PendulumKnown", B, T, HYPER["Q"], HYPER["R"], HYPER["Q"], HYPER["alpha"], HYPER["tol"], mu_u,
@@ -280,7 +301,8 @@ def run_cuda(args, rank, world, local_rank):
                 "what": "per step: H2D start-state belief, one learn_msgs, D2H cost+alpha per problem (sync) and K,k,sigK "
                         "(i2c_get_policy_async into double-buffered pinned arrays: the copy overlaps the next step; all "
                         "copies complete inside the timed region)"
-                        + ("; + final NCCL all_gather of controllers" if world > 1 else "")},
+                        + ("; + final NCCL all_gather of controllers" if world > 1 else "")
+                        + (f"; process bound to the {numa} CPUs local to its GPU" if numa else "")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": NCU_DRAM_BYTES_PER_UPDATE * B * T * K if (B == 4096 and T == 200) else None,
