@@ -432,6 +432,74 @@ class I2cGraph(object):
     def propagate_cost_improved(self):
         return self.costs_pf[-1] <= self.costs_pf[-2] if len(self.costs_pf) > 1 else True
 
+    # ---- likelihood diagnostics (i2c.py:690-718, 1135-1170; never called by the reference's scripts) -------------
+    def _calc_likelihood(self):
+        """Expected complete-data log-likelihood terms of the current messages.  The per-cell dynamics moments
+        (cell._calc_likelihood_quadrature, i2c.py:690-705) are one batched sigma-point launch over the cells; the
+        remaining small traces are formed on the host from the device fields.  Quirks kept: the normalising terms use
+        det(.) (not log det), the smoothed marginals are joined block-diagonally (concat_normals)."""
+        s, H = self.sys, self.H
+        dx = s.dim_x
+        m, S = self._field("mu_xu0_m"), self._field("sig_xu0_m")
+        Sbd = np.zeros_like(S)
+        Sbd[:, :dx, :dx], Sbd[:, dx:, dx:] = S[:, :dx, :dx], S[:, dx:, dx:]
+        kind = self._ctor["kind"]
+        if kind == "linearize":
+            if not hasattr(s, "A"):
+                raise NotImplementedError("likelihood of the Linearize path needs the per-cell linearisation (linear envs only)")
+            A, B, a = np.asarray(s.A, float), np.asarray(s.B, float), np.asarray(s.a, float).reshape(-1)
+            mu_x = m[:, :dx] @ A.T + m[:, dx:] @ B.T + a
+            sig_x = A @ S[:, :dx, :dx] @ A.T + B @ S[:, dx:, dx:] @ B.T
+        else:
+            kw = dict(gh_degree=int(self._ctor["quad"][0])) if kind == "gauss_hermite" else dict(quad=self._ctor["quad"])
+            mu_x, sig_x, _, st = i2c_b200.quadrature(s._b200_env, "forward", m, Sbd, env_par=s._b200_env_par(),
+                                                     device=getattr(s, "device", 0), **kw)
+            if np.any(st != 0):
+                raise np.linalg.LinAlgError("Matrix is not positive definite")
+        sig_eta = np.asarray(s.sig_eta, float)
+        Jx = self._field("J_dyn")[:, :dx, :]
+        mu3, S3 = self._field("mu_x3_m"), self._field("sig_x3_m")
+        lag = Jx @ S3
+        M11 = np.einsum("ti,tj->tij", mu3, mu3) + S3
+        M01 = np.einsum("ti,tj->tij", mu_x, mu3) + lag
+        M00 = np.einsum("ti,tj->tij", mu_x, mu_x) + sig_x
+        ll_xu = -0.5 * np.trace(np.sum(np.linalg.solve(sig_eta, M00 - M01 - np.transpose(M01, (0, 2, 1)) + M11), axis=0))
+        lam_xi = np.linalg.inv(self.sig_xi)
+        ll_z = -0.5 * np.trace(lam_xi @ self.get_z_covar())
+        ll_const = -0.5 * H * (dx + s.dim_z) * np.log(2 * np.pi)
+        ll_sig_xi = -0.5 * H * np.linalg.det(self.sig_xi)
+        ll_sig_eta = -0.5 * H * np.linalg.det(sig_eta)
+        sig_x0 = np.asarray(s.sig_x0, float)
+        ll_sig_x0 = -0.5 * np.linalg.det(sig_x0)
+        d0 = m[0, :dx] - np.asarray(s.x0, float).reshape(-1)
+        ll_mu_x0 = -0.5 * np.trace(np.linalg.solve(sig_x0, np.outer(d0, d0) + S[0, :dx, :dx]))
+        ll_state_action, ll_cost = ll_sig_eta + ll_xu, ll_sig_xi + ll_z
+        return ll_const + ll_cost + ll_state_action + ll_sig_x0 + ll_mu_x0, ll_state_action, ll_cost, ll_xu
+
+    def calc_likelihood(self):
+        ll, _, ll_z, ll_xu = self._calc_likelihood()  # (the reference's tuple unpacking keeps the last ll_xu, i2c.py:1160)
+        self.likelihoods.append(ll)
+        self.likelihoods_xu.append(ll_xu)
+        self.likelihoods_z.append(ll_z)
+        self.risk.append(-2 * ll_xu / self.alpha)
+
+    @staticmethod
+    def list_minima(values, n_min, n_steps):
+        """i2c.py:1172-1181: once more than n_min values exist, True iff the last n_steps steps all went down
+        (None before that, as in the reference)."""
+        if len(values) <= n_min:
+            return None
+        if not (len(values) > n_steps > 0):
+            return False
+        tail = np.asarray(values[-(n_steps + 1):], float)
+        return bool(np.all(np.diff(tail) < 0))
+
+    def likelihood_z_minima(self, n_min, n_steps):
+        return self.list_minima(self.likelihoods_z, n_min, n_steps)
+
+    def likelihood_xu_minima(self, n_min, n_steps):
+        return self.list_minima(self.likelihoods_xu, n_min, n_steps)
+
     def get_prior_state_action_distribution(self):
         return self._g.field("mu_xu0_f")[0].copy(), self._g.field("sig_xu0_f")[0].copy()
 
@@ -503,7 +571,7 @@ class I2cGraph(object):
             self.costs_pf_all.extend(self.costs_pf)
         for name in ("costs_m", "costs_m_var", "costs_pf", "costs_pf_var", "cost_pf_min", "policy_entropy",
                      "sig_eta_entropy", "sig_eta_pf_entropy", "x_prior_entropy", "x_prior_neg_entropy",
-                     "propagate_entropy", "kl_terms", "costs_p", "likelihoods"):
+                     "propagate_entropy", "kl_terms", "costs_p", "likelihoods", "likelihoods_xu", "likelihoods_z", "risk"):
             setattr(self, name, [])
         self.em_iter = 0
 

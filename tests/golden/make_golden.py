@@ -400,8 +400,30 @@ def evaluators():
     save("evaluator_kat", d)
 
 
+def likelihood():
+    """Likelihood diagnostics (I2cGraph.calc_likelihood, i2c.py:1135-1164): never called by the reference's scripts,
+    pinned here by calling it after every EM iteration."""
+    exp = ref_shim.load_experiment("pendulum_known_quad", 0)
+    I = exp.INFERENCE
+    rng = np.random.default_rng(3)
+    T = 30
+    mu_u = 1e-2 * rng.normal(size=(T, 1))
+    sys_ = ns.model.make_env_model("PendulumKnown", None)
+    g = I2cGraph(sys_, T, I.Q, I.R, I.Qf, 100.0, 0.5, mu_u, I.sig_u, None, None, Cub(1, 0, 0))
+    for _ in range(4):
+        g.learn_msgs()
+        g.calc_likelihood()
+    d = dict(T=T, Q=I.Q, R=I.R, Qf=I.Qf, alpha0=100.0, tol=0.5, mu_u=mu_u, sig_u=I.sig_u,
+             likelihoods=np.asarray(g.likelihoods, float), likelihoods_xu=np.asarray(g.likelihoods_xu, float),
+             likelihoods_z=np.asarray(g.likelihoods_z, float), risk=np.asarray(g.risk, float).reshape(-1))
+    vals = [3.0, 2.5, 2.0, 2.2, 1.9, 1.8, 1.7]
+    d["minima"] = np.array([[float(x) if x is not None else -1.0 for x in
+                             (I2cGraph.list_minima(vals[:n], 2, 2), I2cGraph.list_minima(vals[:n], 2, 3))] for n in range(1, 8)])
+    save("likelihood_kat", d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc", "gh", "eval"]
+    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc", "gh", "eval", "ll"]
     if "quad" in which:
         quad_kat()
     if "em" in which:
@@ -414,3 +436,5 @@ if __name__ == "__main__":
         gauss_hermite()
     if "eval" in which:
         evaluators()
+    if "ll" in which:
+        likelihood()

@@ -254,3 +254,21 @@ def test_alpha_helpers_match_device_update(mirror):
     graph.plot_traj(0, dir_name=None, filename="lqr")  # scripts/lqr_compare.py:172
     with pytest.raises(AttributeError):
         graph.no_such_attribute
+
+
+def test_likelihood_diagnostics(mirror):
+    """I2cGraph.calc_likelihood (i2c.py:1135-1164) after every EM iteration, against the reference (likelihood_kat.npz);
+    the values are sums of ~1e5-sized terms, hence the relative tolerance."""
+    g = golden("likelihood_kat")
+    model = mirror.make_env_model("PendulumKnown", None)
+    graph = mirror.I2cGraph(model, int(g["T"]), g["Q"], g["R"], g["Qf"], float(g["alpha0"]), float(g["tol"]), g["mu_u"],
+                            g["sig_u"], None, None, mirror.CubatureQuadrature(1, 0, 0))
+    for _ in range(4):
+        graph.learn_msgs()
+        graph.calc_likelihood()
+    for name in ("likelihoods", "likelihoods_xu", "likelihoods_z", "risk"):
+        assert relerr(np.asarray(getattr(graph, name), float).reshape(-1), g[name]) < 1e-7, name
+    vals = [3.0, 2.5, 2.0, 2.2, 1.9, 1.8, 1.7]
+    mine = np.array([[float(x) if x is not None else -1.0 for x in
+                      (graph.list_minima(vals[:n], 2, 2), graph.list_minima(vals[:n], 2, 3))] for n in range(1, 8)])
+    assert np.array_equal(mine, g["minima"])
