@@ -119,3 +119,32 @@ def test_scan_long_horizon_speedup(i2c_b200):
     assert relerr(Gp.field("K"), Gs.field("K")) < 1e-9
     print("ms per sweep pair:", ms)
     assert ms["scan"] < 0.5 * ms["seq"], ms
+
+
+def test_scan_minimum_energy_covariance_control(i2c_b200):
+    """LinearKnownMinimumEnergy (cost on u only: the state is never observed, J = 0 in every element) with covariance
+    control at the end of the chain (linear_gaussian_covariance_control.py flow, no in-loop propagate) through both kernels."""
+    capi = i2c_b200.capi
+    g = golden("linear_covctrl_linearize")
+    # (T = 60: this system is unstable and its state is never observed, so the filtered covariance grows like 1.1^(2T);
+    #  at T = 200 it reaches 5e9 and BOTH kernels lose seven digits in the smoother differences -- they then agree to 1e-7)
+    T = 60
+    rng = np.random.default_rng(2)
+    mu_u = 1e-2 * rng.normal(size=(T, 1))
+
+    def make():
+        G = i2c_b200.BatchedI2c("LinearKnownMinimumEnergy", 17, T, None, g["R"], None, float(g["alpha0"]), float(g["tol"]), mu_u,
+                                g["sig_u"], g["mu_x_term"], g["sig_x_term"], inference="linearize", enable_aux=True)
+        G.set_cell_flag(capi.CELL_EXPERT, False)
+        return G
+
+    Gs, Gp = make(), make()
+    Gp.time_parallel_chunk = 16
+    for it in range(3):
+        Gs.learn(1)
+        Gp.learn(1)
+        assert np.all(Gp.status()[0] == 0), Gp.status()
+        for f in FIELDS:
+            assert relerr(Gp.field(f), Gs.field(f), floor=1e-9) < 1e-10, (it, f, relerr(Gp.field(f), Gs.field(f), floor=1e-9))
+        assert relerr(Gp.alpha, Gs.alpha) < 1e-10
+    assert Gp.temp == Gs.temp
