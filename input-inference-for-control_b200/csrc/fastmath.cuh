@@ -7,13 +7,35 @@
 
 namespace i2c {
 
+// Polynomial / reduction constants live in the constant bank: fp64 instructions take a c[bank][offset] operand directly,
+// whereas a literal costs two UMOVs (low / high word into a uniform register) at EVERY use -- 164 UMOVs = 12 % of the
+// instructions of a pendulum forward cell (profiles/r01d source view).  Same values, same operation order: bit-identical.
+static __constant__ double kFm[20] = {
+    6.36619772367581382433e-01,   // 0  2/pi
+    1.57079632673412561417e+00,   // 1  P1: first 33 bits of pi/2
+    6.07710050650619224932e-11,   // 2  P2
+    2.02226624879595063154e-21,   // 3  P3
+    -1.66666666666666324348e-01,  // 4  S1
+    8.33333333332248946124e-03,   // 5  S2
+    -1.98412698298579493134e-04,  // 6  S3
+    2.75573137070700676789e-06,   // 7  S4
+    -2.50507602534068634195e-08,  // 8  S5
+    1.58969099521155010221e-10,   // 9  S6
+    4.16666666666666019037e-02,   // 10 C1
+    -1.38888888888741095749e-03,  // 11 C2
+    2.48015872894767294178e-05,   // 12 C3
+    -2.75573143513906633035e-07,  // 13 C4
+    2.08757232129817482790e-09,   // 14 C5
+    -1.13596475577881948265e-11,  // 15 C6
+    0.375, 0.5, 1.0, -0.5};       // 16..19
+
 // 1/sqrt(d) for normal positive d: MUFU.RSQ64H seed (~2^-22) + one third-order step (error ~ e^3 < 2^-66) => <= 1-2 ulp.
 __device__ __forceinline__ double fast_rsqrt(double d) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   const double h = d * y;
-  const double e = fma(-h, y, 1.0);
-  const double p = fma(0.375, e, 0.5);
+  const double e = fma(-h, y, kFm[18]);
+  const double p = fma(kFm[16], e, kFm[17]);
   return fma(y * e, p, y);
 }
 
@@ -21,9 +43,9 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 __device__ __forceinline__ double fast_rcp(double d) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-d, y, 1.0);
+  double e = fma(-d, y, kFm[18]);
   y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
+  e = fma(-d, y, kFm[18]);
   return fma(y, e, y);
 }
 
@@ -35,10 +57,7 @@ __device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
     sincos(x, sp, cp);
     return;
   }
-  const double TWO_OVER_PI = 6.36619772367581382433e-01;
-  const double P1 = 1.57079632673412561417e+00;  // first 33 bits of pi/2
-  const double P2 = 6.07710050650619224932e-11;  // pi/2 - P1, first 33 bits
-  const double P3 = 2.02226624879595063154e-21;  // pi/2 - (P1 + P2)
+  const double TWO_OVER_PI = kFm[0], P1 = kFm[1], P2 = kFm[2], P3 = kFm[3];
   const double kd = rint(x * TWO_OVER_PI);
   const int k = (int)kd;
   double r = fma(-kd, P1, x);
@@ -46,10 +65,8 @@ __device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
   r = fma(-kd, P3, r);
   const double z = r * r;
   // sin(r) = r + r z (S1 + z S2 + z^2 S3 + ...)
-  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
-               S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
-  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
-               C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  const double S1 = kFm[4], S2 = kFm[5], S3 = kFm[6], S4 = kFm[7], S5 = kFm[8], S6 = kFm[9];
+  const double C1 = kFm[10], C2 = kFm[11], C3 = kFm[12], C4 = kFm[13], C5 = kFm[14], C6 = kFm[15];
   const double z2 = z * z;
   // Estrin-style pairing: (S1 + z S2) + z2 ((S3 + z S4) + z2 (S5 + z S6))
   const double s01 = fma(z, S2, S1), s23 = fma(z, S4, S3), s45 = fma(z, S6, S5);
@@ -57,7 +74,7 @@ __device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
   const double c01 = fma(z, C2, C1), c23 = fma(z, C4, C3), c45 = fma(z, C6, C5);
   const double pc = fma(z2, fma(z2, c45, c23), c01);
   const double sr = fma(r * z, ps, r);
-  const double cr = fma(z, fma(z, pc, -0.5), 1.0);
+  const double cr = fma(z, fma(z, pc, kFm[19]), kFm[18]);
   // quadrant: k mod 4 = 0: (s,c) 1: (c,-s) 2: (-s,-c) 3: (-c, s)
   const bool swap = k & 1;
   double s = swap ? cr : sr;
