@@ -61,6 +61,30 @@ struct EnvLinearMinEnergy : EnvLinear {
   __device__ static void obs(const double* xu, int, const TrigT&, double* z) { z[0] = xu[2]; }
 };
 
+// Literals of the hot dynamics live in the constant bank (fp64 instructions take c[bank][offset] operands directly; a
+// literal costs two UMOVs at every use).  The initialisers are the same constant expressions the code used, folded by the
+// same compiler in the same order => bit-identical results.
+static __constant__ double kPendulum[6] = {0.05, 1e-2, -3.0 * 9.80665 / 2.0, 3.0, -2.0, 2.0};
+static __constant__ double kDcp[15] = {
+    1.0 / 125.0,
+    0.127 * (0.3365 / 2) + 0.127 * 0.3365,                                   // a12 = Mp1 l1 + Mp2 L2
+    0.127 * (0.3365 / 2),                                                    // a13 = Mp2 l2
+    0.3365 * (0.3365 / 2) * 0.127,                                           // a23 = L1 l2 Mp2
+    (0.3365 / 2) * (0.3365 / 2) * 0.127 + 0.3365 * 0.3365 * 0.127 + 0.127 * 0.3365 / 12,  // M22
+    (0.3365 / 2) * (0.3365 / 2) * 0.127 + 0.127 * 0.3365 / 12,               // M33
+    -(0.127 * (0.3365 / 2) + 0.127 * 0.3365),
+    -(0.127 * (0.3365 / 2)),
+    -(0.3365 * (0.3365 / 2) * 0.127),
+    -(0.127 * (0.3365 / 2) + 0.127 * 0.3365) * 9.81,                         // -(Mp1 l1 + Mp2 L1) g
+    -0.127 * (0.3365 / 2) * 9.81,                                            // -Mp2 l2 g
+    3.0, -10.0, 10.0, 1.2659242088545832};
+static __constant__ double kQuad[8] = {0.1, 1.0 / (5.0 * (2 * 0.8) * (2 * (400.0 / 30.0 / 100.0))), -9.81, 0.8,
+                                       1.0 / ((5.0 * (2 * 0.8) * (2 * (400.0 / 30.0 / 100.0))) *
+                                              ((2 * 0.8) * (2 * 0.8) + (2 * (400.0 / 30.0 / 100.0)) * (2 * (400.0 / 30.0 / 100.0))) / 12.0),
+                                       1.0 / (1.0 + 0.1 * 0.5), 0.0, 30.0};
+static __constant__ double kCartpole[10] = {-0.127 * 0.3365, (0.37 + 0.127) * 9.81, 0.3365, (4.0 / 3.0) * (0.37 + 0.127), 0.127,
+                                            0.127 * 0.3365, 1.0 / (0.37 + 0.127), 1.0 / 250.0, -5.0, 5.0};
+
 // ------------------------------------------------------------------ pendulum
 // env_autograd.py:5-19 (dynamics), env_def.py:273-291 (features [sin th, cos th, thd, u]).
 struct EnvPendulum {
@@ -90,14 +114,14 @@ struct EnvPendulum {
   __host__ __device__ static constexpr int term_src(int a) { return a < 2 ? -1 - a : a - 1; }
   __device__ static void trig_nl(const double* x, int j, const TrigT& c, double* y) { trig(x, j, c, y[0], y[1]); }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
-    const double dt = 0.05, d = 1e-2, g = 9.80665;
+    const double dt = kPendulum[0], d = kPendulum[1];
     double s, co;
     trig(xu, j, c, s, co);
     (void)co;
-    double u = fmin(fmax(xu[2], -2.0), 2.0);
+    double u = fmin(fmax(xu[2], kPendulum[4]), kPendulum[5]);
     // the reference evaluates np.sin(th + np.pi); sin(th + pi) == -sin(th) up to the rounding of th + pi
-    double acc = -3.0 * g / 2.0 * (-s) - d * xu[1];
-    acc += 3.0 * u;
+    double acc = kPendulum[2] * (-s) - d * xu[1];  // kPendulum[2] = -3 g / 2
+    acc += kPendulum[3] * u;
     double xd = fma(acc, dt, xu[1]);
     y[0] = fma(xd, dt, xu[0]);
     y[1] = xd;
@@ -159,15 +183,16 @@ struct EnvCartpole {
   __host__ __device__ static constexpr int term_src(int a) { return a == 0 ? 0 : (a <= 2 ? -a : a - 1); }
   __device__ static void trig_nl(const double* x, int j, const TrigT& c, double* y) { trig(x, j, c, y[0], y[1]); }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
-    const double g = 9.81, Mc = 0.37, Mp = 0.127, Mt = Mc + Mp, l = 0.3365, dt = 1.0 / 250.0;
-    double u = fmin(fmax(xu[4], -5.0), 5.0);
+    // kCartpole = {-Mp l, Mt g, l, 4/3 Mt, Mp, Mp l, 1/Mt, dt, -5, 5}
+    const double dt = kCartpole[7];
+    double u = fmin(fmax(xu[4], kCartpole[8]), kCartpole[9]);
     double sth, cth;
     trig(xu, j, c, sth, cth);
     double dth2 = xu[3] * xu[3];
-    double num = -Mp * l * sth * cth * dth2 + Mt * g * sth - u * cth;
-    double den = l * ((4.0 / 3.0) * Mt - Mp * cth * cth);
+    double num = kCartpole[0] * sth * cth * dth2 + kCartpole[1] * sth - u * cth;
+    double den = kCartpole[2] * (kCartpole[3] - kCartpole[4] * cth * cth);
     double th_acc = num * fast_rcp(den);
-    double x_acc = (Mp * l * sth * dth2 - Mp * l * th_acc * cth + u) * (1.0 / Mt);
+    double x_acc = (kCartpole[5] * sth * dth2 - kCartpole[5] * th_acc * cth + u) * kCartpole[6];
     y[0] = fma(dt, xu[2], xu[0]);
     y[1] = fma(dt, xu[3], xu[1]);
     y[2] = fma(dt, x_acc, xu[2]);
@@ -248,25 +273,22 @@ struct EnvDoubleCartpole {
     trig2(x, j, c, y[2], y[3]);
   }
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
-    const double dt = 1.0 / 125.0, g = 9.81, Mc = 0.37, Mp1 = 0.127, Mp2 = 0.127, Mt = Mc + Mp1 + Mp2;
-    const double L1 = 0.3365, L2 = 0.3365, l1 = L1 / 2, l2 = L2 / 2, J1 = Mp1 * L1 / 12, J2 = Mp2 * L2 / 12;
-    const double a12 = Mp1 * l1 + Mp2 * L2, a13 = Mp2 * l2, a23 = L1 * l2 * Mp2;
-    const double M11 = Mt, M22 = l1 * l1 * Mp1 + L1 * L1 * Mp2 + J1, M33 = l2 * l2 * Mp2 + J2;
+    // kDcp = {dt, a12, a13, a23, M22, M33, -a12, -a13, -a23, -(Mp1 l1 + Mp2 L1) g, -Mp2 l2 g, 3, -10, 10, 1/sqrt(Mt)}
+    const double dt = kDcp[0], a12 = kDcp[1], a13 = kDcp[2], a23 = kDcp[3], M22 = kDcp[4], M33 = kDcp[5];
     double s1, c1, s2, c2, sd, cd;
     trig1(xu, j, c, s1, c1);
     trig2(xu, j, c, s2, c2);
     fast_sincos(xu[1] - xu[2], &sd, &cd);
     double M12 = a12 * c1, M13 = a13 * c2, M23 = a23 * cd;
-    double qd = xu[3], td1 = xu[4], td2 = xu[5];
-    double C12 = -a12 * td1 * s1, C13 = -a13 * td2 * s2, C23 = a23 * td2 * sd, C32 = -a23 * td1 * sd;
-    double G2 = -(Mp1 * l1 + Mp2 * L1) * g * s1, G3 = -Mp2 * l2 * g * s2;
-    double u = 3.0 * fmin(fmax(xu[6], -10.0), 10.0);
-    (void)qd;
+    double td1 = xu[4], td2 = xu[5];
+    double C12 = kDcp[6] * td1 * s1, C13 = kDcp[7] * td2 * s2, C23 = a23 * td2 * sd, C32 = kDcp[8] * td1 * sd;
+    double G2 = kDcp[9] * s1, G3 = kDcp[10] * s2;
+    double u = kDcp[11] * fmin(fmax(xu[6], kDcp[12]), kDcp[13]);
     double r1 = u - (C12 * td1 + C13 * td2);
     double r2 = -(C23 * td2) - G2;
     double r3 = -(C32 * td1) - G3;
     // solve the SPD 3x3 system M qdd = r by Cholesky (the reference forms inv(M) @ r)
-    const double i11 = 1.2659242088545832;  // 1/sqrt(Mt), Mt = 0.624
+    const double i11 = kDcp[14];  // 1/sqrt(Mt), Mt = 0.624
     double l21 = M12 * i11, l31 = M13 * i11;
     double i22 = fast_rsqrt(M22 - l21 * l21);
     double l32 = (M23 - l31 * l21) * i22;
@@ -336,15 +358,16 @@ struct EnvQuadrotor {
   __host__ __device__ static constexpr int term_src(int a) { return a; }
   __device__ static void trig_nl(const double*, int, const TrigT&, double*) {}
   __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
-    const double h = 0.1;
-    double u1 = fmin(fmax(xu[6], 0.0), 30.0), u2 = fmin(fmax(xu[7], 0.0), 30.0);
+    // kQuad = {h, 1/MASS, -g, VDX, 1/INERTIA, 1/(1 + h/2), 0, 30}
+    const double h = kQuad[0];
+    double u1 = fmin(fmax(xu[6], kQuad[6]), kQuad[7]), u2 = fmin(fmax(xu[7], kQuad[6]), kQuad[7]);
     double s, co;
     trig(xu, j, c, s, co);
     double f = u1 + u2;
-    double vx = xu[3] + h * ((-s * f) * (1.0 / MASS));
-    double vy = xu[4] + h * (-9.81 + (co * f) * (1.0 / MASS));
-    double w = xu[5] + h * (VDX * (u2 - u1)) * (1.0 / INERTIA);
-    w = w * (1.0 / (1.0 + h * 0.5));
+    double vx = xu[3] + h * ((-s * f) * kQuad[1]);
+    double vy = xu[4] + h * (kQuad[2] + (co * f) * kQuad[1]);
+    double w = xu[5] + h * (kQuad[3] * (u2 - u1)) * kQuad[4];
+    w = w * kQuad[5];
     y[0] = xu[0] + h * vx;
     y[1] = xu[1] + h * vy;
     y[2] = xu[2] + h * w;

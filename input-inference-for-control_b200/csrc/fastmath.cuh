@@ -10,7 +10,7 @@ namespace i2c {
 // Polynomial / reduction constants live in the constant bank: fp64 instructions take a c[bank][offset] operand directly,
 // whereas a literal costs two UMOVs (low / high word into a uniform register) at EVERY use -- 164 UMOVs = 12 % of the
 // instructions of a pendulum forward cell (profiles/r01d source view).  Same values, same operation order: bit-identical.
-static __constant__ double kFm[20] = {
+static __constant__ double kFm[23] = {
     6.36619772367581382433e-01,   // 0  2/pi
     1.57079632673412561417e+00,   // 1  P1: first 33 bits of pi/2
     6.07710050650619224932e-11,   // 2  P2
@@ -27,7 +27,8 @@ static __constant__ double kFm[20] = {
     -2.75573143513906633035e-07,  // 13 C4
     2.08757232129817482790e-09,   // 14 C5
     -1.13596475577881948265e-11,  // 15 C6
-    0.375, 0.5, 1.0, -0.5};       // 16..19
+    0.375, 0.5, 1.0, -0.5,        // 16..19
+    1.0e300, 1.0e-150, 1.0e150};  // 20..22 range guards (Cholesky pivots, log-det accumulator)
 
 // 1/sqrt(d) for normal positive d: MUFU.RSQ64H seed (~2^-22) + one third-order step (error ~ e^3 < 2^-66) => <= 1-2 ulp.
 __device__ __forceinline__ double fast_rsqrt(double d) {

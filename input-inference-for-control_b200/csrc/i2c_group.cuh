@@ -147,7 +147,7 @@ struct GroupWorker {
       double d0 = A[j * LD + j];
 #pragma unroll
       for (int k = 0; k < j; ++k) d0 = fma(-A[j * LD + k], A[j * LD + k], d0);
-      ok = ok && (d0 > 0.0) && (d0 < 1.0e300);
+      ok = ok && (d0 > 0.0) && (d0 < kFm[20]);
       const double r0 = fast_rsqrt(d0);
       double l10 = 0.0, d1 = 1.0, r1 = 1.0;
       if (two) {
@@ -159,7 +159,7 @@ struct GroupWorker {
 #pragma unroll
         for (int k = 0; k < j; ++k) d1 = fma(-A[(j + 1) * LD + k], A[(j + 1) * LD + k], d1);
         d1 = fma(-l10, l10, d1);
-        ok = ok && (d1 > 0.0) && (d1 < 1.0e300);
+        ok = ok && (d1 > 0.0) && (d1 < kFm[20]);
         r1 = fast_rsqrt(d1);
       }
       I2C_FOR_ROWS(i, NN) {

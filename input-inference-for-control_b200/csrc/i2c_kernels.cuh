@@ -631,7 +631,7 @@ struct Worker {
       const double det = fma(c00, c11, -c10 * c10);
       const double q = fma(c11 * d_in[0], d_in[0], fma(-2.0 * c10 * d_in[0], d_in[1], c00 * d_in[1] * d_in[1])) * fast_rcp(det);
       rho = exp(-0.5 * q);
-      return (c00 > 0.0) && (det > 0.0) && (det < 1.0e300);
+      return (c00 > 0.0) && (det > 0.0) && (det < kFm[20]);
     } else {
       double C[TRI(DX)], invd[DX], d[DX];
 #pragma unroll

@@ -30,7 +30,7 @@ __device__ __forceinline__ bool chol_rows(double* A, double* invd) {
     double d = A[tix(i, i)];
 #pragma unroll
     for (int k = 0; k < i; ++k) d = fma(-A[tix(i, k)], A[tix(i, k)], d);
-    ok = ok && (d > 0.0) && (d < 1.0e300);
+    ok = ok && (d > 0.0) && (d < kFm[20]);
     double r = fast_rsqrt(d);
     invd[i] = r;
     A[tix(i, i)] = d * r;
@@ -129,7 +129,7 @@ struct LogAcc {
   __device__ __forceinline__ void mul(double x) {
     m *= x;
     // renormalise only when the running product leaves a safe range (pivots are ~1e-6 .. 1e3: rarely taken)
-    if (!(m > 1.0e-150 && m < 1.0e150)) {
+    if (!(m > kFm[21] && m < kFm[22])) {
       int ex;
       m = frexp(m, &ex);
       e += ex;
