@@ -29,8 +29,8 @@ UNIT = "updates/s"
 # SURVEY.md section 8(d), pendulum row: algorithmic work per problem-timestep update
 F_ALG, B_ALG = 3192.0, 704.0
 # measured DRAM bytes per update of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture / updates in that launch): profiles/r01d_ncu_full_em_team_kernel_pendulum_4096.txt
-NCU_DRAM_BYTES_PER_UPDATE = (567.175936e6 + 621.642752e6) / (3 * 4096 * 200)
+# `ncu --set full` capture / updates in that launch): profiles/r01i_ncu_full_em_team_kernel_pendulum_4096.txt
+NCU_DRAM_BYTES_PER_UPDATE = (558.359552e6 + 623.112704e6) / (3 * 4096 * 200)
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
 
 
@@ -306,7 +306,7 @@ def run_cuda(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": NCU_DRAM_BYTES_PER_UPDATE * B * T * K if (B == 4096 and T == 200) else None,
-                     "traffic_source": "ncu dram bytes/update (profiles/r01d_ncu_full_em_team_kernel_pendulum_4096.txt) x updates "
+                     "traffic_source": "ncu dram bytes/update (profiles/r01i_ncu_full_em_team_kernel_pendulum_4096.txt) x updates "
                                        "per launch; algorithmic bytes per launch = %.4g" % (B_ALG * B * T * K),
                      "peak_source": peak_src,
                      "kernel": "em_team_kernel<EnvPendulum,8>" if B <= 148 * 32 else "em_kernel<EnvPendulum>",
