@@ -10,7 +10,7 @@ namespace i2c {
 // Polynomial / reduction constants live in the constant bank: fp64 instructions take a c[bank][offset] operand directly,
 // whereas a literal costs two UMOVs (low / high word into a uniform register) at EVERY use -- 164 UMOVs = 12 % of the
 // instructions of a pendulum forward cell (profiles/r01d source view).  Same values, same operation order: bit-identical.
-static __constant__ double kFm[23] = {
+static __constant__ double kFm[40] = {
     6.36619772367581382433e-01,   // 0  2/pi
     1.57079632673412561417e+00,   // 1  P1: first 33 bits of pi/2
     6.07710050650619224932e-11,   // 2  P2
@@ -28,7 +28,24 @@ static __constant__ double kFm[23] = {
     2.08757232129817482790e-09,   // 14 C5
     -1.13596475577881948265e-11,  // 15 C6
     0.375, 0.5, 1.0, -0.5,        // 16..19
-    1.0e300, 1.0e-150, 1.0e150};  // 20..22 range guards (Cholesky pivots, log-det accumulator)
+    1.0e300, 1.0e-150, 1.0e150,   // 20..22 range guards (Cholesky pivots, log-det accumulator)
+    1.4426950408889634e+00,       // 23 log2(e)
+    6.93147180369123816490e-01,   // 24 ln2 high part (fdlibm split)
+    1.90821492927058770002e-10,   // 25 ln2 low part
+    6755399441055744.0,           // 26 2^52 + 2^51: round-to-nearest-integer magic number
+    -708.0,                       // 27 clamp: exp(-708) = 3e-308 is still normal
+    5.00000000000000000e-01,
+    1.66666666666666657e-01,
+    4.16666666666666644e-02,
+    8.33333333333333322e-03,
+    1.38888888888888894e-03,
+    1.98412698412698413e-04,
+    2.48015873015873016e-05,
+    2.75573192239858925e-06,
+    2.75573192239858883e-07,
+    2.50521083854417202e-08,
+    2.08767569878681002e-09,
+    1.60590438368216133e-10};  // 28..39: 1/2! .. 1/13!
 
 // 1/sqrt(d) for normal positive d: MUFU.RSQ64H seed (~2^-22) + one third-order step (error ~ e^3 < 2^-66) => <= 1-2 ulp.
 __device__ __forceinline__ double fast_rsqrt(double d) {
@@ -48,6 +65,25 @@ __device__ __forceinline__ double fast_rcp(double d) {
   y = fma(y, e, y);
   e = fma(-d, y, kFm[18]);
   return fma(y, e, y);
+}
+
+// exp(x) for x <= 0 (the pdf ratio exp(-q/2) of the feedback prior): round-to-nearest reduction x = k ln2 + r, |r| <= 0.347,
+// degree-13 Taylor polynomial (truncation 4e-18) and
+// the scaling by 2^k added straight into the exponent field.  Branch-free; arguments below -708 are clamped (3e-308, i.e. 0
+// for every use here; the library routine spent 58 % of its calls in a divergent underflow path).  <= 2 ulp.
+__device__ __forceinline__ double fast_exp_neg(double x) {
+  x = fmax(x, kFm[27]);
+  const double km = fma(x, kFm[23], kFm[26]);   // k + 2^52 + 2^51 (k in the low word)
+  const double kd = km - kFm[26];
+  double r = fma(-kd, kFm[24], x);
+  r = fma(-kd, kFm[25], r);
+  // Horner: used by the throughput variants only, where registers matter more than the length of this chain
+  double t = kFm[39];
+#pragma unroll
+  for (int i = 38; i >= 28; --i) t = fma(t, r, kFm[i]);
+  const double pe = fma(r * r, t, r) + kFm[18];
+  const int k = __double2loint(km);
+  return __hiloint2double(__double2hiint(pe) + (k << 20), __double2loint(pe));
 }
 
 // sin and cos for |x| < ~1e5: three-term Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials on
