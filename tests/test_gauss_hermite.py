@@ -185,3 +185,14 @@ def test_gpu_gh_mirror(i2c_b200):
     assert relerr(np.array(graph.alphas), gg["alphas"]) < 1e-8
     K, k, sk = graph.get_local_linear_policy()
     assert relerr(K, gg["final/K"], 1e-6) < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_gh_argument_checks(i2c_b200):
+    capi = i2c_b200.capi
+    m, S = np.zeros((1, 3)), np.eye(3)[None]
+    with pytest.raises(capi.I2cError, match="degree"):
+        i2c_b200.quadrature("PendulumKnown", "observe", m, S, gh_degree=9)
+    with pytest.raises(capi.I2cError, match="degree"):
+        i2c_b200.BatchedI2c("PendulumKnown", 1, 8, np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), np.diag([1.0, 100.0, 1.0]), 100.0, 0.0,
+                            np.zeros((8, 1)), 2.0 * np.eye(1), inference="gauss_hermite", quadrature=12)

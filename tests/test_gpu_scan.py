@@ -148,3 +148,20 @@ def test_scan_minimum_energy_covariance_control(i2c_b200):
             assert relerr(Gp.field(f), Gs.field(f), floor=1e-9) < 1e-10, (it, f, relerr(Gp.field(f), Gs.field(f), floor=1e-9))
         assert relerr(Gp.alpha, Gs.alpha) < 1e-10
     assert Gp.temp == Gs.temp
+
+
+def test_scan_argument_checks(i2c_b200):
+    """Misuse is reported through the C-ABI error string, never silently redirected to another path."""
+    capi = i2c_b200.capi
+    G = well_conditioned(i2c_b200, 4, 64, 0)()
+    for n_iter, phases, chunk, needle in [
+        (1, capi.PH_FORWARD | capi.PH_BACKWARD, 4, "chunk_cells"),
+        (1, capi.PH_FORWARD | capi.PH_BACKWARD, 65, "chunk_cells"),
+        (1, capi.PH_FORWARD | capi.PH_BACKWARD | capi.PH_PROPAGATE, 16, "supports"),
+        (1, capi.PH_BACKWARD | capi.PH_MSTEP, 16, "MSTEP needs FORWARD"),
+        (0, capi.PH_FORWARD, 16, "n_iter"),
+    ]:
+        with pytest.raises(capi.I2cError, match=needle):
+            capi.check(G.lib.i2c_run_scan(G._h, n_iter, phases, chunk))
+    capi.check(G.lib.i2c_run_scan(G._h, 1, capi.PH_FORWARD | capi.PH_BACKWARD, 16))  # and the handle is still usable
+    assert np.all(G.status()[0] == 0)
