@@ -899,11 +899,15 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
     if (phases & (I2C_PH_MSTEP | I2C_PH_CALIBRATE)) alpha_pushed = true;
   }
   if (flip || alpha_pushed) {
+    bool changed = false;
     for (int s = 0; s < h->T; ++s) {
+      const int32_t before = h->flags[s];
       if (flip && h->tau > 0 && h->index[s] <= h->tau) h->flags[s] &= ~I2C_CELL_INDEPENDENT;
       if (alpha_pushed) h->flags[s] &= ~I2C_CELL_OWN_ALPHA;
+      changed = changed || h->flags[s] != before;
     }
-    CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
+    // (a pageable H2D copy serialises with the stream: only when a flag really changed, i.e. after the first iteration)
+    if (changed) CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
   }
   return 0;
 }
