@@ -235,7 +235,7 @@ def run_cuda(args, rank, world, local_rank):
     L = g.lib
 
     def e2e_step(i):
-        capi.check(L.i2c_set_initial_state(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))
+        capi.check(L.i2c_set_initial_state_async(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))  # pinned, persistent buffers
         capi.check(L.i2c_run(g._h, 1, capi.PH_LEARN))
         for m in ("alpha", "cost_m"):
             capi.check(L.i2c_get_metric(g._h, capi.METRICS[m], capi.ptr(h_m), 1))
@@ -270,7 +270,7 @@ def run_cuda(args, rank, world, local_rank):
     # Same loop for a caller that only needs the controllers at the end (EM for Ke iterations, then one read-back): every
     # step still uploads the start-state belief and reads the per-problem cost / alpha back; K, k, sigK cross PCIe once.
     def e2e_step_metrics_only():
-        capi.check(L.i2c_set_initial_state(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))
+        capi.check(L.i2c_set_initial_state_async(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))  # pinned, persistent buffers
         capi.check(L.i2c_run(g._h, 1, capi.PH_LEARN))
         for m in ("alpha", "cost_m"):
             capi.check(L.i2c_get_metric(g._h, capi.METRICS[m], capi.ptr(h_m), 1))

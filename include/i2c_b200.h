@@ -164,6 +164,9 @@ int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, cons
 /* sys.x0 / sys.sig_x0 are re-read at the start of every sweep (i2c.py:877-878); MPC overwrites them
  * (policy/mpc.py:149-150). */
 int i2c_set_initial_state(i2c_handle_t h, const double* x0, const double* sig_x0);
+/* Same without the trailing synchronisation: the (pinned) host buffers must stay valid and unchanged until the next
+ * synchronising call on the handle (i2c_synchronize or any getter); stream-ordered before the next i2c_run. */
+int i2c_set_initial_state_async(i2c_handle_t h, const double* x0, const double* sig_x0);
 int i2c_set_initial_state_dev(i2c_handle_t h, const double* x0_dev, const double* sig_x0_dev);
 
 /* Per-cell flags / indices / tau (attributes the scripts set on cells and graph). */

@@ -425,19 +425,22 @@ static int stage_in(i2c_handle_t h, const double* host, size_t elems, double** d
   return 0;
 }
 
-static int pack(i2c_handle_t h, double* rec, const FieldMap& f, int t0, int nt, const double* host, bool bcast_b) {
+// scratch_off / sync: several packs of one API call stage at different offsets of the scratch buffer and share one
+// synchronisation (the host buffers are only borrowed for the duration of the call)
+static int pack(i2c_handle_t h, double* rec, const FieldMap& f, int t0, int nt, const double* host, bool bcast_b,
+                size_t scratch_off = 0, bool sync = true) {
   size_t per = (size_t)f.rows * f.cols;
   size_t elems = (size_t)(bcast_b ? 1 : h->B) * nt * per;
-  double* dev;
-  int rc = stage_in(h, host, elems, &dev);
-  if (rc) return rc;
+  REQUIRE(scratch_off + elems <= h->scratch_elems, "internal: staging buffer too small");
+  double* dev = h->scratch + scratch_off;
+  CUDA_OK(cudaMemcpyAsync(dev, host, elems * 8, cudaMemcpyHostToDevice, h->stream));
   size_t total = (size_t)h->Bpad * nt * per;
   pack_kernel<<<nblocks(total), 256, 0, h->stream>>>(rec, f, t0, nt, h->T, f.per_cell ? h->cell_head : 0, h->B, h->Bpad,
                                                      h->ntiles, dev, bcast_b ? 1 : 0);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   // the staging buffer is reused by the next call
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (sync) CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -620,13 +623,21 @@ static int upload_flags(i2c_handle_t h) {
 
 extern "C" {
 
-int i2c_set_initial_state(i2c_handle_t h, const double* x0, const double* sig_x0) {
+static int set_initial_state_impl(i2c_handle_t h, const double* x0, const double* sig_x0, bool sync) {
   REQUIRE(h && x0 && sig_x0, "NULL argument");
   FieldMap fx{h->d.dx, 0, 0, h->d.dx, 1, 0, 0, 0};
-  int rc = pack(h, h->x0, fx, 0, 1, x0, false);
+  int rc = pack(h, h->x0, fx, 0, 1, x0, false, 0, false);
   if (rc) return rc;
   FieldMap fs{tri(h->d.dx), 0, 1, h->d.dx, h->d.dx, 0, 0, 0};
-  return pack(h, h->sig_x0, fs, 0, 1, sig_x0, false);
+  return pack(h, h->sig_x0, fs, 0, 1, sig_x0, false, align_up((size_t)h->B * h->d.dx, 32), sync);
+}
+int i2c_set_initial_state(i2c_handle_t h, const double* x0, const double* sig_x0) {
+  return set_initial_state_impl(h, x0, sig_x0, true);
+}
+// Asynchronous variant: the (pinned) host buffers must stay valid and unchanged until the next synchronising call on this
+// handle (i2c_synchronize, any getter); the copies are ordered before the next i2c_run on the handle's stream.
+int i2c_set_initial_state_async(i2c_handle_t h, const double* x0, const double* sig_x0) {
+  return set_initial_state_impl(h, x0, sig_x0, false);
 }
 
 int i2c_set_initial_state_dev(i2c_handle_t h, const double* x0_dev, const double* sig_x0_dev) {

@@ -60,7 +60,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 
 EXPORTS = [
-    "i2c_env_dims", "i2c_workspace_bytes", "i2c_create", "i2c_destroy", "i2c_set_problem", "i2c_set_initial_state",
+    "i2c_env_dims", "i2c_workspace_bytes", "i2c_create", "i2c_destroy", "i2c_set_problem", "i2c_set_initial_state", "i2c_set_initial_state_async",
     "i2c_set_initial_state_dev", "i2c_set_cell_flags", "i2c_get_cell_flags", "i2c_set_cell_index", "i2c_set_tau",
     "i2c_set_cell_targets",
     "i2c_set_alpha", "i2c_get_alpha", "i2c_set_temp", "i2c_get_temp", "i2c_run", "i2c_run_scan", "i2c_synchronize", "i2c_get_metric",
@@ -95,6 +95,7 @@ def lib():
     L.i2c_set_problem.argtypes = [C.c_void_p] + [C.c_void_p] * 11 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
                                                                     C.c_void_p]
     L.i2c_set_initial_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.i2c_set_initial_state_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.i2c_set_initial_state_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.i2c_get_initial_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.i2c_set_cell_flags.argtypes = [C.c_void_p, C.c_void_p]
