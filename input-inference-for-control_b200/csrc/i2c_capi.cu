@@ -233,6 +233,38 @@ __global__ void fill_kernel(double* p, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// Horizon shift of the MPC step in one launch (policy/mpc.py:174-181): the recycled ring slot becomes a fresh last cell
+// (constructor state with the initial action mean), its flags / index / target / alpha are reset.
+__global__ void mpc_shift_kernel(double* recA, double* recB, InitArgs a, const double* __restrict__ x0,
+                                 const double* __restrict__ sig_x0, SmallVals mu, int B, int slot, int32_t* flags, int32_t* index,
+                                 int32_t f, double* alpha_cell, double alpha_init, double* z_cell, SmallVals z, int dz) {
+  const int n = a.n, dx = a.dx, du = a.du;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.Bpad; b += gridDim.x * blockDim.x) {
+    size_t base = (((size_t)slot * a.ntiles + b / TILE) * a.E) * TILE + (b % TILE);
+    size_t xb = ((size_t)(b / TILE) * dx) * TILE + (b % TILE);
+    size_t sb = ((size_t)(b / TILE) * (dx * (dx + 1) / 2)) * TILE + (b % TILE);
+    int e = 0;
+    for (int k = 0; k < dx; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = x0[xb + (size_t)k * TILE];
+    for (int k = 0; k < du; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = mu.v[k];
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c <= r; ++c, ++e) {
+        double v = 0.0;
+        if (r < dx) v = sig_x0[sb + (size_t)(r * (r + 1) / 2 + c) * TILE];
+        else if (c >= dx) v = a.sig_u[(r - dx) * (r - dx + 1) / 2 + (c - dx)];
+        recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = v;
+      }
+    for (int k = 0; k < du * dx; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = 0.0;
+    for (int k = 0; k < du; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = mu.v[k];
+    for (int k = 0; k < du * (du + 1) / 2; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = a.sig_u[k];
+    alpha_cell[(size_t)slot * a.Bpad + b] = alpha_init;
+    if (b == 0) {
+      flags[slot] = f;
+      index[slot] = 0;
+      for (int k = 0; k < dz; ++k) z_cell[(size_t)slot * dz + k] = z.v[k];
+    }
+  }
+}
+
 static inline int nblocks(size_t total) {
   size_t b = (total + 255) / 256;
   return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -1219,18 +1251,17 @@ int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const doubl
   const int slot = (T - 1 + h->cell_head) % T;
   h->flags[slot] = I2C_CELL_INDEPENDENT | I2C_CELL_EXPERT | I2C_CELL_OWN_ALPHA;
   h->index[slot] = 0;
-  set_cell_meta_kernel<<<1, 1, 0, h->stream>>>(h->cell_flags_dev, h->cell_index_dev, slot, h->flags[slot], 0);
-  SmallVals sv;
-  for (int i = 0; i < du; ++i) sv.v[i] = mu_u_init[i];
-  double* mu_dev = h->scratch + (size_t)h->B * du + 64;  // behind the first-action staging
-  set_vals_kernel<<<1, 32, 0, h->stream>>>(mu_dev, sv, du);
-  InitArgs ia{dx, du, n, h->r.e_post(), T, h->cell_head, h->Bpad, h->ntiles, 1, {0, 0, 0}};
-  for (int i = 0; i < tri(du); ++i) ia.sig_u[i] = h->sig_u_host[i];
-  init_cells_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->recA, h->recB, ia, T - 1, 1, h->x0, h->sig_x0, mu_dev, h->B);
-  fill_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->alpha_cell + (size_t)slot * h->Bpad, (size_t)h->Bpad, alpha_init);
-  for (int i = 0; i < dz; ++i) sv.v[i] = z_new[i];
-  set_vals_kernel<<<1, 32, 0, h->stream>>>(h->z_cell + (size_t)slot * dz, sv, dz);
-  h->launches += 5;
+  {
+    SmallVals mu_v, z_v;
+    for (int i = 0; i < du; ++i) mu_v.v[i] = mu_u_init[i];
+    for (int i = 0; i < dz; ++i) z_v.v[i] = z_new[i];
+    InitArgs ia{dx, du, n, h->r.e_post(), T, h->cell_head, h->Bpad, h->ntiles, 1, {0, 0, 0}};
+    for (int i = 0; i < tri(du); ++i) ia.sig_u[i] = h->sig_u_host[i];
+    mpc_shift_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->recA, h->recB, ia, h->x0, h->sig_x0, mu_v, h->B, slot,
+                                                                     h->cell_flags_dev, h->cell_index_dev, h->flags[slot],
+                                                                     h->alpha_cell, alpha_init, h->z_cell, z_v, dz);
+  }
+  h->launches += 1;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
