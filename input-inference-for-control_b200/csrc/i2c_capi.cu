@@ -1276,23 +1276,19 @@ static int ckf_step_impl(i2c_handle_t h, const double* y, const double* u, const
   REQUIRE(h && y && u && sig_zeta, "NULL argument");
   REQUIRE(h->d.dy > 0, "this env defines no measurement map (only the quadrotor does)");
   const int dx = h->d.dx, du = h->d.du, dy = h->d.dy;
-  // stage y and u (tiled) in the scratch buffer: [ntiles][dy][32] then [ntiles][du][32]
-  size_t ny = (size_t)h->ntiles * dy * TILE, nu = (size_t)h->ntiles * du * TILE;
-  REQUIRE(2 * (ny + nu) <= h->scratch_elems, "internal: staging buffer too small");
-  double* ty = h->scratch + (size_t)h->B * (dy + du);
-  double* tu = ty + ny;
-  CUDA_OK(cudaMemcpyAsync(h->scratch, y, (size_t)h->B * dy * 8, cudaMemcpyHostToDevice, h->stream));
-  CUDA_OK(cudaMemcpyAsync(h->scratch + (size_t)h->B * dy, u, (size_t)h->B * du * 8, cudaMemcpyHostToDevice, h->stream));
-  FieldMap fy{dy, 0, 0, dy, 1, 0, 0, 0}, fu{du, 0, 0, du, 1, 0, 0, 0};
-  pack_kernel<<<nblocks((size_t)h->Bpad * dy), 256, 0, h->stream>>>(ty, fy, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles, h->scratch, 0);
-  pack_kernel<<<nblocks((size_t)h->Bpad * du), 256, 0, h->stream>>>(tu, fu, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles,
-                                                                    h->scratch + (size_t)h->B * dy, 0);
+  // stage y and u in the scratch buffer in the caller's layout ([B][dy], [B][du]); the kernel reads them directly
+  REQUIRE((size_t)h->B * (dy + du) <= h->scratch_elems, "internal: staging buffer too small");
+  double* ty = h->scratch;
+  double* tu = h->scratch + (size_t)h->B * dy;
+  CUDA_OK(cudaMemcpyAsync(ty, y, (size_t)h->B * dy * 8, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(tu, u, (size_t)h->B * du * 8, cudaMemcpyHostToDevice, h->stream));
   CkfArgs a;
   memset(&a, 0, sizeof(a));
   a.x0 = h->x0;
   a.sig_x0 = h->sig_x0;
   a.y = ty;
   a.u = tu;
+  a.canonical = 1;
   a.envpar = h->envpar;
   a.status = h->status;
   a.B = h->B;
@@ -1301,7 +1297,7 @@ static int ckf_step_impl(i2c_handle_t h, const double* y, const double* u, const
   for (int i = 0; i < tri(dx); ++i) a.sig_eta[i] = h->kp.sig_eta[i];
   full_to_tri(sig_zeta, dy, a.sig_zeta);
   int rc = launch_ckf(h->cfg.env, a, (void*)h->stream);
-  h->launches += 3;
+  h->launches += 1;
   if (rc != 0) return set_err(-100 - rc, "CKF kernel launch failed");
   if (sync) CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;

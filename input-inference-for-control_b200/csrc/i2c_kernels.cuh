@@ -2089,8 +2089,9 @@ __global__ void __launch_bounds__(64) ckf_kernel(const __grid_constant__ CkfArgs
   for (int i = 0; i < DX; ++i) m[i] = a.x0[((size_t)tile * DX + i) * TILE + lane];
 #pragma unroll
   for (int i = 0; i < TRI(DX); ++i) L[i] = a.sig_x0[((size_t)tile * TRI(DX) + i) * TILE + lane];
+  const int bc = min(tile * TILE + lane, a.B - 1);  // canonical inputs: padded lanes repeat the last roll-out
 #pragma unroll
-  for (int i = 0; i < DU; ++i) u[i] = a.u[((size_t)tile * DU + i) * TILE + lane];
+  for (int i = 0; i < DU; ++i) u[i] = a.canonical ? a.u[(size_t)bc * DU + i] : a.u[((size_t)tile * DU + i) * TILE + lane];
   bool ok = chol_rows<DX>(L, invd);
   typename Env::TrigT ctx;
   // predict: pass the belief through the dynamics with the applied control appended to every point
@@ -2121,7 +2122,7 @@ __global__ void __launch_bounds__(64) ckf_kernel(const __grid_constant__ CkfArgs
 #pragma unroll
   for (int i = 0; i < TRI(DY); ++i) Sy[i] += a.sig_zeta[i];
 #pragma unroll
-  for (int i = 0; i < DY; ++i) yv[i] = a.y[((size_t)tile * DY + i) * TILE + lane];
+  for (int i = 0; i < DY; ++i) yv[i] = a.canonical ? a.y[(size_t)bc * DY + i] : a.y[((size_t)tile * DY + i) * TILE + lane];
   ok = condition<DX, DY>(mf, S, Sy, Sxy, my, yv) && ok;
 #pragma unroll
   for (int i = 0; i < DX; ++i) a.x0[((size_t)tile * DX + i) * TILE + lane] = mf[i];

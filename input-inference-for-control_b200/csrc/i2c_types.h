@@ -104,11 +104,12 @@ int launch_quadrature(int env, int fn, const QuadArgs& a, void* stream);
 struct CkfArgs {
   double* x0;        // [ntiles][DX][32]   belief mean, updated in place
   double* sig_x0;    // [ntiles][TRI DX][32]
-  const double* y;   // [ntiles][DY][32]
-  const double* u;   // [ntiles][DU][32]
+  const double* y;   // [ntiles][DY][32], or canonical [B][DY] (canonical = 1)
+  const double* u;   // [ntiles][DU][32], or canonical [B][DU]
   const double* envpar;
   int32_t* status;
   int32_t B, ntiles;
+  int32_t canonical, pad;  // inputs in the caller's [B][d] layout (no pack kernels)
   double sf, w0, wi;
   double sig_eta[MAX_DX * (MAX_DX + 1) / 2];
   double sig_zeta[MAX_DY * (MAX_DY + 1) / 2];
