@@ -801,6 +801,70 @@ struct Worker {
 #pragma unroll
         for (int i = 0; i < DX; ++i) d[i] = c.m[i] - mx[i];
         double rho = 1.0;
+#ifndef I2C_NO_RHO_LINEAR
+        if constexpr (!LIN) {
+          // Everything below is linear or quadratic in rho: form the rho-free parts first so that they overlap with the
+          // exp() chain of the pdf ratio, and apply rho afterwards (2-3 dependent operations instead of ~15).
+          double KS0[DU * DX], kd0[DU], A0[TRI(DU)], B0[TRI(DU)], W0[DU * DX];
+#pragma unroll
+          for (int r = 0; r < DU; ++r) {
+            double sd = 0.0;
+#pragma unroll
+            for (int k = 0; k < DX; ++k) sd = fma(Kt[r * DX + k], d[k], sd);
+            kd0[r] = sd;
+#pragma unroll
+            for (int j = 0; j < DX; ++j) {
+              double s = 0.0;
+#pragma unroll
+              for (int k = 0; k < DX; ++k) s = fma(Kt[r * DX + k], c.S[six(k, j)], s);
+              KS0[r * DX + j] = s;
+              W0[r * DX + j] = s;
+            }
+            fwd_subst<DX>(c.L, c.invd, W0 + r * DX);
+          }
+#pragma unroll
+          for (int r = 0; r < DU; ++r)
+#pragma unroll
+            for (int q = 0; q <= r; ++q) {
+              double a = 0.0, b = 0.0;
+#pragma unroll
+              for (int k = 0; k < DX; ++k) {
+                a = fma(Kt[r * DX + k], Sux[q * DX + k], a);
+                b = fma(KS0[r * DX + k], Kt[q * DX + k], b);
+              }
+              A0[tix(r, q)] = a;
+              B0[tix(r, q)] = b;
+            }
+          if (!pdf_ratio(C, d, rho)) fail(I2C_FAIL_MVN, it, t);
+          const double rho2 = rho * rho;
+#pragma unroll
+          for (int i = 0; i < DX; ++i) mu[i] = c.m[i];
+#pragma unroll
+          for (int i = 0; i < TRI(DX); ++i) {
+            Sig[i] = c.S[i];
+            L[i] = c.L[i];
+          }
+#pragma unroll
+          for (int i = 0; i < DX; ++i) invd[i] = c.invd[i];
+#pragma unroll
+          for (int r = 0; r < DU; ++r) {
+            mu[DX + r] = fma(rho, kd0[r], mu_u[r]);
+#pragma unroll
+            for (int j = 0; j < DX; ++j) {
+              Sig[tix(DX + r, j)] = rho * KS0[r * DX + j];
+              L[tix(DX + r, j)] = rho * W0[r * DX + j];
+            }
+#pragma unroll
+            for (int q = 0; q <= r; ++q) {
+              const double v = fma(rho2, B0[tix(r, q)], fma(-rho, A0[tix(r, q)], Suu[tix(r, q)]));
+              Sig[tix(DX + r, DX + q)] = v;
+              L[tix(DX + r, DX + q)] = v;
+            }
+          }
+          if (!chol_rows_pre<N, DX>(L, invd)) fail(I2C_FAIL_CHOL_PRIOR, it, t);
+          goto joint_done;
+        }
+#endif
         // the quadrature cell always applies the ratio (quirk A.6.3); the linearize cell only for expert cells (:259)
         if (!lin() || (flags & I2C_CELL_EXPERT)) {
           if (!pdf_ratio(C, d, rho)) fail(I2C_FAIL_MVN, it, t);
@@ -837,6 +901,9 @@ struct Worker {
       }
       if (!build_joint(c, Kt, mu_u, Suu, !indep, mu, Sig, L, invd)) fail(I2C_FAIL_CHOL_PRIOR, it, t);
     }
+#ifndef I2C_NO_RHO_LINEAR
+  joint_done:
+#endif
     double* af = aux ? rec(p.auxf, t, LY::E_AUXF) : nullptr;
     if (aux) {
 #pragma unroll

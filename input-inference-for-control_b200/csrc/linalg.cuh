@@ -38,6 +38,31 @@ __device__ __forceinline__ bool chol_rows(double* A, double* invd) {
   return ok;
 }
 
+// Rows [START, N) whose first START columns have ALREADY been eliminated against the finished rows (the caller did the
+// forward substitution): only the trailing block is factorised.
+template <int N, int START>
+__device__ __forceinline__ bool chol_rows_pre(double* A, double* invd) {
+  bool ok = true;
+#pragma unroll
+  for (int i = START; i < N; ++i) {
+#pragma unroll
+    for (int j = START; j < i; ++j) {
+      double s = A[tix(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s = fma(-A[tix(i, k)], A[tix(j, k)], s);
+      A[tix(i, j)] = s * invd[j];
+    }
+    double d = A[tix(i, i)];
+#pragma unroll
+    for (int k = 0; k < i; ++k) d = fma(-A[tix(i, k)], A[tix(i, k)], d);
+    ok = ok && (d > 0.0) && (d < kFm[20]);
+    double r = fast_rsqrt(d);
+    invd[i] = r;
+    A[tix(i, i)] = d * r;
+  }
+  return ok;
+}
+
 // y <- L^{-1} y  (forward substitution), L packed lower with reciprocal pivots invd.
 template <int N>
 __device__ __forceinline__ void fwd_subst(const double* L, const double* invd, double* y) {
