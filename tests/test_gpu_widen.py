@@ -241,3 +241,26 @@ def test_async_policy_copy(i2c_b200):
     G.get_local_linear_policy_async(K, k, s)
     G.wait_copies()
     assert np.array_equal(K, K1) and not np.array_equal(K1, K0)
+
+
+def test_initial_state_async_upload(i2c_b200):
+    """i2c_set_initial_state_async (no trailing synchronisation; the caller keeps the pinned buffers alive) gives the same
+    sweep as the synchronous call."""
+    import torch
+
+    capi = i2c_b200.capi
+    Q, R = np.diag([1.0, 100.0, 1.0]), np.diag([2.0])
+    Ga, _ = make_pair(i2c_b200, "PendulumKnown", 70, 30, Q, R, Q, 100.0, 0.0, 5, np.array([0.3, 0.5]), 2.0 * np.eye(1), enable_aux=False)
+    Gb, _ = make_pair(i2c_b200, "PendulumKnown", 70, 30, Q, R, Q, 100.0, 0.0, 5, np.array([0.3, 0.5]), 2.0 * np.eye(1), enable_aux=False)
+    rng = np.random.default_rng(9)
+    x0 = torch.empty((70, 2), dtype=torch.float64, pin_memory=True).numpy()
+    s0 = torch.empty((70, 2, 2), dtype=torch.float64, pin_memory=True).numpy()
+    x0[:] = np.array([np.pi, 0.0]) + 0.2 * rng.normal(size=(70, 2))
+    s0[:] = 1e-4 * np.eye(2)
+    capi.check(Ga.lib.i2c_set_initial_state(Ga._h, capi.ptr(x0), capi.ptr(s0)))
+    capi.check(Gb.lib.i2c_set_initial_state_async(Gb._h, capi.ptr(x0), capi.ptr(s0)))
+    Ga.learn(2)
+    Gb.learn(2)
+    assert np.array_equal(Ga.field("K"), Gb.field("K")) and np.array_equal(Ga.alpha, Gb.alpha)
+    xa, sa = Ga.get_initial_state()
+    assert np.array_equal(xa, x0) and relerr(sa, s0) < 1e-15
