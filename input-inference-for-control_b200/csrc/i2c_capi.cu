@@ -883,6 +883,8 @@ static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   {
     const char* gm = getenv("I2C_B200_GROUP");
     kp.group_mode = gm ? atoi(gm) : -1;
+    const char* mb = getenv("I2C_B200_MINB");
+    kp.minb = mb ? atoi(mb) : 0;
     const char* gt = getenv("I2C_B200_GROUP_MAX_TILES");
     kp.group_max_tiles = gt ? atoi(gt) : 0;
   }

@@ -2072,7 +2072,16 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   if (p.ntiles <= 296 && p.T >= 8 && !p.no_team) return launch_em_team<Env, 4>(p, s);  // two blocks per SM
   if constexpr (Lay<Env>::N <= 3) {
     // small envs fit 128 registers with a few bytes of spill: worth it once >= 12 warps per SM are available
-    if (p.ntiles >= 148 * 12) return launch_em_v<Env, 4, false>(p, s, 128);
+    if (p.ntiles >= 148 * 12) {
+      // 168 registers / 12 warps per SM (no spills) is 17 % faster per wave than 128 registers / 16 warps per SM, but its
+      // waves hold 1776 warps instead of 2368: take it when the batch fills its waves to >= 87 % (measured: 10.3e9 against
+      // 8.8e9 updates/s at 56 832 and 113 664 problems, 10.3e9 against 9.7e9 at 262 144; 7.0e9 against 8.9e9 at 65 536)
+      const int waves3 = (p.ntiles + 148 * 12 - 1) / (148 * 12);
+      const bool fills3 = (long long)waves3 * 148 * 12 * 100 <= (long long)p.ntiles * 115;
+      const int minb = p.minb ? p.minb : (fills3 ? 3 : 4);
+      if (minb == 3) return launch_em_v<Env, 3, false>(p, s, 128);
+      return launch_em_v<Env, 4, false>(p, s, 128);
+    }
   }
   // fewer than 4 warps per SM: every warp is latency-bound -> cp.async + staged targets; else TMA bulk copies
   if (p.ntiles < 148 * 4) return launch_em_v<Env, 1, true>(p, s, threads);

@@ -69,6 +69,7 @@ struct KParams {
   // (new fields go at the END: the offsets of the hot fields above are part of the tuned code generation)
   int32_t group_mode;      // -1 auto, 0 never, 1 always: G-lanes-per-problem kernel (i2c_group.cuh)
   int32_t group_max_tiles; // auto: use it up to this many tiles (0 = built-in policy)
+  int32_t minb;            // A/B: resident 128-thread blocks per SM of the small-env throughput variant (0 = default 4)
 };
 
 // element counts of the records for given dims
