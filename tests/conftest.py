@@ -31,8 +31,29 @@ def relerr(a, ref, floor=0.0):
         return float("inf")
     denom = max(float(np.max(np.abs(ref))) if ref.size else 0.0, floor)
     if denom == 0.0:
-        return float(np.max(np.abs(a))) if a.size else 0.0
-    return float(np.max(np.abs(a - ref)) / denom)
+        e = float(np.max(np.abs(a))) if a.size else 0.0
+    else:
+        e = float(np.max(np.abs(a - ref)) / denom)
+    _report(e, floor)
+    return e
+
+
+def _report(e, floor):
+    """With I2C_PARITY_REPORT=<file> every measured error is appended as {test, where, err}: the evidence behind the
+    tolerances written in the tests (tools/parity_floors.py summarises it; profiles/*parity_floors*)."""
+    path = os.environ.get("I2C_PARITY_REPORT")
+    if not path:
+        return
+    import inspect
+    import json
+
+    fr = inspect.stack()[2]
+    where = f"{os.path.basename(fr.filename)}:{fr.lineno}"
+    if os.path.basename(fr.filename) == "conftest.py" or fr.function in ("rel", "compare_cells"):
+        up = inspect.stack()[3]
+        where += f"<{os.path.basename(up.filename)}:{up.lineno}"
+    with open(path, "a") as f:
+        f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "where": where + ("[gain]" if floor > 0 else ""), "err": e}) + "\n")
 
 
 # tensors whose value is a solve against a small covariance: their round-off floor in the reference
