@@ -12,9 +12,9 @@ namespace i2c {
 // instructions of a pendulum forward cell (profiles/r01d source view).  Same values, same operation order: bit-identical.
 static __constant__ double kFm[40] = {
     6.36619772367581382433e-01,   // 0  2/pi
-    1.57079632673412561417e+00,   // 1  P1: first 33 bits of pi/2
-    6.07710050650619224932e-11,   // 2  P2
-    2.02226624879595063154e-21,   // 3  P3
+    1.5707963267948966,           // 1  P1 = fl(pi/2)
+    6.123233995736766e-17,        // 2  P2 = fl(pi/2 - P1)
+    -1.4973849048591698e-33,      // 3  P3 = fl(pi/2 - P1 - P2)
     -1.66666666666666324348e-01,  // 4  S1
     8.33333333332248946124e-03,   // 5  S2
     -1.98412698298579493134e-04,  // 6  S3
@@ -86,17 +86,20 @@ __device__ __forceinline__ double fast_exp_neg(double x) {
   return __hiloint2double(__double2hiint(pe) + (k << 20), __double2loint(pe));
 }
 
-// sin and cos for |x| < ~1e5: three-term Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials on
-// [-pi/4, pi/4] (Horner split in even/odd halves for ILP).  Branch-free quadrant selection.  Larger arguments fall
-// back to the library routine (warp-uniform in practice: never taken for the registered environments).
+// sin and cos, branch-free for every finite argument: round-to-nearest multiple of pi/2 by the magic-number trick (the
+// quadrant is the low word of the biased sum), then a three-term Cody-Waite reduction with FULL-precision constants.  With
+// FMA the first step r1 = x - k P1 is exact for |k| < 2^51 (x and k P1 are multiples of 2^-52 and |r1| < 1), so the
+// classical 33-bit split of fdlibm -- and with it the |x| < 1e5 range limit and the library fall-back that used to sit
+// behind a branch in every call -- is not needed: <= 1.5 ulp for |x| <= 1e12 rad (tools/micro/sincos_model.c on the host,
+// tests/test_gpu_fastmath.py on the device).  The branch mattered: with it every sincos of a cell was its own basic block
+// (BSSY / BRA / BSYNC), ptxas could not interleave the three independent evaluations of a sigma-point transform, and the
+// jump over the slow-path code cost instruction-cache misses (profiles/r01i source view: 3 x 160-230 cycles per transform,
+// serialised).  fdlibm kernel polynomials on [-pi/4, pi/4] (Estrin pairing for ILP), branch-free quadrant selection.
 __device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
-  if (fabs(x) > 1.0e5) {
-    sincos(x, sp, cp);
-    return;
-  }
-  const double TWO_OVER_PI = kFm[0], P1 = kFm[1], P2 = kFm[2], P3 = kFm[3];
-  const double kd = rint(x * TWO_OVER_PI);
-  const int k = (int)kd;
+  const double P1 = kFm[1], P2 = kFm[2], P3 = kFm[3];
+  const double km = fma(x, kFm[0], kFm[26]);  // k + 2^52 + 2^51
+  const double kd = km - kFm[26];
+  const int k = __double2loint(km);
   double r = fma(-kd, P1, x);
   r = fma(-kd, P2, r);
   r = fma(-kd, P3, r);

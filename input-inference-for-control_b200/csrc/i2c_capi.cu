@@ -913,6 +913,12 @@ static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   kp.z_per_problem = h->cfg.z_per_problem;
   kp.temp0 = h->temp;
   kp.dtemp = h->dtemp;
+  {
+    bool own = false;
+    for (int f : h->flags) own = own || (f & I2C_CELL_OWN_ALPHA);
+    kp.hot = kp.fast_obs && !kp.z_per_problem && !own && !(phases & I2C_PH_STORE_AUX) && !kp.linearize && kp.gh.degree == 0 &&
+             getenv("I2C_B200_NO_HOT") == nullptr;
+  }
   return kp;
 }
 

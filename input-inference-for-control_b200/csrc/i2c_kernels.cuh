@@ -458,7 +458,11 @@ struct Carry {
 // warp and cell (fewest instructions), targets / flags are plain cached loads.
 // LIN = Linearize inference compiled in (separate instantiation: keeps the cubature kernels small).
 // GH = Gauss-Hermite tensor-grid rule instead of the cubature points (separate instantiation as well).
-template <class Env, bool META, bool LIN = false, bool GH = false>
+// HOT = the common configuration is compiled in instead of tested per cell (launcher: KParams::hot): cubature rule with
+// zero centre weight (structured cost-feature moments), no auxiliary records, shared cell targets staged with the records,
+// no per-cell alpha.  Every one of these run-time switches was a (uniform) branch in the cell loops: ~10 basic-block
+// boundaries per forward cell that stop ptxas from overlapping the independent dependency chains across them.
+template <class Env, bool META, bool LIN = false, bool GH = false, bool HOT = false>
 struct Worker {
   static constexpr bool BULK = kUseBulk && !META;
   using LY = Lay<Env>;
@@ -502,8 +506,11 @@ struct Worker {
       info = (it << 16) | (t & 0xffff);
     }
   }
+  __device__ __forceinline__ bool fobs() const { return HOT || p.fast_obs; }
+  __device__ __forceinline__ bool smeta() const { return HOT || p.stage_meta; }
+  __device__ __forceinline__ bool zpp() const { return !HOT && p.z_per_problem; }
   __device__ __forceinline__ void load_z(int t, double* z) const {
-    if (p.z_per_problem) {
+    if (zpp()) {
       const double* q = p.z_cell + ((size_t)slot(t) * p.ntiles + tile) * DZ * TILE + lane;
 #pragma unroll
       for (int a = 0; a < DZ; ++a) z[a] = q[a * TILE];
@@ -516,8 +523,8 @@ struct Worker {
   __device__ __forceinline__ void stage_meta(double* sbuf, int t) const {
     const int sl = slot(t);
     const unsigned s0 = (unsigned)__cvta_generic_to_shared(sbuf);
-    const double* zsrc = p.z_per_problem ? p.z_cell + ((size_t)sl * p.ntiles + tile) * DZ * TILE + lane : p.z_cell + sl * DZ;
-    const size_t zstride = p.z_per_problem ? TILE : 1;
+    const double* zsrc = zpp() ? p.z_cell + ((size_t)sl * p.ntiles + tile) * DZ * TILE + lane : p.z_cell + sl * DZ;
+    const size_t zstride = zpp() ? TILE : 1;
 #pragma unroll
     for (int a = 0; a < DZ; ++a)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s0 + (LY::S_Z + a) * TILE * 8), "l"(zsrc + a * zstride) : "memory");
@@ -525,7 +532,7 @@ struct Worker {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s0 + LY::S_META * TILE * 8 + 4), "l"(p.cell_index + sl) : "memory");
   }
   __device__ __forceinline__ void staged_z(const double* sbuf, int t, double* z) const {
-    if (LY::STAGED && META && p.stage_meta) {
+    if (LY::STAGED && META && smeta()) {
 #pragma unroll
       for (int a = 0; a < DZ; ++a) z[a] = sbuf[(LY::S_Z + a) * TILE];
     } else {
@@ -534,7 +541,7 @@ struct Worker {
   }
   __device__ __forceinline__ int staged_flags(const double* sbuf, int t, bool flipped) const {
     int flags, index;
-    if (LY::STAGED && META && p.stage_meta) {
+    if (LY::STAGED && META && smeta()) {
       const int2 m = *reinterpret_cast<const int2*>(sbuf + LY::S_META * TILE);
       flags = m.x;
       index = m.y;
@@ -586,7 +593,7 @@ struct Worker {
       if (tn_valid) {
         double* nxt = stage + (tn & 1) * (LY::E_STAGE_TOT * TILE);
         rec_issue<E>(nxt, rec(base_g, tn, Erec), tn & 1);
-        if (META && p.stage_meta) stage_meta(nxt, tn);
+        if (META && smeta()) stage_meta(nxt, tn);
       }
       stage_commit();
       stage_wait<1>();
@@ -602,7 +609,7 @@ struct Worker {
     if constexpr (LY::STAGED) {
       double* nxt = stage + (t & 1) * (LY::E_STAGE_TOT * TILE);
       rec_issue<E>(nxt, rec(base_g, t, Erec), t & 1);
-      if (META && p.stage_meta) stage_meta(nxt, t);
+      if (META && smeta()) stage_meta(nxt, t);
       stage_commit();
     }
   }
@@ -620,6 +627,7 @@ struct Worker {
     }
   }
   __device__ __forceinline__ double cell_alpha(int t, int flags, double alpha) const {
+    if constexpr (HOT) return alpha;
     return ((flags & I2C_CELL_OWN_ALPHA) && own_alpha_valid) ? p.alpha_cell[(size_t)slot(t) * p.Bpad + b] : alpha;
   }
 
@@ -627,8 +635,10 @@ struct Worker {
   // the library routine: measured, the custom one makes ptxas schedule the forward cell worse (-3 % at 4096 problems,
   // Estrin or Horner alike) although its dependency chain is shorter.  The two agree to <= 2 ulp.
   __device__ __forceinline__ static double pdf_exp(double x) {
+#ifdef I2C_LAT_LIBEXP
     if constexpr (META) return exp(x);
-    else return fast_exp_neg(x);
+#endif
+    return fast_exp_neg(x);
   }
   // exp(-1/2 d^T C^-1 d): the pdf ratio w/Z of i2c.py:369-374 (scipy multivariate_normal)
   __device__ __forceinline__ bool pdf_ratio(const double* C_in, const double* d_in, double& rho) {
@@ -764,7 +774,7 @@ struct Worker {
   __device__ __forceinline__ void xform(const double* m, const double* L, double sf, double w0, double wi, Eval&& eval,
                                         double* my, double* Syy, double* Dm) const {
     if constexpr (GH) grid_transform<D_, DY_>(m, L, p.gh, eval, my, Syy, Dm);
-    else sigma_transform<D_, DY_>(m, L, sf, w0, wi, eval, my, Syy, Dm);
+    else sigma_transform<D_, DY_>(m, L, sf, HOT ? 0.0 : w0, wi, eval, my, Syy, Dm);  // HOT: zero centre weight
   }
 
   // ---------------------------------------------------------------------------------- forward cell
@@ -917,7 +927,7 @@ struct Worker {
       double mz[DZ], Sz[TRI(DZ)], Sxy[N * DZ], z[DZ];
       if constexpr (LIN) {
         lin_obs_moments<N, DZ, false, true>(mu, Sig, mz, Sz, Sxy);
-      } else if (p.fast_obs) {
+      } else if (fobs()) {
         structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Sxy);
       } else {
         TrigT ctx;
@@ -982,7 +992,7 @@ struct Worker {
     // ---- terminal cost update on the outgoing message (i2c.py:430-443)
     if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf && !lin()) {
       double mz[DZT], Sz[TRI(DZT)], Sxy[DX * DZT];
-      if (p.fast_obs) {
+      if (fobs()) {
         structured_obs_moments<Env, DX, DZT, true>(c.m, c.S, c.L, p.sf_x, p.wi_x, mz, Sz, Sxy);
       } else {
         TrigT ctx;
@@ -1127,7 +1137,7 @@ struct Worker {
       if constexpr (LIN) {
         // mu_z0_m = observe(mu_xu0_m); sig_z0_m = C sig_x0_m C^T + D sig_u0_m D^T (no cross term, i2c.py:538-540)
         lin_obs_moments<N, DZ, false, false>(mu, Sig, mz, Sz, nullptr);
-      } else if (p.fast_obs) {
+      } else if (fobs()) {
         double Cxy[N * DZ];
         structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Cxy);
       } else {
@@ -1372,7 +1382,7 @@ struct Worker {
     }
     {
       double mz[DZ], Sz[TRI(DZ)], Dm[N * DZ], z[DZ];
-      if (p.fast_obs) {
+      if (fobs()) {
         structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Dm);
       } else {
         TrigT ctx;
@@ -1781,7 +1791,7 @@ struct Worker {
     if (main_warp) pipe_init();
     const double HALF_LOG_2PIE = 1.4189385332046727;  // 0.5 * log(2 pi e)
     double alpha = p.alpha[b];
-    const bool aux = p.phases & I2C_PH_STORE_AUX;
+    const bool aux = !HOT && (p.phases & I2C_PH_STORE_AUX);
     bool flipped = false;  // _update_priors has cleared state_action_independence for index <= tau
     double temp = p.temp0;
     const int T = p.T;
@@ -2004,29 +2014,34 @@ __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ K
 }
 
 // Latency-regime kernel: one block of W warps per tile (see Worker::run_impl<true>).
-template <class Env, int W>
+template <class Env, int W, bool HOT>
 __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_constant__ KParams pin) {
   const int w = threadIdx.x / TILE, lane = threadIdx.x % TILE;
   extern __shared__ __align__(128) double stage_smem[];
   double* red = stage_smem + Lay<Env>::E_TEAM_STAGE * TILE + kNumBars;
-  Worker<Env, true> wk(pin, blockIdx.x, lane, stage_smem + lane,
+  Worker<Env, true, false, false, HOT> wk(pin, blockIdx.x, lane, stage_smem + lane,
                        reinterpret_cast<uint64_t*>(stage_smem + Lay<Env>::E_TEAM_STAGE * TILE));
   wk.template run_impl<true>(w, W, red);
 }
 
-template <class Env, int W>
-static int launch_em_team(const KParams& p, cudaStream_t s) {
+template <class Env, int W, bool HOT>
+static int launch_em_team_v(const KParams& p, cudaStream_t s) {
   const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(em_team_kernel<Env, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(em_team_kernel<Env, W, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   KParams q = p;
   q.stage_meta = Lay<Env>::STAGED;
-  em_team_kernel<Env, W><<<p.ntiles, W * TILE, smem, s>>>(q);
+  em_team_kernel<Env, W, HOT><<<p.ntiles, W * TILE, smem, s>>>(q);
   return (int)cudaGetLastError();
+}
+template <class Env, int W>
+static int launch_em_team(const KParams& p, cudaStream_t s) {
+  if (p.hot) return launch_em_team_v<Env, W, true>(p, s);
+  return launch_em_team_v<Env, W, false>(p, s);
 }
 
 template <class Env, int MINB, bool LAT, bool LIN = false, bool GH = false>

@@ -152,13 +152,13 @@ struct LogAcc {
   int e;
   __device__ __forceinline__ void reset() { m = 1.0; e = 0; }
   __device__ __forceinline__ void mul(double x) {
+    // branch-free renormalisation: move the exponent of the running product into e after every factor (five integer
+    // instructions; a data-dependent branch here split the cell updates into extra basic blocks).  Factors are Cholesky
+    // pivots: positive and normal whenever the problem's status is OK.
     m *= x;
-    // renormalise only when the running product leaves a safe range (pivots are ~1e-6 .. 1e3: rarely taken)
-    if (!(m > kFm[21] && m < kFm[22])) {
-      int ex;
-      m = frexp(m, &ex);
-      e += ex;
-    }
+    const int hi = __double2hiint(m);
+    e += ((hi >> 20) & 0x7ff) - 1023;
+    m = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(m));
   }
   __device__ __forceinline__ double value() const { return log(m) + 0.6931471805599453 * (double)e; }
 };
