@@ -12,9 +12,29 @@
 
 namespace i2c {
 
-template <int NA>
+// MODE bit 0: branch-free sincos (latency variants: independent evaluations interleave) instead of the sequenced one
+//              (throughput variants: lower register pressure);
+// MODE bit 1: angle addition ("PM").  The sigma points of column j move an angle by +-d, d = sf L[angle][j], so
+//              sin / cos(m +- d) = s_m c_d +- c_m s_d / c_m c_d -+ s_m s_d: ONE sincos of the offset serves both points of
+//              the column (offsets(): once per transform).  The minus point is announced to the env maps by bit 6 of
+//              the column index (kMinus).
+constexpr int kMinus = 64;
+template <int NA, int MODE = 0, int NJ = 1>
 struct Trig {
-  double s[NA > 0 ? NA : 1], c[NA > 0 ? NA : 1];
+  static constexpr bool kFree = MODE & 1, kPM = (MODE & 2) != 0;
+  static constexpr int A = NA > 0 ? NA : 1, J = NJ > 0 ? NJ : 1;
+  double s[A], c[A];
+  double ds[kPM ? A * J : 1], dc[kPM ? A * J : 1];
+  __device__ __forceinline__ void sc(double x, double* sp, double* cp) const {
+    if constexpr (kFree) fast_sincos(x, sp, cp);
+    else seq_sincos(x, sp, cp);
+  }
+  // sin / cos of (centre angle a) +- (offset of column j)
+  __device__ __forceinline__ void pm(int a, int j, bool minus, double& so, double& co) const {
+    const double sd = minus ? -ds[a * J + j] : ds[a * J + j], cd = dc[a * J + j];
+    so = fma(s[a], cd, c[a] * sd);
+    co = fma(c[a], cd, -(s[a] * sd));
+  }
 };
 
 // ------------------------------------------------------------------ linear systems
@@ -23,7 +43,9 @@ struct Trig {
 struct EnvLinear {
   static constexpr int DX = 2, DU = 1, DZ = 3, DZT = 2, NP = 8, DY = 0, NA = 0;
   static constexpr bool HAS_TERM = true, LINEAR = true;
+  static constexpr int NJ = 0;
   using TrigT = Trig<NA>;
+  template <class TT> __device__ static void offsets(const double*, double, TT&) {}
   // z = E x + F u (+ e = 0): observe_linearize (env_def.py:171-181): E = [I2; 0], F = [0 0 1]^T
   __host__ __device__ static constexpr double obsE(int a, int i) { return a == i ? 1.0 : 0.0; }
   __host__ __device__ static constexpr double obsF(int a, int) { return a == 2 ? 1.0 : 0.0; }
@@ -38,17 +60,17 @@ struct EnvLinear {
     y[0] = par[0] * xu[0] + par[1] * xu[1] + par[4] * xu[2] + par[6];
     y[1] = par[2] * xu[0] + par[3] * xu[1] + par[5] * xu[2] + par[7];
   }
-  __device__ static void trig_nl(const double*, int, const TrigT&, double*) {}
-  __device__ static void center(const double*, TrigT&) {}
-  __device__ static void dyn(const double* xu, int, const TrigT&, const double* par, double* y) {
+  template <class TT> __device__ static void trig_nl(const double*, int, const TT&, double*) {}
+  template <class TT> __device__ static void center(const double*, TT&) {}
+  template <class TT> __device__ static void dyn(const double* xu, int, const TT&, const double* par, double* y) {
     y[0] = fma(par[0], xu[0], fma(par[1], xu[1], fma(par[4], xu[2], par[6])));
     y[1] = fma(par[2], xu[0], fma(par[3], xu[1], fma(par[5], xu[2], par[7])));
   }
-  __device__ static void obs(const double* xu, int, const TrigT&, double* z) {
+  template <class TT> __device__ static void obs(const double* xu, int, const TT&, double* z) {
     z[0] = xu[0]; z[1] = xu[1]; z[2] = xu[2];
   }
-  __device__ static void obs_term(const double* x, int, const TrigT&, double* z) { z[0] = x[0]; z[1] = x[1]; }
-  __device__ static void measure(const double*, int, const TrigT&, double*) {}
+  template <class TT> __device__ static void obs_term(const double* x, int, const TT&, double* z) { z[0] = x[0]; z[1] = x[1]; }
+  template <class TT> __device__ static void measure(const double*, int, const TT&, double*) {}
 };
 
 // LinearMinimumEnergyDef: env_def.py:194-230 (cost on u only).
@@ -58,7 +80,7 @@ struct EnvLinearMinEnergy : EnvLinear {
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 1.0; }
   __host__ __device__ static constexpr int obs_src(int) { return 2; }
-  __device__ static void obs(const double* xu, int, const TrigT&, double* z) { z[0] = xu[2]; }
+  template <class TT> __device__ static void obs(const double* xu, int, const TT&, double* z) { z[0] = xu[2]; }
 };
 
 // Literals of the hot dynamics live in the constant bank (fp64 instructions take c[bank][offset] operands directly; a
@@ -92,10 +114,16 @@ struct EnvPendulum {
   static constexpr bool HAS_TERM = true, LINEAR = false;
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
-  using TrigT = Trig<NA>;
-  __device__ static void center(const double* m, TrigT& t) { fast_sincos(m[0], &t.s[0], &t.c[0]); }
-  __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j != 0) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[0], &s, &co); }
+  static constexpr int NJ = 1;
+  using TrigT = Trig<NA, 0, NJ>;
+  template <class TT> __device__ static void center(const double* m, TT& t) { t.sc(m[0], &t.s[0], &t.c[0]); }
+  template <class TT> __device__ static void offsets(const double* L, double sf, TT& t) {
+    if constexpr (TT::kPM) t.sc(sf * L[tix(0, 0)], &t.ds[0], &t.dc[0]);
+  }
+  template <class TT> __device__ static void trig(const double* x, int j, const TT& c, double& s, double& co) {
+    if (j < 0 || (j & ~kMinus) != 0) { s = c.s[0]; co = c.c[0]; }
+    else if constexpr (TT::kPM) c.pm(0, 0, j & kMinus, s, co);
+    else c.sc(x[0], &s, &co);
   }
   // scalar-generic dynamics (double or Dual): used by the Linearize inference to get value + Jacobian in one pass
   template <class T>
@@ -112,8 +140,8 @@ struct EnvPendulum {
   static constexpr int OBS_NL = 2, OBS_JMAX = 0;  // z = [sin th, cos th | thd, u]
   __host__ __device__ static constexpr int obs_src(int a) { return a < 2 ? -1 - a : a - 1; }
   __host__ __device__ static constexpr int term_src(int a) { return a < 2 ? -1 - a : a - 1; }
-  __device__ static void trig_nl(const double* x, int j, const TrigT& c, double* y) { trig(x, j, c, y[0], y[1]); }
-  __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
+  template <class TT> __device__ static void trig_nl(const double* x, int j, const TT& c, double* y) { trig(x, j, c, y[0], y[1]); }
+  template <class TT> __device__ static void dyn(const double* xu, int j, const TT& c, const double*, double* y) {
     const double dt = kPendulum[0], d = kPendulum[1];
     double s, co;
     trig(xu, j, c, s, co);
@@ -126,16 +154,16 @@ struct EnvPendulum {
     y[0] = fma(xd, dt, xu[0]);
     y[1] = xd;
   }
-  __device__ static void obs(const double* xu, int j, const TrigT& c, double* z) {
+  template <class TT> __device__ static void obs(const double* xu, int j, const TT& c, double* z) {
     trig(xu, j, c, z[0], z[1]);
     z[2] = xu[1];
     z[3] = xu[2];
   }
-  __device__ static void obs_term(const double* x, int j, const TrigT& c, double* z) {
+  template <class TT> __device__ static void obs_term(const double* x, int j, const TT& c, double* z) {
     trig(x, j, c, z[0], z[1]);
     z[2] = x[1];
   }
-  __device__ static void measure(const double*, int, const TrigT&, double*) {}
+  template <class TT> __device__ static void measure(const double*, int, const TT&, double*) {}
 };
 
 // PendulumKnownActReg: env_def.py:312-346 (cost on u only, no terminal features).
@@ -145,9 +173,9 @@ struct EnvPendulumActReg : EnvPendulum {
   static constexpr int OBS_NL = 0, OBS_JMAX = -1;
   __host__ __device__ static constexpr int obs_src(int) { return 2; }
   __host__ __device__ static constexpr int term_src(int) { return 0; }
-  __device__ static void trig_nl(const double*, int, const TrigT&, double*) {}
-  __device__ static void obs(const double* xu, int, const TrigT&, double* z) { z[0] = xu[2]; }
-  __device__ static void obs_term(const double*, int, const TrigT&, double* z) { z[0] = 0.0; }
+  template <class TT> __device__ static void trig_nl(const double*, int, const TT&, double*) {}
+  template <class TT> __device__ static void obs(const double* xu, int, const TT&, double* z) { z[0] = xu[2]; }
+  template <class TT> __device__ static void obs_term(const double*, int, const TT&, double* z) { z[0] = 0.0; }
 };
 
 // ------------------------------------------------------------------ cart-pole
@@ -157,10 +185,19 @@ struct EnvCartpole {
   static constexpr bool HAS_TERM = true, LINEAR = false;
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
-  using TrigT = Trig<NA>;
-  __device__ static void center(const double* m, TrigT& t) { fast_sincos(m[1], &t.s[0], &t.c[0]); }
-  __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[1], &s, &co); }
+  static constexpr int NJ = 2;
+  using TrigT = Trig<NA, 0, NJ>;
+  template <class TT> __device__ static void center(const double* m, TT& t) { t.sc(m[1], &t.s[0], &t.c[0]); }
+  template <class TT> __device__ static void offsets(const double* L, double sf, TT& t) {
+    if constexpr (TT::kPM) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) t.sc(sf * L[tix(1, j)], &t.ds[j], &t.dc[j]);
+    }
+  }
+  template <class TT> __device__ static void trig(const double* x, int j, const TT& c, double& s, double& co) {
+    if (j < 0 || (j & ~kMinus) > 1) { s = c.s[0]; co = c.c[0]; }
+    else if constexpr (TT::kPM) c.pm(0, j & ~kMinus, j & kMinus, s, co);
+    else c.sc(x[1], &s, &co);
   }
   template <class T>
   __device__ static void dyn_g(const T* xu, const double*, T* y) {
@@ -181,8 +218,8 @@ struct EnvCartpole {
   static constexpr int OBS_NL = 2, OBS_JMAX = 1;  // z = [x, sin th, cos th, xd, thd, u]
   __host__ __device__ static constexpr int obs_src(int a) { return a == 0 ? 0 : (a <= 2 ? -a : a - 1); }
   __host__ __device__ static constexpr int term_src(int a) { return a == 0 ? 0 : (a <= 2 ? -a : a - 1); }
-  __device__ static void trig_nl(const double* x, int j, const TrigT& c, double* y) { trig(x, j, c, y[0], y[1]); }
-  __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
+  template <class TT> __device__ static void trig_nl(const double* x, int j, const TT& c, double* y) { trig(x, j, c, y[0], y[1]); }
+  template <class TT> __device__ static void dyn(const double* xu, int j, const TT& c, const double*, double* y) {
     // kCartpole = {-Mp l, Mt g, l, 4/3 Mt, Mp, Mp l, 1/Mt, dt, -5, 5}
     const double dt = kCartpole[7];
     double u = fmin(fmax(xu[4], kCartpole[8]), kCartpole[9]);
@@ -198,17 +235,17 @@ struct EnvCartpole {
     y[2] = fma(dt, x_acc, xu[2]);
     y[3] = fma(dt, th_acc, xu[3]);
   }
-  __device__ static void obs(const double* xu, int j, const TrigT& c, double* z) {
+  template <class TT> __device__ static void obs(const double* xu, int j, const TT& c, double* z) {
     z[0] = xu[0];
     trig(xu, j, c, z[1], z[2]);
     z[3] = xu[2]; z[4] = xu[3]; z[5] = xu[4];
   }
-  __device__ static void obs_term(const double* x, int j, const TrigT& c, double* z) {
+  template <class TT> __device__ static void obs_term(const double* x, int j, const TT& c, double* z) {
     z[0] = x[0];
     trig(x, j, c, z[1], z[2]);
     z[3] = x[2]; z[4] = x[3];
   }
-  __device__ static void measure(const double*, int, const TrigT&, double*) {}
+  template <class TT> __device__ static void measure(const double*, int, const TT&, double*) {}
 };
 
 // ------------------------------------------------------------------ double cart-pole
@@ -219,16 +256,29 @@ struct EnvDoubleCartpole {
   static constexpr bool HAS_TERM = true, LINEAR = false;
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
-  using TrigT = Trig<NA>;
-  __device__ static void center(const double* m, TrigT& t) {
-    fast_sincos(m[1], &t.s[0], &t.c[0]);
-    fast_sincos(m[2], &t.s[1], &t.c[1]);
+  static constexpr int NJ = 3;
+  using TrigT = Trig<NA, 0, NJ>;
+  template <class TT> __device__ static void center(const double* m, TT& t) {
+    t.sc(m[1], &t.s[0], &t.c[0]);
+    t.sc(m[2], &t.s[1], &t.c[1]);
   }
-  __device__ static void trig1(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j < 0 || j > 1) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[1], &s, &co); }
+  template <class TT> __device__ static void offsets(const double* L, double sf, TT& t) {
+    if constexpr (TT::kPM) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) t.sc(sf * L[tix(1, j)], &t.ds[j], &t.dc[j]);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t.sc(sf * L[tix(2, j)], &t.ds[3 + j], &t.dc[3 + j]);
+    }
   }
-  __device__ static void trig2(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j < 0 || j > 2) { s = c.s[1]; co = c.c[1]; } else { fast_sincos(x[2], &s, &co); }
+  template <class TT> __device__ static void trig1(const double* x, int j, const TT& c, double& s, double& co) {
+    if (j < 0 || (j & ~kMinus) > 1) { s = c.s[0]; co = c.c[0]; }
+    else if constexpr (TT::kPM) c.pm(0, j & ~kMinus, j & kMinus, s, co);
+    else c.sc(x[1], &s, &co);
+  }
+  template <class TT> __device__ static void trig2(const double* x, int j, const TT& c, double& s, double& co) {
+    if (j < 0 || (j & ~kMinus) > 2) { s = c.s[1]; co = c.c[1]; }
+    else if constexpr (TT::kPM) c.pm(1, j & ~kMinus, j & kMinus, s, co);
+    else c.sc(x[2], &s, &co);
   }
   template <class T>
   __device__ static void dyn_g(const T* xu, const double*, T* y) {
@@ -268,17 +318,22 @@ struct EnvDoubleCartpole {
   static constexpr int OBS_NL = 4, OBS_JMAX = 2;  // z = [x, s1, c1, s2, c2, xd, thd1, thd2, u]
   __host__ __device__ static constexpr int obs_src(int a) { return a == 0 ? 0 : (a <= 4 ? -a : a - 2); }
   __host__ __device__ static constexpr int term_src(int a) { return a == 0 ? 0 : (a <= 4 ? -a : a - 2); }
-  __device__ static void trig_nl(const double* x, int j, const TrigT& c, double* y) {
+  template <class TT> __device__ static void trig_nl(const double* x, int j, const TT& c, double* y) {
     trig1(x, j, c, y[0], y[1]);
     trig2(x, j, c, y[2], y[3]);
   }
-  __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
+  template <class TT> __device__ static void dyn(const double* xu, int j, const TT& c, const double*, double* y) {
     // kDcp = {dt, a12, a13, a23, M22, M33, -a12, -a13, -a23, -(Mp1 l1 + Mp2 L1) g, -Mp2 l2 g, 3, -10, 10, 1/sqrt(Mt)}
     const double dt = kDcp[0], a12 = kDcp[1], a13 = kDcp[2], a23 = kDcp[3], M22 = kDcp[4], M33 = kDcp[5];
     double s1, c1, s2, c2, sd, cd;
     trig1(xu, j, c, s1, c1);
     trig2(xu, j, c, s2, c2);
-    fast_sincos(xu[1] - xu[2], &sd, &cd);
+    if constexpr (TT::kPM) {  // sin / cos(th1 - th2) from the angles' own values: no third evaluation per point
+      sd = fma(s1, c2, -(c1 * s2));
+      cd = fma(c1, c2, s1 * s2);
+    } else {
+      c.sc(xu[1] - xu[2], &sd, &cd);
+    }
     double M12 = a12 * c1, M13 = a13 * c2, M23 = a23 * cd;
     double td1 = xu[4], td2 = xu[5];
     double C12 = kDcp[6] * td1 * s1, C13 = kDcp[7] * td2 * s2, C23 = a23 * td2 * sd, C32 = kDcp[8] * td1 * sd;
@@ -305,19 +360,19 @@ struct EnvDoubleCartpole {
     y[2] = fma(v3, dt, xu[2]);
     y[3] = v1; y[4] = v2; y[5] = v3;
   }
-  __device__ static void obs(const double* xu, int j, const TrigT& c, double* z) {
+  template <class TT> __device__ static void obs(const double* xu, int j, const TT& c, double* z) {
     z[0] = xu[0];
     trig1(xu, j, c, z[1], z[2]);
     trig2(xu, j, c, z[3], z[4]);
     z[5] = xu[3]; z[6] = xu[4]; z[7] = xu[5]; z[8] = xu[6];
   }
-  __device__ static void obs_term(const double* x, int j, const TrigT& c, double* z) {
+  template <class TT> __device__ static void obs_term(const double* x, int j, const TT& c, double* z) {
     z[0] = x[0];
     trig1(x, j, c, z[1], z[2]);
     trig2(x, j, c, z[3], z[4]);
     z[5] = x[3]; z[6] = x[4]; z[7] = x[5];
   }
-  __device__ static void measure(const double*, int, const TrigT&, double*) {}
+  template <class TT> __device__ static void measure(const double*, int, const TT&, double*) {}
 };
 
 // ------------------------------------------------------------------ planar quadrotor
@@ -329,13 +384,22 @@ struct EnvQuadrotor {
   static constexpr bool HAS_TERM = true, LINEAR = false;
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
-  using TrigT = Trig<NA>;
+  static constexpr int NJ = 3;
+  using TrigT = Trig<NA, 0, NJ>;
   static constexpr double VDX = 0.8;                                      // W/25
   static constexpr double MASS = 5.0 * (2 * 0.8) * (2 * (400.0 / 30.0 / 100.0));
   static constexpr double INERTIA = MASS * ((2 * 0.8) * (2 * 0.8) + (2 * (400.0 / 30.0 / 100.0)) * (2 * (400.0 / 30.0 / 100.0))) / 12.0;
-  __device__ static void center(const double* m, TrigT& t) { fast_sincos(m[2], &t.s[0], &t.c[0]); }
-  __device__ static void trig(const double* x, int j, const TrigT& c, double& s, double& co) {
-    if (j < 0 || j > 2) { s = c.s[0]; co = c.c[0]; } else { fast_sincos(x[2], &s, &co); }
+  template <class TT> __device__ static void center(const double* m, TT& t) { t.sc(m[2], &t.s[0], &t.c[0]); }
+  template <class TT> __device__ static void offsets(const double* L, double sf, TT& t) {
+    if constexpr (TT::kPM) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t.sc(sf * L[tix(2, j)], &t.ds[j], &t.dc[j]);
+    }
+  }
+  template <class TT> __device__ static void trig(const double* x, int j, const TT& c, double& s, double& co) {
+    if (j < 0 || (j & ~kMinus) > 2) { s = c.s[0]; co = c.c[0]; }
+    else if constexpr (TT::kPM) c.pm(0, j & ~kMinus, j & kMinus, s, co);
+    else c.sc(x[2], &s, &co);
   }
   template <class T>
   __device__ static void dyn_g(const T* xu, const double*, T* y) {
@@ -356,8 +420,8 @@ struct EnvQuadrotor {
   static constexpr int OBS_NL = 0, OBS_JMAX = -1;  // observe / observe_terminal are identities
   __host__ __device__ static constexpr int obs_src(int a) { return a; }
   __host__ __device__ static constexpr int term_src(int a) { return a; }
-  __device__ static void trig_nl(const double*, int, const TrigT&, double*) {}
-  __device__ static void dyn(const double* xu, int j, const TrigT& c, const double*, double* y) {
+  template <class TT> __device__ static void trig_nl(const double*, int, const TT&, double*) {}
+  template <class TT> __device__ static void dyn(const double* xu, int j, const TT& c, const double*, double* y) {
     // kQuad = {h, 1/MASS, -g, VDX, 1/INERTIA, 1/(1 + h/2), 0, 30}
     const double h = kQuad[0];
     double u1 = fmin(fmax(xu[6], kQuad[6]), kQuad[7]), u2 = fmin(fmax(xu[7], kQuad[6]), kQuad[7]);
@@ -373,15 +437,15 @@ struct EnvQuadrotor {
     y[2] = xu[2] + h * w;
     y[3] = vx; y[4] = vy; y[5] = w;
   }
-  __device__ static void obs(const double* xu, int, const TrigT&, double* z) {
+  template <class TT> __device__ static void obs(const double* xu, int, const TT&, double* z) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) z[i] = xu[i];
   }
-  __device__ static void obs_term(const double* x, int, const TrigT&, double* z) {
+  template <class TT> __device__ static void obs_term(const double* x, int, const TT&, double* z) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) z[i] = x[i];
   }
-  __device__ static void measure(const double* x, int j, const TrigT& c, double* yv) {
+  template <class TT> __device__ static void measure(const double* x, int j, const TT& c, double* yv) {
     double s, co;
     trig(x, j, c, s, co);
     yv[0] = x[0] - VDX * co;

@@ -125,4 +125,16 @@ __device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
   *cp = c;
 }
 
+// The same routine behind a (never taken) range test: used by the throughput variants.  The branch makes every evaluation
+// its own basic block, i.e. ptxas cannot interleave the evaluations of a transform -- which is exactly what those variants
+// need: interleaving costs registers (spills at the 128 / 168-register caps: -7 % at 65 536 problems), and with 12-16 warps
+// per SM other warps fill the issue slots anyway.  Arguments beyond 1e12 rad take the library routine.
+__device__ __forceinline__ void seq_sincos(double x, double* sp, double* cp) {
+  if (fabs(x) > 1.0e12) {
+    sincos(x, sp, cp);
+    return;
+  }
+  fast_sincos(x, sp, cp);
+}
+
 }  // namespace i2c

@@ -114,7 +114,8 @@ __device__ __forceinline__ void stage_wait() {
 //   Syy = sum_p w_p y_p y_p^T - my my^T        (packed lower, no noise added)
 //   Dm[j][:] = w * sf * (y_{+j} - y_{-j})      so that  S_xy = L * Dm  (exact rewrite of
 //              sum_p w_p x_p y_p^T - m my^T for the symmetric point set m +- sf L[:,j])
-template <int D, int DY, class Eval>
+// PM: the env maps take the minus point of a column from the angle-addition cache (envs.cuh: Trig, kMinus)
+template <int D, int DY, bool PM = false, class Eval>
 __device__ __forceinline__ void sigma_transform(const double* m, const double* L, double sf, double w0, double wi,
                                                 Eval&& eval, double* my, double* Syy, double* Dm) {
   double sy[DY], syy[TRI(DY)];
@@ -138,7 +139,7 @@ __device__ __forceinline__ void sigma_transform(const double* m, const double* L
       }
     }
     eval(xp, j, yp);
-    eval(xm, j, ym);
+    eval(xm, PM ? (j | kMinus) : j, ym);
 #pragma unroll
     for (int a = 0; a < DY; ++a) {
       sy[a] += yp[a] + ym[a];
@@ -286,15 +287,16 @@ __device__ __forceinline__ bool condition(double* mu, double* Sig, double* Sy, d
 // identity feature is S_xy[i][nl] (both are sum_j D_j[nl] L[i][j]), and sigma-point columns j > OBS_JMAX reproduce
 // the centre value of every nonlinear feature.  Only the nonlinear block is therefore evaluated at the 2 (JMAX + 1)
 // points that differ from the centre.  Same numbers as sigma_transform + cross_cov up to round-off.
-template <class Env, int D, int DY, bool TERM>
+template <class Env, int D, int DY, bool TERM, class TT = typename Env::TrigT>
 __device__ __forceinline__ void structured_obs_moments(const double* m, const double* Sig, const double* L, double sf,
                                                        double wi, double* my, double* Syy, double* Sxy) {
   constexpr int NL = Env::OBS_NL, JM = Env::OBS_JMAX;
   constexpr int NLs = NL > 0 ? NL : 1;
   double mnl[NLs], Snl[TRI(NLs)], Dm[(JM + 1 > 0 ? JM + 1 : 1) * NLs], Cx[D * NLs];
   if constexpr (NL > 0) {
-    typename Env::TrigT ctx;
+    TT ctx;
     Env::center(m, ctx);
+    Env::offsets(L, sf, ctx);
     double yc[NL], sy[NL], syy[TRI(NL)];
     Env::trig_nl(m, -1, ctx, yc);
     constexpr double mult = 2.0 * (D - 1 - JM);
@@ -320,7 +322,7 @@ __device__ __forceinline__ void structured_obs_moments(const double* m, const do
         }
       }
       Env::trig_nl(xp, j, ctx, yp);
-      Env::trig_nl(xm, j, ctx, ym);
+      Env::trig_nl(xm, TT::kPM ? (j | kMinus) : j, ctx, ym);
 #pragma unroll
       for (int a = 0; a < NL; ++a) {
         sy[a] += yp[a] + ym[a];
@@ -467,7 +469,16 @@ struct Worker {
   static constexpr bool BULK = kUseBulk && !META;
   using LY = Lay<Env>;
   static constexpr int DX = LY::DX, DU = LY::DU, N = LY::N, DZ = LY::DZ, DZT = LY::DZT;
-  using TrigT = typename Env::TrigT;
+  // sincos flavour of this variant (envs.cuh: Trig): latency variants branch-free + angle addition, throughput variants
+  // sequenced; the Gauss-Hermite grid evaluates every point afresh (no +- pairs)
+#ifndef I2C_TRIG_LAT
+#define I2C_TRIG_LAT 3
+#endif
+#ifndef I2C_TRIG_THR
+#define I2C_TRIG_THR 2
+#endif
+  static constexpr int TRIG_MODE = GH ? (META ? 1 : 0) : (META ? I2C_TRIG_LAT : I2C_TRIG_THR);
+  using TrigT = Trig<Env::NA, TRIG_MODE, Env::NJ>;
 
   const KParams& p;
   const int tile, lane, b;
@@ -774,7 +785,7 @@ struct Worker {
   __device__ __forceinline__ void xform(const double* m, const double* L, double sf, double w0, double wi, Eval&& eval,
                                         double* my, double* Syy, double* Dm) const {
     if constexpr (GH) grid_transform<D_, DY_>(m, L, p.gh, eval, my, Syy, Dm);
-    else sigma_transform<D_, DY_>(m, L, sf, HOT ? 0.0 : w0, wi, eval, my, Syy, Dm);  // HOT: zero centre weight
+    else sigma_transform<D_, DY_, TrigT::kPM>(m, L, sf, HOT ? 0.0 : w0, wi, eval, my, Syy, Dm);  // HOT: zero centre weight
   }
 
   // ---------------------------------------------------------------------------------- forward cell
@@ -928,10 +939,11 @@ struct Worker {
       if constexpr (LIN) {
         lin_obs_moments<N, DZ, false, true>(mu, Sig, mz, Sz, Sxy);
       } else if (fobs()) {
-        structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Sxy);
+        structured_obs_moments<Env, N, DZ, false, TrigT>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Sxy);
       } else {
         TrigT ctx;
         Env::center(mu, ctx);
+        Env::offsets(L, p.sf_n, ctx);
         xform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                                [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Sxy);
         cross_cov<N, DZ>(L, Sxy);
@@ -967,6 +979,7 @@ struct Worker {
       } else {
         TrigT ctx;
         Env::center(mu, ctx);
+        Env::offsets(L, p.sf_n, ctx);
         xform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                                [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Sxy);
         cross_cov<N, DX>(L, Sxy);
@@ -993,10 +1006,11 @@ struct Worker {
     if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf && !lin()) {
       double mz[DZT], Sz[TRI(DZT)], Sxy[DX * DZT];
       if (fobs()) {
-        structured_obs_moments<Env, DX, DZT, true>(c.m, c.S, c.L, p.sf_x, p.wi_x, mz, Sz, Sxy);
+        structured_obs_moments<Env, DX, DZT, true, TrigT>(c.m, c.S, c.L, p.sf_x, p.wi_x, mz, Sz, Sxy);
       } else {
         TrigT ctx;
         Env::center(c.m, ctx);
+        Env::offsets(c.L, p.sf_x, ctx);
         xform<DX, DZT>(c.m, c.L, p.sf_x, p.w0_x, p.wi_x,
                                  [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Sxy);
         cross_cov<DX, DZT>(c.L, Sxy);
@@ -1139,11 +1153,12 @@ struct Worker {
         lin_obs_moments<N, DZ, false, false>(mu, Sig, mz, Sz, nullptr);
       } else if (fobs()) {
         double Cxy[N * DZ];
-        structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Cxy);
+        structured_obs_moments<Env, N, DZ, false, TrigT>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Cxy);
       } else {
         double Dm[N * DZ];
         TrigT ctx;
         Env::center(mu, ctx);
+        Env::offsets(L, p.sf_n, ctx);
         xform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                                [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
       }
@@ -1163,7 +1178,7 @@ struct Worker {
         if (Env::OBS_NL == 0) {
           lin_obs_moments<N, DZ, false, true>(mu, Sig, mzf, Szf, Sxyf);
         } else {
-          structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mzf, Szf, Sxyf);
+          structured_obs_moments<Env, N, DZ, false, TrigT>(mu, Sig, L, p.sf_n, p.wi_n, mzf, Szf, Sxyf);
         }
         cost_stats<DZ>(p, mzf, Szf, p.z_graph, cm, cv);
       } else {
@@ -1292,6 +1307,7 @@ struct Worker {
       double mz[DZT], Sz[TRI(DZT)], Dm[DX * DZT];
       TrigT ctx;
       Env::center(m3m, ctx);
+      Env::offsets(Lm, p.sf_x, ctx);
       xform<DX, DZT>(m3m, Lm, p.sf_x, p.w0_x, p.wi_x,
                                [&](const double* x, int j, double* y) { Env::obs_term(x, j, ctx, y); }, mz, Sz, Dm);
       double* tm = p.term + ((size_t)tile * LY::E_TERM) * TILE + lane;
@@ -1383,10 +1399,11 @@ struct Worker {
     {
       double mz[DZ], Sz[TRI(DZ)], Dm[N * DZ], z[DZ];
       if (fobs()) {
-        structured_obs_moments<Env, N, DZ, false>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Dm);
+        structured_obs_moments<Env, N, DZ, false, TrigT>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Dm);
       } else {
         TrigT ctx;
         Env::center(mu, ctx);
+        Env::offsets(L, p.sf_n, ctx);
         xform<N, DZ>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                                [&](const double* x, int j, double* y) { Env::obs(x, j, ctx, y); }, mz, Sz, Dm);
       }
@@ -1408,6 +1425,7 @@ struct Worker {
       double Dm[N * DX];
       TrigT ctx;
       Env::center(mu, ctx);
+      Env::offsets(L, p.sf_n, ctx);
       xform<N, DX>(mu, L, p.sf_n, p.w0_n, p.wi_n,
                              [&](const double* x, int j, double* y) { Env::dyn(x, j, ctx, par, y); }, c.m, c.S, Dm);
 #pragma unroll
@@ -1783,8 +1801,9 @@ struct Worker {
   // ---------------------------------------------------------------------------------- the EM loop
   // TEAM = false: one warp does everything for its tile.  TEAM = true (latency regime, one block of W warps per
   // tile): warp 0 runs the sequential recursions (forward sweep, RTS heads, propagate); the per-cell work of the
-  // backward pass that does not feed the recursion (backward_tail) is spread over all W warps, cell t -> warp
-  // (T-1-t) mod W, and the M-step statistics are reduced through shared memory in a fixed order.
+  // backward pass that does not feed the recursion (backward_tail) runs on the W-1 helper warps WHILE warp 0 walks the
+  // RTS heads (static cell -> warp map, progress counter in shared memory), and the M-step statistics are reduced through
+  // shared memory in a fixed order.
   template <bool TEAM>
   __device__ void run_impl(const int w, const int W, double* red) {
     const bool main_warp = !TEAM || w == 0;
@@ -1814,6 +1833,20 @@ struct Worker {
       }
       if (p.phases & I2C_PH_BACKWARD) {
         double m3m[DX], S3m[TRI(DX)];
+        // TEAM: the tails run CONCURRENTLY with the RTS heads.  Warp 0 publishes the number of finished heads in shared
+        // memory (after a block-scope fence: the tails read the posterior from the post records); helper warp w takes the
+        // cells i = T-1-t with i mod (W-1) = w-1 and waits for head i; the last n_main cells are kept for warp 0, which
+        // joins once its heads are done.  The assignment is static, so the per-warp partial sums -- and with them
+        // alpha -- are bit-reproducible.  (Before: all heads, a barrier, then all tails: the tails were 11 % of an iteration.)
+        volatile int* prog = TEAM ? reinterpret_cast<volatile int*>(red + (size_t)7 * W * TILE) : nullptr;
+        int n_main = 0;
+        if constexpr (TEAM) {
+          // tail : head cost is about 7 : 1; balance warp 0's share so that it and the helpers finish together
+          const int nm = (T * (7 - (W - 1))) / (7 * W);
+          n_main = nm > 0 ? nm : 0;
+          if (main_warp && lane == 0) *prog = 0;
+          __syncthreads();  // forward sweep done; progress counter reset
+        }
         if (main_warp) {
           if (!(p.phases & I2C_PH_FORWARD)) {
             // resume from the stored filtered message of the last cell
@@ -1850,12 +1883,18 @@ struct Worker {
                 backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
                 if (t - DEPTH >= 0) rec_issue<LY::E_FILT>(cur, rec(p.filt, t - DEPTH, LY::E_FILT), t % DEPTH);
                 stage_commit();
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) *prog = T - t;
               }
               stage_wait<0>();
             } else {
               for (int t = T - 1; t >= 0; --t) {
                 double mu[N], Sig[TRI(N)];
                 backward_head(it, t, aux, rec(p.filt, t, LY::E_FILT), m3m, S3m, mu, Sig);
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) *prog = T - t;
               }
             }
           } else {
@@ -1869,15 +1908,20 @@ struct Worker {
         }
         if (p.cov_ctrl) temp += p.dtemp;
         if constexpr (TEAM) {
-          __threadfence_block();
-          __syncthreads();  // every posterior (mu, Sigma) of this sweep is in the post records
-          for (int t = T - 1 - w; t >= 0; t -= W) {
+          // cells [0, T - n_main) (in head order i = T-1-t) belong to the helpers, the rest to warp 0
+          const int i0 = main_warp ? T - n_main : w - 1, di = main_warp ? 1 : W - 1, i1 = main_warp ? T : T - n_main;
+          for (int i = i0; i < i1; i += di) {
+            if (!main_warp) {
+              while (*prog <= i) __nanosleep(64);
+              __threadfence_block();
+            }
+            const int t = T - 1 - i;
             const double* po = rec(post, t, LY::E_POST);
             double mu[N], Sig[TRI(N)];
 #pragma unroll
-            for (int i = 0; i < N; ++i) mu[i] = __ldcg(po + (LY::P_MU + i) * TILE);
+            for (int k = 0; k < N; ++k) mu[k] = __ldcg(po + (LY::P_MU + k) * TILE);
 #pragma unroll
-            for (int i = 0; i < TRI(N); ++i) Sig[i] = __ldcg(po + (LY::P_SIG + i) * TILE);
+            for (int k = 0; k < TRI(N); ++k) Sig[k] = __ldcg(po + (LY::P_SIG + k) * TILE);
             backward_tail(it, t, aux, nullptr, mu, Sig, st);
           }
           // fixed-order reduction of the per-warp statistics: red[k][w][lane]
@@ -2026,7 +2070,7 @@ __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_c
 
 template <class Env, int W, bool HOT>
 static int launch_em_team_v(const KParams& p, cudaStream_t s) {
-  const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars) * sizeof(double);
+  const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars + 2) * sizeof(double);  // + progress counter
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(em_team_kernel<Env, W, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
