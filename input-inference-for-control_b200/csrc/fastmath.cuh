@@ -86,6 +86,27 @@ __device__ __forceinline__ double fast_exp_neg(double x) {
   return __hiloint2double(__double2hiint(pe) + (k << 20), __double2loint(pe));
 }
 
+// Latency-regime flavour of the same function: Estrin evaluation (dependency depth 7 instead of 13 fused multiply-adds) and
+// no clamp on the critical path -- fp64 max() is a four-instruction sequence on this machine; arguments below -708 are
+// flushed to 0 by a select on the final result, whose compare runs beside the chain.  Same polynomial: results agree with
+// fast_exp_neg to <= 1 ulp (different summation order).
+__device__ __forceinline__ double fast_exp_neg_lat(double x) {
+  const double km = fma(x, kFm[23], kFm[26]);
+  const double kd = km - kFm[26];
+  double r = fma(-kd, kFm[24], x);
+  r = fma(-kd, kFm[25], r);
+  const double r2 = r * r;
+  const double a0 = fma(kFm[29], r, kFm[28]), a1 = fma(kFm[31], r, kFm[30]), a2 = fma(kFm[33], r, kFm[32]);
+  const double a3 = fma(kFm[35], r, kFm[34]), a4 = fma(kFm[37], r, kFm[36]), a5 = fma(kFm[39], r, kFm[38]);
+  const double r4 = r2 * r2;
+  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+  const double t = fma(fma(b2, r4, b1), r4, b0);
+  const double pe = fma(r2, t, r) + kFm[18];
+  const int k = __double2loint(km);
+  const double v = __hiloint2double(__double2hiint(pe) + (k << 20), __double2loint(pe));
+  return x < kFm[27] ? 0.0 : v;
+}
+
 // sin and cos, branch-free for every finite argument: round-to-nearest multiple of pi/2 by the magic-number trick (the
 // quadrant is the low word of the biased sum), then a three-term Cody-Waite reduction with FULL-precision constants.  With
 // FMA the first step r1 = x - k P1 is exact for |k| < 2^51 (x and k P1 are multiples of 2^-52 and |r1| < 1), so the

@@ -51,7 +51,10 @@ struct Lay {
   static constexpr bool STAGED = E_FILT <= 64;
   // team kernel: depth of the filtered-record stream of the RTS head loop, and the staging area it needs
   static constexpr int TEAM_DEPTH = 6;
-  static constexpr int E_TEAM_STAGE = !STAGED ? 0 : ((TEAM_DEPTH * E_FILT > 2 * E_STAGE_TOT) ? TEAM_DEPTH * E_FILT : 2 * E_STAGE_TOT);
+  // team kernel, HOT: producer / consumer ring of RING slots (E_STAGE doubles per lane each) filled by a copy warp
+  static constexpr int RING = E_FILT > 32 ? 4 : 8;
+  static constexpr int E_TEAM_A = (TEAM_DEPTH * E_FILT > 2 * E_STAGE_TOT) ? TEAM_DEPTH * E_FILT : 2 * E_STAGE_TOT;
+  static constexpr int E_TEAM_STAGE = !STAGED ? 0 : (E_TEAM_A > RING * E_STAGE ? E_TEAM_A : RING * E_STAGE);
 
 };
 
@@ -83,6 +86,9 @@ __device__ __forceinline__ void bulk_load(double* sdst, const double* gsrc, unsi
                "l"(gsrc), "r"(bytes), "r"(b)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
   asm volatile(
@@ -97,12 +103,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+// the same on precomputed 32-bit shared addresses (no generic -> shared conversion inside the cell loops: it costs an
+// S2R SR_CgaCtaId + address arithmetic per use), plus the non-blocking probe
+__device__ __forceinline__ bool mbar_test_s(unsigned bar_s, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar_s), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_s(unsigned bar_s, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar_s),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(unsigned bar_s) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
+}
 #ifdef I2C_NO_BULK
 constexpr bool kUseBulk = false;
 #else
 constexpr bool kUseBulk = true;
 #endif
-constexpr int kNumBars = 8;  // mbarriers per warp (>= deepest record pipeline)
+constexpr int kNumBars = 16;  // mbarriers per warp (>= deepest record pipeline; team ring: RING full + RING empty)
 template <int N>
 __device__ __forceinline__ void stage_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -466,7 +503,9 @@ struct Carry {
 // boundaries per forward cell that stop ptxas from overlapping the independent dependency chains across them.
 template <class Env, bool META, bool LIN = false, bool GH = false, bool HOT = false>
 struct Worker {
-  static constexpr bool BULK = kUseBulk && !META;
+  // HOT moves the records with bulk copies as well: targets / flags come from a shared-memory table built once per launch
+  // (team kernel), so the per-thread LDGSTS stream (17 + 20 instructions and ~25 of address arithmetic per cell) is gone
+  static constexpr bool BULK = kUseBulk && (!META || HOT);
   using LY = Lay<Env>;
   static constexpr int DX = LY::DX, DU = LY::DU, N = LY::N, DZ = LY::DZ, DZT = LY::DZT;
   // sincos flavour of this variant (envs.cuh: Trig): latency variants branch-free + angle addition, throughput variants
@@ -491,9 +530,12 @@ struct Worker {
   double* stage;  // this warp's double buffer: [2][E_STAGE][32], already offset by lane
   uint64_t* bars; // this warp's mbarriers (bulk-copy completion), kNumBars of them
   unsigned bar_phase;  // one parity bit per mbarrier
+  const double* ztab;  // HOT: [T][DZ] cell targets in shared memory (logical cell order)
+  const int2* ftab;    // HOT: [T] {flags, index}
 
   __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_, uint64_t* bars_)
-      : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_), bars(bars_), bar_phase(0) {
+      : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_), bars(bars_), bar_phase(0), ring_q(0), ring_ready(false) {
+    bars_s = (unsigned)__cvta_generic_to_shared(bars_);
     status = I2C_OK;
     info = 0;
     prior = p.prior;
@@ -518,7 +560,7 @@ struct Worker {
     }
   }
   __device__ __forceinline__ bool fobs() const { return HOT || p.fast_obs; }
-  __device__ __forceinline__ bool smeta() const { return HOT || p.stage_meta; }
+  __device__ __forceinline__ bool smeta() const { return !HOT && p.stage_meta; }
   __device__ __forceinline__ bool zpp() const { return !HOT && p.z_per_problem; }
   __device__ __forceinline__ void load_z(int t, double* z) const {
     if (zpp()) {
@@ -543,7 +585,10 @@ struct Worker {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s0 + LY::S_META * TILE * 8 + 4), "l"(p.cell_index + sl) : "memory");
   }
   __device__ __forceinline__ void staged_z(const double* sbuf, int t, double* z) const {
-    if (LY::STAGED && META && smeta()) {
+    if constexpr (HOT) {
+#pragma unroll
+      for (int a = 0; a < DZ; ++a) z[a] = ztab[t * DZ + a];
+    } else if (LY::STAGED && META && smeta()) {
 #pragma unroll
       for (int a = 0; a < DZ; ++a) z[a] = sbuf[(LY::S_Z + a) * TILE];
     } else {
@@ -552,7 +597,11 @@ struct Worker {
   }
   __device__ __forceinline__ int staged_flags(const double* sbuf, int t, bool flipped) const {
     int flags, index;
-    if (LY::STAGED && META && smeta()) {
+    if constexpr (HOT) {
+      const int2 m = ftab[t];
+      flags = m.x;
+      index = m.y;
+    } else if (LY::STAGED && META && smeta()) {
       const int2 m = *reinterpret_cast<const int2*>(sbuf + LY::S_META * TILE);
       flags = m.x;
       index = m.y;
@@ -562,6 +611,47 @@ struct Worker {
     }
     if (flipped && p.tau > 0 && index <= p.tau) flags &= ~I2C_CELL_INDEPENDENT;
     return flags;
+  }
+  // ---- record ring of the team kernel (HOT): the copy warp (lane 0 of warp W-1) streams the records of the sequential
+  // sweeps with TMA bulk copies; warp 0 only waits on the slot's "full" mbarrier and arrives on its "empty" one.  Warp 0
+  // therefore issues no copy, no address arithmetic and no commit / wait bookkeeping for its input stream.
+  static constexpr int RING = LY::RING, RSTRIDE = LY::E_STAGE;
+  unsigned ring_q;  // cells produced / consumed so far: slot = q % RING, phase parity = (q / RING) & 1
+  unsigned bars_s;  // 32-bit shared address of bars[0]
+  bool ring_ready;  // early probe of the slot the next ring_acquire() will take (hides the mbarrier round trip)
+  __device__ __forceinline__ void ring_init() {  // one thread, before the block-wide barrier that precedes any use
+#pragma unroll
+    for (int i = 0; i < RING; ++i) {
+      mbar_init(bars + i, 1);            // full: the producer's arrive.expect_tx
+      mbar_init(bars + RING + i, TILE);  // empty: every lane of warp 0 arrives after its last read of the slot
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __device__ __forceinline__ const double* ring_acquire() {
+    const unsigned s = ring_q % RING;
+    if (!ring_ready) mbar_wait_s(bars_s + 8u * s, (ring_q / RING) & 1u);
+    // probe the NEXT cell's slot now: an mbarrier query takes ~100 cycles to come back, and the copy warp runs several
+    // cells ahead, so the answer (consumed by the next acquire) is almost always "ready"
+    const unsigned q1 = ring_q + 1;
+    ring_ready = mbar_test_s(bars_s + 8u * (q1 % RING), (q1 / RING) & 1u);
+    return stage + s * (RSTRIDE * TILE);
+  }
+  __device__ __forceinline__ void ring_release() {
+    mbar_arrive_s(bars_s + 8u * (RING + ring_q % RING));
+    ++ring_q;
+  }
+  __device__ __forceinline__ void ring_produce(double* base_g, int Erec, int Ecopy, int t) {
+    const unsigned s = ring_q % RING;
+    mbar_wait(bars + RING + s, ((ring_q / RING) & 1u) ^ 1u);
+    bulk_load(stage + s * (RSTRIDE * TILE), rec(base_g, t, Erec), Ecopy * TILE * 8, bars + s);
+    ++ring_q;
+  }
+  // HOT: true when every cell but the last of this sweep is a feedback, non-terminal cell (flags table in shared memory)
+  __device__ __forceinline__ bool sweep_is_plain(bool flipped) const {
+    bool bad = false;
+    for (int t = lane; t < p.T - 1; t += TILE)
+      bad = bad || (staged_flags(nullptr, t, flipped) & (I2C_CELL_INDEPENDENT | I2C_CELL_TERMINAL)) != 0;
+    return !__any_sync(0xffffffffu, bad);
   }
   // init of this warp's mbarriers (call once, all lanes)
   __device__ __forceinline__ void pipe_init() {
@@ -606,8 +696,10 @@ struct Worker {
         rec_issue<E>(nxt, rec(base_g, tn, Erec), tn & 1);
         if (META && smeta()) stage_meta(nxt, tn);
       }
-      stage_commit();
-      stage_wait<1>();
+      if constexpr (!BULK) {
+        stage_commit();
+        stage_wait<1>();
+      }
       rec_wait(t & 1);
       return cur;
     } else {
@@ -621,11 +713,11 @@ struct Worker {
       double* nxt = stage + (t & 1) * (LY::E_STAGE_TOT * TILE);
       rec_issue<E>(nxt, rec(base_g, t, Erec), t & 1);
       if (META && smeta()) stage_meta(nxt, t);
-      stage_commit();
+      if constexpr (!BULK) stage_commit();
     }
   }
   __device__ __forceinline__ void stream_end() {
-    if constexpr (LY::STAGED) stage_wait<0>();
+    if constexpr (LY::STAGED && !BULK) stage_wait<0>();
   }
   __device__ __forceinline__ void load_zterm(double* zt) const {
     if (p.z_term_pp) {
@@ -649,7 +741,8 @@ struct Worker {
 #ifdef I2C_LAT_LIBEXP
     if constexpr (META) return exp(x);
 #endif
-    return fast_exp_neg(x);
+    if constexpr (META) return fast_exp_neg_lat(x);
+    else return fast_exp_neg(x);
   }
   // exp(-1/2 d^T C^-1 d): the pdf ratio w/Z of i2c.py:369-374 (scipy multivariate_normal)
   __device__ __forceinline__ bool pdf_ratio(const double* C_in, const double* d_in, double& rho) {
@@ -791,6 +884,9 @@ struct Worker {
   // ---------------------------------------------------------------------------------- forward cell
   // I2cCell._forward_msgs_quadrature (i2c.py:350-447); with p.linearize (linear envs) the same cell with exact
   // linear moments = _forward_msgs_linearize (i2c.py:244-348; the terminal update then happens in the backward pass).  c: (mu_x0_f, sig_x0_f) in, (mu_x3_f, sig_x3_f) out.
+  // PLAIN: the cell is known to be a feedback (not independent), non-terminal cell -- the sweep checked the flags of the
+  // whole horizon beforehand (sweep_is_plain) -- so neither branch exists in the loop body.
+  template <bool PLAIN = false>
   __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, const double* pr,
                                                Carry<DX>& c, LogAcc& ent_x) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
@@ -802,7 +898,7 @@ struct Worker {
       for (int r = 0; r < DU; ++r)
 #pragma unroll
         for (int q = 0; q <= r; ++q) Suu[tix(r, q)] = pr[(LY::P_SIG + tix(DX + r, DX + q)) * TILE];
-      const bool indep = flags & I2C_CELL_INDEPENDENT;
+      const bool indep = PLAIN ? false : (flags & I2C_CELL_INDEPENDENT);
       if (!indep) {
         // feedback prior (i2c.py:361-387): K <- K * N(mu_x0_f; mu_prev, C)/N(mu_prev; mu_prev, C), C = Sig_xx + sig_x0_f
         double mx[DX], Sxx[TRI(DX)], Sux[DU * DX], C[TRI(DX)], d[DX];
@@ -1003,7 +1099,7 @@ struct Worker {
       }
     }
     // ---- terminal cost update on the outgoing message (i2c.py:430-443)
-    if (Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf && !lin()) {
+    if (!PLAIN && Env::HAS_TERM && (flags & I2C_CELL_TERMINAL) && p.has_qf && !lin()) {
       double mz[DZT], Sz[TRI(DZT)], Sxy[DX * DZT];
       if (fobs()) {
         structured_obs_moments<Env, DX, DZT, true, TrigT>(c.m, c.S, c.L, p.sf_x, p.wi_x, mz, Sz, Sxy);
@@ -1807,7 +1903,11 @@ struct Worker {
   template <bool TEAM>
   __device__ void run_impl(const int w, const int W, double* red) {
     const bool main_warp = !TEAM || w == 0;
-    if (main_warp) pipe_init();
+    // PROD: the last warp of the team is the copy warp of the record ring (see ring_init); H = warps that run tails
+    constexpr bool PROD = TEAM && HOT && LY::STAGED;
+    const bool copy_warp = PROD && w == W - 1;
+    const int H = PROD ? W - 2 : W - 1;
+    if (main_warp && !PROD) pipe_init();
     const double HALF_LOG_2PIE = 1.4189385332046727;  // 0.5 * log(2 pi e)
     double alpha = p.alpha[b];
     const bool aux = !HOT && (p.phases & I2C_PH_STORE_AUX);
@@ -1824,25 +1924,53 @@ struct Worker {
       double tr_term = 0.0;
       if (main_warp && (p.phases & I2C_PH_FORWARD)) {
         if (!load_x0(c)) fail(I2C_FAIL_CHOL_PRIOR, it, 0);
-        stream_begin<LY::E_STAGE_POST>(prior, LY::E_POST, 0);
-        for (int t = 0; t < T; ++t) {
-          const double* cur = stream<LY::E_STAGE_POST>(prior, LY::E_POST, t, t + 1, t + 1 < T);
-          forward_cell(it, t, staged_flags(cur, t, flipped), alpha, aux, cur, c, ent_x);
+        if constexpr (PROD) {
+          int t = 0;
+          if (sweep_is_plain(flipped)) {
+            for (; t < T - 1; ++t) {
+              const double* cur = ring_acquire();
+              forward_cell<true>(it, t, 0, alpha, aux, cur, c, ent_x);
+              ring_release();
+            }
+          }
+          for (; t < T; ++t) {
+            const double* cur = ring_acquire();
+            forward_cell(it, t, staged_flags(cur, t, flipped), alpha, aux, cur, c, ent_x);
+            ring_release();
+          }
+          // the filtered records written above are read back by the copy warp's bulk copies after the barrier below
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
+        } else {
+          stream_begin<LY::E_STAGE_POST>(prior, LY::E_POST, 0);
+          for (int t = 0; t < T; ++t) {
+            const double* cur = stream<LY::E_STAGE_POST>(prior, LY::E_POST, t, t + 1, t + 1 < T);
+            forward_cell(it, t, staged_flags(cur, t, flipped), alpha, aux, cur, c, ent_x);
+          }
+          stream_end();
         }
-        stream_end();
+      }
+      if (copy_warp && (p.phases & I2C_PH_FORWARD)) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          for (int t = 0; t < T; ++t) ring_produce(prior, LY::E_POST, LY::E_STAGE_POST, t);
+        }
+        __syncwarp();
       }
       if (p.phases & I2C_PH_BACKWARD) {
         double m3m[DX], S3m[TRI(DX)];
         // TEAM: the tails run CONCURRENTLY with the RTS heads.  Warp 0 publishes the number of finished heads in shared
         // memory (after a block-scope fence: the tails read the posterior from the post records); helper warp w takes the
-        // cells i = T-1-t with i mod (W-1) = w-1 and waits for head i; the last n_main cells are kept for warp 0, which
+        // cells i = T-1-t with i mod H = w-1 and waits for head i; the last n_main cells are kept for warp 0, which
         // joins once its heads are done.  The assignment is static, so the per-warp partial sums -- and with them
         // alpha -- are bit-reproducible.  (Before: all heads, a barrier, then all tails: the tails were 11 % of an iteration.)
         volatile int* prog = TEAM ? reinterpret_cast<volatile int*>(red + (size_t)7 * W * TILE) : nullptr;
         int n_main = 0;
         if constexpr (TEAM) {
-          // tail : head cost is about 7 : 1; balance warp 0's share so that it and the helpers finish together
-          const int nm = (T * (7 - (W - 1))) / (7 * W);
+          // tail : head cost is about r : 1 (7 with the per-thread record stream, 10 with the copy warp); balance warp 0's
+          // share so that it and the H helpers finish together
+          const int r = PROD ? 10 : 7;
+          const int nm = (T * (r - H)) / (r * (H + 1));
           n_main = nm > 0 ? nm : 0;
           if (main_warp && lane == 0) *prog = 0;
           __syncthreads();  // forward sweep done; progress counter reset
@@ -1861,7 +1989,17 @@ struct Worker {
             chol_rows<DX>(c.L, c.invd);
           }
           backward_terminal(it, T - 1, temp, cell_alpha(T - 1, p.cell_flags[slot(T - 1)], alpha), c, m3m, S3m, tr_term);
-          if constexpr (TEAM) {
+          if constexpr (PROD) {
+            for (int t = T - 1; t >= 0; --t) {
+              const double* cur = ring_acquire();
+              double mu[N], Sig[TRI(N)];
+              backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
+              ring_release();
+              asm volatile("fence.acq_rel.cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) *prog = T - t;
+            }
+          } else if constexpr (TEAM) {
             // RTS heads only: a head is a few hundred cycles, so the filtered records are streamed TEAM_DEPTH cells
             // ahead (a one-cell double buffer would expose the DRAM latency of every record)
             if constexpr (LY::STAGED) {
@@ -1873,21 +2011,21 @@ struct Worker {
                 const int tt = T - 1 - k;
                 if (tt >= 0)
                   rec_issue<LY::E_FILT>(stage + (tt % DEPTH) * (LY::E_FILT * TILE), rec(p.filt, tt, LY::E_FILT), tt % DEPTH);
-                stage_commit();
+                if constexpr (!BULK) stage_commit();
               }
               for (int t = T - 1; t >= 0; --t) {
-                stage_wait<DEPTH - 1>();
+                if constexpr (!BULK) stage_wait<DEPTH - 1>();
                 rec_wait(t % DEPTH);
                 double* cur = stage + (t % DEPTH) * (LY::E_FILT * TILE);
                 double mu[N], Sig[TRI(N)];
                 backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
                 if (t - DEPTH >= 0) rec_issue<LY::E_FILT>(cur, rec(p.filt, t - DEPTH, LY::E_FILT), t % DEPTH);
-                stage_commit();
+                if constexpr (!BULK) stage_commit();
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) *prog = T - t;
               }
-              stage_wait<0>();
+              if constexpr (!BULK) stage_wait<0>();
             } else {
               for (int t = T - 1; t >= 0; --t) {
                 double mu[N], Sig[TRI(N)];
@@ -1906,14 +2044,22 @@ struct Worker {
             stream_end();
           }
         }
+        if (copy_warp) {
+          if (lane == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            for (int t = T - 1; t >= 0; --t) ring_produce(p.filt, LY::E_FILT, LY::E_FILT, t);
+          }
+          __syncwarp();
+        }
         if (p.cov_ctrl) temp += p.dtemp;
         if constexpr (TEAM) {
           // cells [0, T - n_main) (in head order i = T-1-t) belong to the helpers, the rest to warp 0
-          const int i0 = main_warp ? T - n_main : w - 1, di = main_warp ? 1 : W - 1, i1 = main_warp ? T : T - n_main;
+          const int i0 = main_warp ? T - n_main : w - 1, di = main_warp ? 1 : H;
+          const int i1 = main_warp ? T : (copy_warp ? 0 : T - n_main);
           for (int i = i0; i < i1; i += di) {
             if (!main_warp) {
               while (*prog <= i) __nanosleep(64);
-              __threadfence_block();
+              asm volatile("fence.acq_rel.cta;" ::: "memory");
             }
             const int t = T - 1 - i;
             const double* po = rec(post, t, LY::E_POST);
@@ -1923,6 +2069,10 @@ struct Worker {
 #pragma unroll
             for (int k = 0; k < TRI(N); ++k) Sig[k] = __ldcg(po + (LY::P_SIG + k) * TILE);
             backward_tail(it, t, aux, nullptr, mu, Sig, st);
+          }
+          if constexpr (BULK) {  // K, k, sigK written here are read back by warp 0's bulk copies in the next forward sweep
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
           }
           // fixed-order reduction of the per-warp statistics: red[k][w][lane]
           double* r = red + (size_t)w * TILE + lane;
@@ -1960,12 +2110,20 @@ struct Worker {
       if (main_warp && (p.phases & I2C_PH_PROPAGATE)) {
         Carry<DX> cp;
         if (!load_x0(cp)) fail(I2C_FAIL_CHOL_PROPAGATE, it, 0);
-        stream_begin<LY::E_STAGE_POST>(latest, LY::E_POST, 0);
-        for (int t = 0; t < T; ++t) {
-          const double* cur = stream<LY::E_STAGE_POST>(latest, LY::E_POST, t, t + 1, t + 1 < T);
-          propagate_cell(it, t, staged_flags(cur, t, flipped), aux, cur, cp, ps);
+        if constexpr (PROD) {
+          for (int t = 0; t < T; ++t) {
+            const double* cur = ring_acquire();
+            propagate_cell(it, t, staged_flags(cur, t, flipped), aux, cur, cp, ps);
+            ring_release();
+          }
+        } else {
+          stream_begin<LY::E_STAGE_POST>(latest, LY::E_POST, 0);
+          for (int t = 0; t < T; ++t) {
+            const double* cur = stream<LY::E_STAGE_POST>(latest, LY::E_POST, t, t + 1, t + 1 < T);
+            propagate_cell(it, t, staged_flags(cur, t, flipped), aux, cur, cp, ps);
+          }
+          stream_end();
         }
-        stream_end();
         if (p.cov_ctrl) {
           // KL(N(mu_x3_pf, sig_x3_pf) || N(mu_xT, sig_xT)) of the last cell (i2c.py:1012-1019, 1223-1229)
           double A[TRI(DX)], ia[DX], d[DX];
@@ -1991,6 +2149,13 @@ struct Worker {
           }
           metric(I2C_M_KL_TERM, it, 0.5 * (p.sxt_logdet - 2.0 * ld1 + tr + dist - (double)DX));
         }
+      }
+      if (copy_warp && (p.phases & I2C_PH_PROPAGATE)) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          for (int t = 0; t < T; ++t) ring_produce(latest, LY::E_POST, LY::E_STAGE_POST, t);
+        }
+        __syncwarp();
       }
       if (main_warp && (p.phases & I2C_PH_RICCATI)) riccati_sweep(alpha);
       if (main_warp && (p.phases & I2C_PH_MSTEP)) {
@@ -2065,12 +2230,25 @@ __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_c
   double* red = stage_smem + Lay<Env>::E_TEAM_STAGE * TILE + kNumBars;
   Worker<Env, true, false, false, HOT> wk(pin, blockIdx.x, lane, stage_smem + lane,
                        reinterpret_cast<uint64_t*>(stage_smem + Lay<Env>::E_TEAM_STAGE * TILE));
+  if constexpr (HOT) {
+    if (Lay<Env>::STAGED && threadIdx.x == 0) wk.ring_init();
+    // cell targets and {flags, index} of the whole horizon, in logical cell order (the ring offset is fixed during a launch)
+    constexpr int DZ = Env::DZ;
+    double* ztab = red + (size_t)7 * W * TILE + 2;
+    int2* ftab = reinterpret_cast<int2*>(ztab + (size_t)pin.T * DZ);
+    for (int i = threadIdx.x; i < pin.T * DZ; i += W * TILE) ztab[i] = pin.z_cell[wk.slot(i / DZ) * DZ + i % DZ];
+    for (int t = threadIdx.x; t < pin.T; t += W * TILE) ftab[t] = make_int2(pin.cell_flags[wk.slot(t)], pin.cell_index[wk.slot(t)]);
+    __syncthreads();
+    wk.ztab = ztab;
+    wk.ftab = ftab;
+  }
   wk.template run_impl<true>(w, W, red);
 }
 
 template <class Env, int W, bool HOT>
 static int launch_em_team_v(const KParams& p, cudaStream_t s) {
-  const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars + 2) * sizeof(double);  // + progress counter
+  // staging + mbarriers + reduction + progress counter (+ HOT: target / flag table of the horizon)
+  const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars + 2 + (HOT ? (size_t)p.T * (Env::DZ + 1) : 0)) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(em_team_kernel<Env, W, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
