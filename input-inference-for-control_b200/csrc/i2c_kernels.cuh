@@ -324,16 +324,23 @@ __device__ __forceinline__ bool condition(double* mu, double* Sig, double* Sy, d
 // identity feature is S_xy[i][nl] (both are sum_j D_j[nl] L[i][j]), and sigma-point columns j > OBS_JMAX reproduce
 // the centre value of every nonlinear feature.  Only the nonlinear block is therefore evaluated at the 2 (JMAX + 1)
 // points that differ from the centre.  Same numbers as sigma_transform + cross_cov up to round-off.
+// pre: sin / cos of the centre and of the column offsets evaluated beforehand (they depend on the state block of (m, L)
+// only; the plain forward loop computes them at the END of the previous cell, beside that cell's off-chain work)
 template <class Env, int D, int DY, bool TERM, class TT = typename Env::TrigT>
 __device__ __forceinline__ void structured_obs_moments(const double* m, const double* Sig, const double* L, double sf,
-                                                       double wi, double* my, double* Syy, double* Sxy) {
+                                                       double wi, double* my, double* Syy, double* Sxy,
+                                                       const TT* pre = nullptr) {
   constexpr int NL = Env::OBS_NL, JM = Env::OBS_JMAX;
   constexpr int NLs = NL > 0 ? NL : 1;
   double mnl[NLs], Snl[TRI(NLs)], Dm[(JM + 1 > 0 ? JM + 1 : 1) * NLs], Cx[D * NLs];
   if constexpr (NL > 0) {
     TT ctx;
-    Env::center(m, ctx);
-    Env::offsets(L, sf, ctx);
+    if (pre) {
+      ctx = *pre;
+    } else {
+      Env::center(m, ctx);
+      Env::offsets(L, sf, ctx);
+    }
     double yc[NL], sy[NL], syy[TRI(NL)];
     Env::trig_nl(m, -1, ctx, yc);
     constexpr double mult = 2.0 * (D - 1 - JM);
@@ -886,9 +893,12 @@ struct Worker {
   // linear moments = _forward_msgs_linearize (i2c.py:244-348; the terminal update then happens in the backward pass).  c: (mu_x0_f, sig_x0_f) in, (mu_x3_f, sig_x3_f) out.
   // PLAIN: the cell is known to be a feedback (not independent), non-terminal cell -- the sweep checked the flags of the
   // whole horizon beforehand (sweep_is_plain) -- so neither branch exists in the loop body.
+  // With PLAIN the ring slot is released as soon as the record is in registers (an mbarrier arrive has release semantics:
+  // placed after the cell's stores it waited ~90 cycles for them), and the trigonometric context of the cost-feature
+  // transform comes in through octx and is re-evaluated for the NEXT cell at the end, from the outgoing message.
   template <bool PLAIN = false>
   __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, const double* pr,
-                                               Carry<DX>& c, LogAcc& ent_x) {
+                                               Carry<DX>& c, LogAcc& ent_x, TrigT* octx = nullptr) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
     {
       double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];
@@ -913,6 +923,7 @@ struct Worker {
             Sux[r * DX + j] = pr[(LY::P_SIG + tix(DX + r, j)) * TILE];
             Kt[r * DX + j] = pr[(LY::P_K + r * DX + j) * TILE];
           }
+        if constexpr (PLAIN) ring_release();  // every field of the staged record has been read
 #pragma unroll
         for (int i = 0; i < TRI(DX); ++i) C[i] = Sxx[i] + c.S[i];
 #pragma unroll
@@ -1035,7 +1046,7 @@ struct Worker {
       if constexpr (LIN) {
         lin_obs_moments<N, DZ, false, true>(mu, Sig, mz, Sz, Sxy);
       } else if (fobs()) {
-        structured_obs_moments<Env, N, DZ, false, TrigT>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Sxy);
+        structured_obs_moments<Env, N, DZ, false, TrigT>(mu, Sig, L, p.sf_n, p.wi_n, mz, Sz, Sxy, PLAIN ? octx : nullptr);
       } else {
         TrigT ctx;
         Env::center(mu, ctx);
@@ -1130,6 +1141,13 @@ struct Worker {
     }
 #pragma unroll
     for (int i = 0; i < TRI(DX); ++i) fr[(LY::F_SIG3 + i) * TILE] = c.S[i];
+    if constexpr (PLAIN && Env::OBS_NL > 0) obs_trig(c, *octx);
+  }
+  // trigonometric context of the cost-feature transform of the cell that receives message c: the angles are state
+  // components, and the state block of the joint's mean / factor is the message itself
+  __device__ __forceinline__ void obs_trig(const Carry<DX>& c, TrigT& o) const {
+    Env::center(c.m, o);
+    Env::offsets(c.L, p.sf_n, o);
   }
 
   // ---------------------------------------------------------------------------------- backward cell
@@ -1141,17 +1159,20 @@ struct Worker {
   };
   // RTS recursion of one cell (i2c.py:578-592): posterior joint from the filtered record and the next cell's
   // smoothed state; stores mu_xu0_m / sig_xu0_m and hands (mu_x0_m, sig_x0_m) to the previous cell.
+  // FS = element stride of the filtered record at fr: TILE for the tiled layouts in shared / global memory, 1 for a copy
+  // held in registers
+  template <int FS = TILE>
   __device__ __forceinline__ void backward_head(int it, int t, bool aux, const double* fr, double* m3m, double* S3m,
                                                 double* mu, double* Sig) {
     double J[N * DX];
     {
       double dm[DX], dS[TRI(DX)];
 #pragma unroll
-      for (int i = 0; i < DX; ++i) dm[i] = m3m[i] - fr[(LY::F_MU3 + i) * TILE];
+      for (int i = 0; i < DX; ++i) dm[i] = m3m[i] - fr[(LY::F_MU3 + i) * FS];
 #pragma unroll
-      for (int i = 0; i < TRI(DX); ++i) dS[i] = S3m[i] - fr[(LY::F_SIG3 + i) * TILE];
+      for (int i = 0; i < TRI(DX); ++i) dS[i] = S3m[i] - fr[(LY::F_SIG3 + i) * FS];
 #pragma unroll
-      for (int i = 0; i < N * DX; ++i) J[i] = fr[(LY::F_J + i) * TILE];
+      for (int i = 0; i < N * DX; ++i) J[i] = fr[(LY::F_J + i) * FS];
       if (aux) {
         double* ab = rec(p.auxb, t, LY::E_AUXB);
 #pragma unroll
@@ -1163,7 +1184,7 @@ struct Worker {
       double JD[N * DX];
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        double s = fr[(LY::F_MU1 + i) * TILE];
+        double s = fr[(LY::F_MU1 + i) * FS];
 #pragma unroll
         for (int k = 0; k < DX; ++k) s = fma(J[i * DX + k], dm[k], s);
         mu[i] = s;
@@ -1179,7 +1200,7 @@ struct Worker {
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-          double s = fr[(LY::F_SIG1 + tix(i, j)) * TILE];
+          double s = fr[(LY::F_SIG1 + tix(i, j)) * FS];
 #pragma unroll
           for (int k = 0; k < DX; ++k) s = fma(JD[i * DX + k], J[j * DX + k], s);
           Sig[tix(i, j)] = s;
@@ -1927,10 +1948,11 @@ struct Worker {
         if constexpr (PROD) {
           int t = 0;
           if (sweep_is_plain(flipped)) {
+            TrigT octx;
+            if constexpr (Env::OBS_NL > 0) obs_trig(c, octx);
             for (; t < T - 1; ++t) {
               const double* cur = ring_acquire();
-              forward_cell<true>(it, t, 0, alpha, aux, cur, c, ent_x);
-              ring_release();
+              forward_cell<true>(it, t, 0, alpha, aux, cur, c, ent_x, &octx);  // releases the slot itself
             }
           }
           for (; t < T; ++t) {
@@ -1967,9 +1989,9 @@ struct Worker {
         volatile int* prog = TEAM ? reinterpret_cast<volatile int*>(red + (size_t)7 * W * TILE) : nullptr;
         int n_main = 0;
         if constexpr (TEAM) {
-          // tail : head cost is about r : 1 (7 with the per-thread record stream, 10 with the copy warp); balance warp 0's
+          // tail : head cost is about r : 1 (7 with the per-thread record stream, 4 with the copy warp: profiles/r02); balance warp 0's
           // share so that it and the H helpers finish together
-          const int r = PROD ? 10 : 7;
+          const int r = PROD ? 4 : 7;
           const int nm = (T * (r - H)) / (r * (H + 1));
           n_main = nm > 0 ? nm : 0;
           if (main_warp && lane == 0) *prog = 0;
@@ -1992,13 +2014,21 @@ struct Worker {
           if constexpr (PROD) {
             for (int t = T - 1; t >= 0; --t) {
               const double* cur = ring_acquire();
-              double mu[N], Sig[TRI(N)];
-              backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
-              ring_release();
+              double fr[LY::E_FILT];
+#pragma unroll
+              for (int e = 0; e < LY::E_FILT; ++e) fr[e] = cur[e * TILE];
+              ring_release();  // the record is in registers
+              // publish the PREVIOUS head here: its stores were issued a whole cell ago, so the fence does not wait for them
+              // (fencing right after a cell's own stores cost ~90 cycles per cell)
               asm volatile("fence.acq_rel.cta;" ::: "memory");
               __syncwarp();
-              if (lane == 0) *prog = T - t;
+              if (lane == 0) *prog = T - 1 - t;
+              double mu[N], Sig[TRI(N)];
+              backward_head<1>(it, t, aux, fr, m3m, S3m, mu, Sig);
             }
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) *prog = T;
           } else if constexpr (TEAM) {
             // RTS heads only: a head is a few hundred cycles, so the filtered records are streamed TEAM_DEPTH cells
             // ahead (a one-cell double buffer would expose the DRAM latency of every record)
