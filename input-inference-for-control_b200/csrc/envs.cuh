@@ -19,6 +19,14 @@ namespace i2c {
 //              the column (offsets(): once per transform).  The minus point is announced to the env maps by bit 6 of
 //              the column index (kMinus).
 constexpr int kMinus = 64;
+
+// np.clip for the action limits: two compares and selects.  fmin(fmax()) carries IEEE NaN handling that costs ~8 instructions
+// per call on this machine (DSETP.MAX + a select / sign-fix sequence per 32-bit half): 100 of the ~220 instructions of a
+// pendulum dynamics transform.  A NaN input stays NaN, as in np.clip.
+__device__ __forceinline__ double clipd(double x, double lo, double hi) {
+  double y = x > hi ? hi : x;
+  return x < lo ? lo : y;
+}
 template <int NA, int MODE = 0, int NJ = 1>
 struct Trig {
   static constexpr bool kFree = MODE & 1, kPM = (MODE & 2) != 0;
@@ -146,7 +154,7 @@ struct EnvPendulum {
     double s, co;
     trig(xu, j, c, s, co);
     (void)co;
-    double u = fmin(fmax(xu[2], kPendulum[4]), kPendulum[5]);
+    double u = clipd(xu[2], kPendulum[4], kPendulum[5]);
     // the reference evaluates np.sin(th + np.pi); sin(th + pi) == -sin(th) up to the rounding of th + pi
     double acc = kPendulum[2] * (-s) - d * xu[1];  // kPendulum[2] = -3 g / 2
     acc += kPendulum[3] * u;
@@ -222,7 +230,7 @@ struct EnvCartpole {
   template <class TT> __device__ static void dyn(const double* xu, int j, const TT& c, const double*, double* y) {
     // kCartpole = {-Mp l, Mt g, l, 4/3 Mt, Mp, Mp l, 1/Mt, dt, -5, 5}
     const double dt = kCartpole[7];
-    double u = fmin(fmax(xu[4], kCartpole[8]), kCartpole[9]);
+    double u = clipd(xu[4], kCartpole[8], kCartpole[9]);
     double sth, cth;
     trig(xu, j, c, sth, cth);
     double dth2 = xu[3] * xu[3];
@@ -338,7 +346,7 @@ struct EnvDoubleCartpole {
     double td1 = xu[4], td2 = xu[5];
     double C12 = kDcp[6] * td1 * s1, C13 = kDcp[7] * td2 * s2, C23 = a23 * td2 * sd, C32 = kDcp[8] * td1 * sd;
     double G2 = kDcp[9] * s1, G3 = kDcp[10] * s2;
-    double u = kDcp[11] * fmin(fmax(xu[6], kDcp[12]), kDcp[13]);
+    double u = kDcp[11] * clipd(xu[6], kDcp[12], kDcp[13]);
     double r1 = u - (C12 * td1 + C13 * td2);
     double r2 = -(C23 * td2) - G2;
     double r3 = -(C32 * td1) - G3;
@@ -424,7 +432,7 @@ struct EnvQuadrotor {
   template <class TT> __device__ static void dyn(const double* xu, int j, const TT& c, const double*, double* y) {
     // kQuad = {h, 1/MASS, -g, VDX, 1/INERTIA, 1/(1 + h/2), 0, 30}
     const double h = kQuad[0];
-    double u1 = fmin(fmax(xu[6], kQuad[6]), kQuad[7]), u2 = fmin(fmax(xu[7], kQuad[6]), kQuad[7]);
+    double u1 = clipd(xu[6], kQuad[6], kQuad[7]), u2 = clipd(xu[7], kQuad[6], kQuad[7]);
     double s, co;
     trig(xu, j, c, s, co);
     double f = u1 + u2;

@@ -134,6 +134,22 @@ __device__ __forceinline__ void mbar_wait_s(unsigned bar_s, unsigned parity) {
 __device__ __forceinline__ void mbar_arrive_s(unsigned bar_s) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
 }
+__device__ __forceinline__ double lds_f64(unsigned addr_s) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr_s));
+  return v;
+}
+// read-only tables (written once before a block-wide barrier): plain asm, the compiler may move / merge these loads
+__device__ __forceinline__ double lds_f64_ro(unsigned addr_s) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr_s));
+  return v;
+}
+__device__ __forceinline__ int2 lds_i2_ro(unsigned addr_s) {
+  int2 v;
+  asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr_s));
+  return v;
+}
 #ifdef I2C_NO_BULK
 constexpr bool kUseBulk = false;
 #else
@@ -537,12 +553,12 @@ struct Worker {
   double* stage;  // this warp's double buffer: [2][E_STAGE][32], already offset by lane
   uint64_t* bars; // this warp's mbarriers (bulk-copy completion), kNumBars of them
   unsigned bar_phase;  // one parity bit per mbarrier
-  const double* ztab;  // HOT: [T][DZ] cell targets in shared memory (logical cell order)
-  const int2* ftab;    // HOT: [T] {flags, index}
+  unsigned ztab_s, ftab_s;  // HOT: shared addresses of the [T][DZ] cell targets and the [T] {flags, index} table
 
   __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_, uint64_t* bars_)
       : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_), bars(bars_), bar_phase(0), ring_q(0), ring_ready(false) {
     bars_s = (unsigned)__cvta_generic_to_shared(bars_);
+    stage_s = (unsigned)__cvta_generic_to_shared(stage_);
     status = I2C_OK;
     info = 0;
     prior = p.prior;
@@ -594,7 +610,7 @@ struct Worker {
   __device__ __forceinline__ void staged_z(const double* sbuf, int t, double* z) const {
     if constexpr (HOT) {
 #pragma unroll
-      for (int a = 0; a < DZ; ++a) z[a] = ztab[t * DZ + a];
+      for (int a = 0; a < DZ; ++a) z[a] = lds_f64_ro(ztab_s + (t * DZ + a) * 8);
     } else if (LY::STAGED && META && smeta()) {
 #pragma unroll
       for (int a = 0; a < DZ; ++a) z[a] = sbuf[(LY::S_Z + a) * TILE];
@@ -605,7 +621,7 @@ struct Worker {
   __device__ __forceinline__ int staged_flags(const double* sbuf, int t, bool flipped) const {
     int flags, index;
     if constexpr (HOT) {
-      const int2 m = ftab[t];
+      const int2 m = lds_i2_ro(ftab_s + t * 8);
       flags = m.x;
       index = m.y;
     } else if (LY::STAGED && META && smeta()) {
@@ -624,7 +640,7 @@ struct Worker {
   // therefore issues no copy, no address arithmetic and no commit / wait bookkeeping for its input stream.
   static constexpr int RING = LY::RING, RSTRIDE = LY::E_STAGE;
   unsigned ring_q;  // cells produced / consumed so far: slot = q % RING, phase parity = (q / RING) & 1
-  unsigned bars_s;  // 32-bit shared address of bars[0]
+  unsigned bars_s, stage_s;  // 32-bit shared addresses of bars[0] and of this lane's column of the staging area
   bool ring_ready;  // early probe of the slot the next ring_acquire() will take (hides the mbarrier round trip)
   __device__ __forceinline__ void ring_init() {  // one thread, before the block-wide barrier that precedes any use
 #pragma unroll
@@ -634,14 +650,24 @@ struct Worker {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __device__ __forceinline__ const double* ring_acquire() {
+  // ring_acquire() hands out the slot as a 32-bit shared address (lane offset included): reading through the generic
+  // pointer made the compiler rebuild the shared-window base (S2R SR_CgaCtaId + arithmetic, ~100 exposed cycles in the
+  // short RTS-head cells) in every cell
+  template <int E>
+  __device__ __forceinline__ void ring_read(double* dst) {
+    const unsigned a = ring_acquire();
+#pragma unroll
+    for (int e = 0; e < E; ++e) dst[e] = lds_f64(a + e * (TILE * 8));
+    ring_release();  // the record is in registers (an arrive placed after the cell's stores waited ~90 cycles for them)
+  }
+  __device__ __forceinline__ unsigned ring_acquire() {
     const unsigned s = ring_q % RING;
     if (!ring_ready) mbar_wait_s(bars_s + 8u * s, (ring_q / RING) & 1u);
     // probe the NEXT cell's slot now: an mbarrier query takes ~100 cycles to come back, and the copy warp runs several
     // cells ahead, so the answer (consumed by the next acquire) is almost always "ready"
     const unsigned q1 = ring_q + 1;
     ring_ready = mbar_test_s(bars_s + 8u * (q1 % RING), (q1 / RING) & 1u);
-    return stage + s * (RSTRIDE * TILE);
+    return stage_s + s * (RSTRIDE * TILE * 8);
   }
   __device__ __forceinline__ void ring_release() {
     mbar_arrive_s(bars_s + 8u * (RING + ring_q % RING));
@@ -893,37 +919,35 @@ struct Worker {
   // linear moments = _forward_msgs_linearize (i2c.py:244-348; the terminal update then happens in the backward pass).  c: (mu_x0_f, sig_x0_f) in, (mu_x3_f, sig_x3_f) out.
   // PLAIN: the cell is known to be a feedback (not independent), non-terminal cell -- the sweep checked the flags of the
   // whole horizon beforehand (sweep_is_plain) -- so neither branch exists in the loop body.
-  // With PLAIN the ring slot is released as soon as the record is in registers (an mbarrier arrive has release semantics:
-  // placed after the cell's stores it waited ~90 cycles for them), and the trigonometric context of the cost-feature
-  // transform comes in through octx and is re-evaluated for the NEXT cell at the end, from the outgoing message.
-  template <bool PLAIN = false>
+  // With PLAIN the trigonometric context of the cost-feature transform comes in through octx and is re-evaluated for the
+  // NEXT cell at the end, from the outgoing message.  PS = element stride of the prior record at pr (1: register copy).
+  template <bool PLAIN = false, int PS = TILE>
   __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, const double* pr,
                                                Carry<DX>& c, LogAcc& ent_x, TrigT* octx = nullptr) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
     {
       double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];
 #pragma unroll
-      for (int r = 0; r < DU; ++r) mu_u[r] = pr[(LY::P_MU + DX + r) * TILE];
+      for (int r = 0; r < DU; ++r) mu_u[r] = pr[(LY::P_MU + DX + r) * PS];
 #pragma unroll
       for (int r = 0; r < DU; ++r)
 #pragma unroll
-        for (int q = 0; q <= r; ++q) Suu[tix(r, q)] = pr[(LY::P_SIG + tix(DX + r, DX + q)) * TILE];
+        for (int q = 0; q <= r; ++q) Suu[tix(r, q)] = pr[(LY::P_SIG + tix(DX + r, DX + q)) * PS];
       const bool indep = PLAIN ? false : (flags & I2C_CELL_INDEPENDENT);
       if (!indep) {
         // feedback prior (i2c.py:361-387): K <- K * N(mu_x0_f; mu_prev, C)/N(mu_prev; mu_prev, C), C = Sig_xx + sig_x0_f
         double mx[DX], Sxx[TRI(DX)], Sux[DU * DX], C[TRI(DX)], d[DX];
 #pragma unroll
-        for (int i = 0; i < DX; ++i) mx[i] = pr[(LY::P_MU + i) * TILE];
+        for (int i = 0; i < DX; ++i) mx[i] = pr[(LY::P_MU + i) * PS];
 #pragma unroll
-        for (int i = 0; i < TRI(DX); ++i) Sxx[i] = pr[(LY::P_SIG + i) * TILE];
+        for (int i = 0; i < TRI(DX); ++i) Sxx[i] = pr[(LY::P_SIG + i) * PS];
 #pragma unroll
         for (int r = 0; r < DU; ++r)
 #pragma unroll
           for (int j = 0; j < DX; ++j) {
-            Sux[r * DX + j] = pr[(LY::P_SIG + tix(DX + r, j)) * TILE];
-            Kt[r * DX + j] = pr[(LY::P_K + r * DX + j) * TILE];
+            Sux[r * DX + j] = pr[(LY::P_SIG + tix(DX + r, j)) * PS];
+            Kt[r * DX + j] = pr[(LY::P_K + r * DX + j) * PS];
           }
-        if constexpr (PLAIN) ring_release();  // every field of the staged record has been read
 #pragma unroll
         for (int i = 0; i < TRI(DX); ++i) C[i] = Sxx[i] + c.S[i];
 #pragma unroll
@@ -1303,7 +1327,7 @@ struct Worker {
       }
       st.cost += cm;
       st.cost_var += cv;
-      if (zbuf) staged_z(zbuf, t, z); else load_z(t, z);
+      if (HOT || zbuf) staged_z(zbuf, t, z); else load_z(t, z);  // HOT: the shared-memory table
       st.tr += alpha_trace<DZ>(p.QR, p.qr_diag, mz, Sz, z);
     }
   }
@@ -1444,25 +1468,26 @@ struct Worker {
     double cost, cost_var, cost_min, tr;
     LogAcc ent;
   };
+  template <int PS = TILE>
   __device__ __forceinline__ void propagate_cell(int it, int t, int flags, bool aux, const double* po, Carry<DX>& c,
                                                  PStats& st) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
     {
       double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];
 #pragma unroll
-      for (int r = 0; r < DU; ++r) mu_u[r] = po[(LY::P_MU + DX + r) * TILE];
+      for (int r = 0; r < DU; ++r) mu_u[r] = po[(LY::P_MU + DX + r) * PS];
 #pragma unroll
       for (int r = 0; r < DU; ++r)
 #pragma unroll
-        for (int q = 0; q <= r; ++q) Suu[tix(r, q)] = po[(LY::P_SIG + tix(DX + r, DX + q)) * TILE];
+        for (int q = 0; q <= r; ++q) Suu[tix(r, q)] = po[(LY::P_SIG + tix(DX + r, DX + q)) * PS];
 #pragma unroll
-      for (int i = 0; i < DU * DX; ++i) Kt[i] = po[(LY::P_K + i) * TILE];
+      for (int i = 0; i < DU * DX; ++i) Kt[i] = po[(LY::P_K + i) * PS];
       if (!(flags & I2C_CELL_INDEPENDENT)) {
         double mx[DX], Sxx[TRI(DX)], d[DX];
 #pragma unroll
-        for (int i = 0; i < DX; ++i) mx[i] = po[(LY::P_MU + i) * TILE];
+        for (int i = 0; i < DX; ++i) mx[i] = po[(LY::P_MU + i) * PS];
 #pragma unroll
-        for (int i = 0; i < TRI(DX); ++i) Sxx[i] = po[(LY::P_SIG + i) * TILE];
+        for (int i = 0; i < TRI(DX); ++i) Sxx[i] = po[(LY::P_SIG + i) * PS];
 #pragma unroll
         for (int i = 0; i < DX; ++i) d[i] = c.m[i] - mx[i];
         if (flags & I2C_CELL_EXPERT) {
@@ -1951,14 +1976,15 @@ struct Worker {
             TrigT octx;
             if constexpr (Env::OBS_NL > 0) obs_trig(c, octx);
             for (; t < T - 1; ++t) {
-              const double* cur = ring_acquire();
-              forward_cell<true>(it, t, 0, alpha, aux, cur, c, ent_x, &octx);  // releases the slot itself
+              double pr[LY::E_STAGE_POST];
+              ring_read<LY::E_STAGE_POST>(pr);
+              forward_cell<true, 1>(it, t, 0, alpha, aux, pr, c, ent_x, &octx);
             }
           }
           for (; t < T; ++t) {
-            const double* cur = ring_acquire();
-            forward_cell(it, t, staged_flags(cur, t, flipped), alpha, aux, cur, c, ent_x);
-            ring_release();
+            double pr[LY::E_STAGE_POST];
+            ring_read<LY::E_STAGE_POST>(pr);
+            forward_cell<false, 1>(it, t, staged_flags(nullptr, t, flipped), alpha, aux, pr, c, ent_x);
           }
           // the filtered records written above are read back by the copy warp's bulk copies after the barrier below
           __threadfence();
@@ -2013,11 +2039,8 @@ struct Worker {
           backward_terminal(it, T - 1, temp, cell_alpha(T - 1, p.cell_flags[slot(T - 1)], alpha), c, m3m, S3m, tr_term);
           if constexpr (PROD) {
             for (int t = T - 1; t >= 0; --t) {
-              const double* cur = ring_acquire();
               double fr[LY::E_FILT];
-#pragma unroll
-              for (int e = 0; e < LY::E_FILT; ++e) fr[e] = cur[e * TILE];
-              ring_release();  // the record is in registers
+              ring_read<LY::E_FILT>(fr);
               // publish the PREVIOUS head here: its stores were issued a whole cell ago, so the fence does not wait for them
               // (fencing right after a cell's own stores cost ~90 cycles per cell)
               asm volatile("fence.acq_rel.cta;" ::: "memory");
@@ -2142,9 +2165,9 @@ struct Worker {
         if (!load_x0(cp)) fail(I2C_FAIL_CHOL_PROPAGATE, it, 0);
         if constexpr (PROD) {
           for (int t = 0; t < T; ++t) {
-            const double* cur = ring_acquire();
-            propagate_cell(it, t, staged_flags(cur, t, flipped), aux, cur, cp, ps);
-            ring_release();
+            double po[LY::E_STAGE_POST];
+            ring_read<LY::E_STAGE_POST>(po);
+            propagate_cell<1>(it, t, staged_flags(nullptr, t, flipped), aux, po, cp, ps);
           }
         } else {
           stream_begin<LY::E_STAGE_POST>(latest, LY::E_POST, 0);
@@ -2269,8 +2292,8 @@ __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_c
     for (int i = threadIdx.x; i < pin.T * DZ; i += W * TILE) ztab[i] = pin.z_cell[wk.slot(i / DZ) * DZ + i % DZ];
     for (int t = threadIdx.x; t < pin.T; t += W * TILE) ftab[t] = make_int2(pin.cell_flags[wk.slot(t)], pin.cell_index[wk.slot(t)]);
     __syncthreads();
-    wk.ztab = ztab;
-    wk.ftab = ftab;
+    wk.ztab_s = (unsigned)__cvta_generic_to_shared(ztab);
+    wk.ftab_s = (unsigned)__cvta_generic_to_shared(ftab);
   }
   wk.template run_impl<true>(w, W, red);
 }
