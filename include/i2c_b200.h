@@ -276,6 +276,12 @@ int i2c_kernel_launches(i2c_handle_t h, int64_t* n); /* kernels launched by this
 int i2c_last_run_ms(i2c_handle_t h, float* ms);      /* CUDA-event time of the last i2c_run kernel */
 /* Measured fp64 FMA-pipe peak of the device in TFLOP/s (roofline denominator; 8 independent DFMA chains/thread). */
 int i2c_dfma_peak(int32_t device, double* tflops);
+/* The device math primitives (csrc/fastmath.cuh) on caller-provided arguments, for accuracy tests against libm:
+ * fn 0 rsqrt, 1 reciprocal, 2 exp (x <= 0, throughput flavour), 3 exp (latency flavour), 4 sincos (branch-free),
+ * 5 sincos (sequenced), 6 log-determinant accumulator log(x * x^2).  y1 receives the cosine for fn 4 / 5.  Replaces
+ * nothing in the reference (NumPy libm calls: np.sin / np.cos env_def.py:273-291, np.linalg.cholesky quadrature.py:18,
+ * scipy multivariate_normal.pdf i2c.py:369-374). */
+int i2c_fastmath_probe(int32_t device, int32_t fn, int32_t n, const double* x, double* y0, double* y1);
 const char* i2c_last_error(void);
 const char* i2c_build_info(void);
 

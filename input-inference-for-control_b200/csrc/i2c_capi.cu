@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "i2c_types.h"
+#include "linalg.cuh"  // fastmath probe (LogAcc, fast_* primitives)
 
 using namespace i2c;
 
@@ -1538,6 +1539,53 @@ int i2c_rollout(int32_t env, int32_t n_problems, int32_t n_rollouts, int32_t hor
   }
   cudaFree(buf);
   return rc;
+}
+
+// Device math primitives of csrc/fastmath.cuh evaluated on host-provided arguments (accuracy tests: tests/test_gpu_fastmath.py)
+__global__ void fastmath_probe_kernel(int fn, int n, const double* x, double* y0, double* y1) {
+  using namespace i2c;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0, b = 0.0;
+  switch (fn) {
+    case 0: a = fast_rsqrt(x[i]); break;
+    case 1: a = fast_rcp(x[i]); break;
+    case 2: a = fast_exp_neg(x[i]); break;
+    case 3: a = fast_exp_neg_lat(x[i]); break;
+    case 4: fast_sincos(x[i], &a, &b); break;
+    case 5: seq_sincos(x[i], &a, &b); break;
+    case 6: {  // log-determinant accumulator: log of the running product of x[i], x[i]^2
+      LogAcc l;
+      l.reset();
+      l.mul(x[i]);
+      l.mul(x[i] * x[i]);
+      a = l.value();
+      break;
+    }
+    default: break;
+  }
+  y0[i] = a;
+  y1[i] = b;
+}
+
+int i2c_fastmath_probe(int32_t device, int32_t fn, int32_t n, const double* x, double* y0, double* y1) {
+  REQUIRE(x && y0 && y1 && n > 0 && fn >= 0 && fn <= 6, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(-2, "no CUDA device available");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CUDA_OK(cudaSetDevice(device));
+  double* d = nullptr;
+  CUDA_OK(cudaMalloc((void**)&d, (size_t)n * 8 * 3));
+  CUDA_OK(cudaMemcpy(d, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+  fastmath_probe_kernel<<<(n + 127) / 128, 128>>>(fn, n, d, d + n, d + 2 * (size_t)n);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(y0, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(y1, d + 2 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  cudaSetDevice(prev);
+  CUDA_OK(e);
+  return 0;
 }
 
 int i2c_dfma_peak(int32_t device, double* tflops) {

@@ -653,21 +653,25 @@ struct Worker {
   // ring_acquire() hands out the slot as a 32-bit shared address (lane offset included): reading through the generic
   // pointer made the compiler rebuild the shared-window base (S2R SR_CgaCtaId + arithmetic, ~100 exposed cycles in the
   // short RTS-head cells) in every cell
+  // small systems copy the record into registers and release the slot at once; for n > 3 that many live registers spill
+  // (cart-pole: 600 bytes of stack), so those read the slot in place and release it after the cell
+  static constexpr bool RCOPY = N <= 3;
   template <int E>
   __device__ __forceinline__ void ring_read(double* dst) {
-    const unsigned a = ring_acquire();
+    const unsigned a = stage_s + ring_acquire() * (RSTRIDE * TILE * 8);
 #pragma unroll
     for (int e = 0; e < E; ++e) dst[e] = lds_f64(a + e * (TILE * 8));
     ring_release();  // the record is in registers (an arrive placed after the cell's stores waited ~90 cycles for them)
   }
-  __device__ __forceinline__ unsigned ring_acquire() {
+  __device__ __forceinline__ const double* ring_view() { return stage + ring_acquire() * (RSTRIDE * TILE); }
+  __device__ __forceinline__ unsigned ring_acquire() {  // -> slot index
     const unsigned s = ring_q % RING;
     if (!ring_ready) mbar_wait_s(bars_s + 8u * s, (ring_q / RING) & 1u);
     // probe the NEXT cell's slot now: an mbarrier query takes ~100 cycles to come back, and the copy warp runs several
     // cells ahead, so the answer (consumed by the next acquire) is almost always "ready"
     const unsigned q1 = ring_q + 1;
     ring_ready = mbar_test_s(bars_s + 8u * (q1 % RING), (q1 / RING) & 1u);
-    return stage_s + s * (RSTRIDE * TILE * 8);
+    return s;
   }
   __device__ __forceinline__ void ring_release() {
     mbar_arrive_s(bars_s + 8u * (RING + ring_q % RING));
@@ -1976,15 +1980,25 @@ struct Worker {
             TrigT octx;
             if constexpr (Env::OBS_NL > 0) obs_trig(c, octx);
             for (; t < T - 1; ++t) {
-              double pr[LY::E_STAGE_POST];
-              ring_read<LY::E_STAGE_POST>(pr);
-              forward_cell<true, 1>(it, t, 0, alpha, aux, pr, c, ent_x, &octx);
+              if constexpr (RCOPY) {
+                double pr[LY::E_STAGE_POST];
+                ring_read<LY::E_STAGE_POST>(pr);
+                forward_cell<true, 1>(it, t, 0, alpha, aux, pr, c, ent_x, &octx);
+              } else {
+                forward_cell<true>(it, t, 0, alpha, aux, ring_view(), c, ent_x, &octx);
+                ring_release();
+              }
             }
           }
           for (; t < T; ++t) {
-            double pr[LY::E_STAGE_POST];
-            ring_read<LY::E_STAGE_POST>(pr);
-            forward_cell<false, 1>(it, t, staged_flags(nullptr, t, flipped), alpha, aux, pr, c, ent_x);
+            if constexpr (RCOPY) {
+              double pr[LY::E_STAGE_POST];
+              ring_read<LY::E_STAGE_POST>(pr);
+              forward_cell<false, 1>(it, t, staged_flags(nullptr, t, flipped), alpha, aux, pr, c, ent_x);
+            } else {
+              forward_cell(it, t, staged_flags(nullptr, t, flipped), alpha, aux, ring_view(), c, ent_x);
+              ring_release();
+            }
           }
           // the filtered records written above are read back by the copy warp's bulk copies after the barrier below
           __threadfence();
@@ -2039,15 +2053,18 @@ struct Worker {
           backward_terminal(it, T - 1, temp, cell_alpha(T - 1, p.cell_flags[slot(T - 1)], alpha), c, m3m, S3m, tr_term);
           if constexpr (PROD) {
             for (int t = T - 1; t >= 0; --t) {
-              double fr[LY::E_FILT];
-              ring_read<LY::E_FILT>(fr);
+              double fr[RCOPY ? LY::E_FILT : 1];
+              const double* frv = fr;
+              if constexpr (RCOPY) ring_read<LY::E_FILT>(fr);
+              else frv = ring_view();
               // publish the PREVIOUS head here: its stores were issued a whole cell ago, so the fence does not wait for them
               // (fencing right after a cell's own stores cost ~90 cycles per cell)
               asm volatile("fence.acq_rel.cta;" ::: "memory");
               __syncwarp();
               if (lane == 0) *prog = T - 1 - t;
               double mu[N], Sig[TRI(N)];
-              backward_head<1>(it, t, aux, fr, m3m, S3m, mu, Sig);
+              backward_head<RCOPY ? 1 : TILE>(it, t, aux, frv, m3m, S3m, mu, Sig);
+              if constexpr (!RCOPY) ring_release();
             }
             asm volatile("fence.acq_rel.cta;" ::: "memory");
             __syncwarp();
@@ -2165,9 +2182,14 @@ struct Worker {
         if (!load_x0(cp)) fail(I2C_FAIL_CHOL_PROPAGATE, it, 0);
         if constexpr (PROD) {
           for (int t = 0; t < T; ++t) {
-            double po[LY::E_STAGE_POST];
-            ring_read<LY::E_STAGE_POST>(po);
-            propagate_cell<1>(it, t, staged_flags(nullptr, t, flipped), aux, po, cp, ps);
+            if constexpr (RCOPY) {
+              double po[LY::E_STAGE_POST];
+              ring_read<LY::E_STAGE_POST>(po);
+              propagate_cell<1>(it, t, staged_flags(nullptr, t, flipped), aux, po, cp, ps);
+            } else {
+              propagate_cell(it, t, staged_flags(nullptr, t, flipped), aux, ring_view(), cp, ps);
+              ring_release();
+            }
           }
         } else {
           stream_begin<LY::E_STAGE_POST>(latest, LY::E_POST, 0);

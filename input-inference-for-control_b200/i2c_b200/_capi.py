@@ -66,7 +66,7 @@ EXPORTS = [
     "i2c_set_alpha", "i2c_get_alpha", "i2c_set_temp", "i2c_get_temp", "i2c_run", "i2c_run_scan", "i2c_synchronize", "i2c_get_metric",
     "i2c_get_status", "i2c_get_field", "i2c_set_field", "i2c_field_shape", "i2c_get_policy", "i2c_get_policy_async", "i2c_copy_wait", "i2c_get_policy_dev",
     "i2c_shift_horizon", "i2c_ckf_step", "i2c_mpc_step", "i2c_get_initial_state", "i2c_get_first_action", "i2c_quadrature", "i2c_quadrature_gh", "i2c_gauss_hermite",
-    "i2c_rollout", "i2c_snapshot_bytes", "i2c_snapshot", "i2c_restore", "i2c_kernel_launches", "i2c_last_run_ms", "i2c_dfma_peak",
+    "i2c_rollout", "i2c_snapshot_bytes", "i2c_snapshot", "i2c_restore", "i2c_kernel_launches", "i2c_last_run_ms", "i2c_dfma_peak", "i2c_fastmath_probe",
     "i2c_last_error",
     "i2c_build_info",
 ]
@@ -137,6 +137,7 @@ def lib():
     L.i2c_kernel_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.i2c_last_run_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.i2c_dfma_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    L.i2c_fastmath_probe.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]
     L.i2c_env_dims.argtypes = [C.c_int32, _ip, _ip, _ip, _ip, _ip, _ip]
     _lib = L
     return L
@@ -163,6 +164,18 @@ def dfma_peak(device=0):
     v = C.c_double()
     check(lib().i2c_dfma_peak(device, C.byref(v)))
     return v.value
+
+
+FASTMATH_FN = {"rsqrt": 0, "rcp": 1, "exp_neg": 2, "exp_neg_lat": 3, "sincos": 4, "seq_sincos": 5, "logacc": 6}
+
+
+def fastmath_probe(fn, x, device=0):
+    """Evaluate one device math primitive of csrc/fastmath.cuh on the array x; returns (y0, y1)."""
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    y0, y1 = np.empty_like(x), np.empty_like(x)
+    check(lib().i2c_fastmath_probe(device, FASTMATH_FN[fn], x.size, x.ctypes.data_as(_dp), y0.ctypes.data_as(_dp),
+                                   y1.ctypes.data_as(_dp)))
+    return y0, y1
 
 
 def env_dims(env_id):

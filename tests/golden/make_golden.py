@@ -422,8 +422,75 @@ def likelihood():
     save("likelihood_kat", d)
 
 
+def rollouts():
+    """Pin for oracle/rollout.py: the reference's BaseSim.run (i2c/env.py:40-74) with BaseKnownSim.forward (:180-187)
+    under TimeIndexedLinearGaussianPolicy / ExpertTimeIndexedLinearGaussianPolicy (policy/linear.py:31-90), global NumPy RNG
+    seeded.  Every disturbance the reference draws (numpy.random.multivariate_normal in i2c.env and i2c.policy.linear) is
+    logged, so that the oracle / the CUDA kernel can be fed the very same realisations."""
+    import importlib
+
+    env_mod = importlib.import_module("i2c.env")
+    lin_mod = importlib.import_module("i2c.policy.linear")
+    log = []
+    real_mvn = np.random.multivariate_normal
+
+    def logged(mean, cov, size=None):
+        out = real_mvn(mean, cov, size)
+        log.append(np.asarray(out, float).reshape(-1) - np.asarray(mean, float).reshape(-1))
+        return out
+
+    env_mod.mvn = logged
+    lin_mod.mvn = logged
+    d = {}
+    for env_key, exp_name, T in [("PendulumKnown", "pendulum_known_quad", 40), ("CartpoleKnown", "cartpole_known_quad", 30)]:
+        exp = ref_shim.load_experiment(exp_name, 0)
+        I = exp.INFERENCE
+        exp.N_DURATION = T
+        sim = env_mod.make_env(exp)
+        sys_ = ns.model.make_env_model(env_key, None)
+        rng = np.random.default_rng(9)
+        mu_u = 1e-2 * rng.normal(size=(T, sys_.dim_u))
+        g = I2cGraph(sys_, T, I.Q, I.R, I.Qf, I.alpha, 0.0, mu_u, I.sig_u, None, None, Cub(1, 0, 0))
+        for _ in range(6):
+            g.learn_msgs()
+        K, k, sk = g.get_local_linear_policy()
+        pol = lin_mod.TimeIndexedLinearGaussianPolicy(I.sig_u, T, sys_.dim_u, sys_.dim_x)
+        pol.write(K, k, sk)
+        Ke, ke, ske, mue, lame = g.get_local_expert_linear_policy()
+        d[f"{env_key}/T"], d[f"{env_key}/K"], d[f"{env_key}/k"], d[f"{env_key}/sigK"] = T, K, k, sk
+        d[f"{env_key}/x0"] = np.asarray(sim.x0, float).reshape(-1)
+        d[f"{env_key}/ex_K"], d[f"{env_key}/ex_k"], d[f"{env_key}/ex_mu"], d[f"{env_key}/ex_lam"] = Ke, ke, mue, lame
+        runs = [("det_env_det_pol", True, True, pol), ("noisy_env_det_pol", False, True, pol),
+                ("noisy_env_noisy_pol", False, False, pol)]
+        for soft in (True, False):
+            ep = lin_mod.ExpertTimeIndexedLinearGaussianPolicy(I.sig_u, T, sys_.dim_u, sys_.dim_x, soft=soft)
+            ep.write(Ke, ke, ske, mue, lame)
+            runs.append((f"expert_{'soft' if soft else 'hard'}", False, True, ep))
+        for tag, env_det, pol_det, policy in runs:
+            np.random.seed(123)
+            sim.deterministic = env_det
+            log.clear()
+            xt, yt, zt, z_term = sim.run(policy, deterministic=pol_det)
+            draws = [np.array(v) for v in log]
+            # order of the draws inside one step: policy first (if stochastic), then the environment (env.py:57-61)
+            eta = np.zeros((T, sys_.dim_x))
+            eu = np.zeros((T, sys_.dim_u))
+            it = iter(draws)
+            for t in range(T):
+                if not pol_det:
+                    eu[t] = next(it)
+                if not env_det:
+                    eta[t] = next(it)
+            assert next(it, None) is None
+            d[f"{env_key}/{tag}/xt"], d[f"{env_key}/{tag}/zt"], d[f"{env_key}/{tag}/z_term"] = xt, zt, z_term
+            d[f"{env_key}/{tag}/eta"], d[f"{env_key}/{tag}/u_noise"] = eta, eu
+    env_mod.mvn = real_mvn
+    lin_mod.mvn = real_mvn
+    save("rollout_kat", d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc", "gh", "eval", "ll"]
+    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc", "gh", "eval", "ll", "roll"]
     if "quad" in which:
         quad_kat()
     if "em" in which:
@@ -438,3 +505,5 @@ if __name__ == "__main__":
         evaluators()
     if "ll" in which:
         likelihood()
+    if "roll" in which:
+        rollouts()

@@ -55,10 +55,11 @@ def test_config4_shard_double_cartpole_covariance_control(i2c_b200):
     for _ in range(iters):
         ref.learn_msgs()
     # T = 500 cells of a chaotic system: the noise floor of the reference itself is ~1e-9 after ONE sweep
-    assert relerr(G.field("mu_xu0_m")[idx], ref.stack("mu_xu0_m")) < 1e-6
-    assert relerr(G.field("sig_xu0_m")[idx], ref.stack("sig_xu0_m")) < 1e-5
-    assert relerr(G.alpha[idx], ref.alpha) < 1e-8  # the ratio clip binds (tol 0.99): schedules agree to round-off
-    assert relerr(np.array(G.metrics["cost_m"])[:, idx], np.array(ref.costs_m)) < 1e-6
+    # measured (profiles/r02_parity_floors.txt): 3.3e-10 / 1.1e-9 / 0 / 4e-11 -> 10 x
+    assert relerr(G.field("mu_xu0_m")[idx], ref.stack("mu_xu0_m")) < 5e-9
+    assert relerr(G.field("sig_xu0_m")[idx], ref.stack("sig_xu0_m")) < 1e-8
+    assert relerr(G.alpha[idx], ref.alpha) < 1e-9  # the ratio clip binds (tol 0.99): schedules agree to round-off
+    assert relerr(np.array(G.metrics["cost_m"])[:, idx], np.array(ref.costs_m)) < 1e-9
     sig = G.field("sig_xu0_m")
     assert np.all(np.isfinite(sig)) and np.all(np.linalg.eigvalsh(sig.reshape(-1, 7, 7)) > 0)
     K, k, sk = G.get_local_linear_policy()
@@ -120,9 +121,9 @@ def test_config5_shard_quadrotor_mpc(i2c_b200):
         y = sys_.measure(x) + rng.multivariate_normal(np.zeros(8), sig_zeta, B)
         u = np.clip(pol(t, y, u), 0.0, 30.0)
         ur = np.clip(rp(t, y[:n_ref], ur), 0.0, 30.0)
-        assert relerr(u[:n_ref], ur) < 1e-6, t
+        assert relerr(u[:n_ref], ur) < 1e-9, t  # measured 1e-10 over the closed loop
         assert np.all(np.isfinite(u))
         x = sys_.dynamics(np.concatenate((x, u), axis=-1)) + rng.multivariate_normal(np.zeros(6), sys_.sig_eta, B)
     assert np.all(G.status()[0] == 0)
     mu, cov = pol.belief
-    assert relerr(mu[:n_ref], rp.mu) < 1e-6 and np.all(np.linalg.eigvalsh(cov) > 0)
+    assert relerr(mu[:n_ref], rp.mu) < 1e-9 and np.all(np.linalg.eigvalsh(cov) > 0)

@@ -117,11 +117,11 @@ def test_nonlinear_covariance_control_flow(mirror):
         i2c.learn_msgs()
     c = i2c.cells[-1]
     assert c.mu_x3_m.shape == (2, 1) and c.sig_x3_pf.shape == (2, 2)
-    assert relerr(np.array(i2c.kl_terms), g["kl_terms"]) < 1e-5
-    assert relerr(np.array(i2c.costs_pf), g["costs_pf"]) < 1e-6
+    assert relerr(np.array(i2c.kl_terms), g["kl_terms"]) < 3e-8  # measured 2.2e-9 (reference's own floor 2e-9, see test_gpu_widen)
+    assert relerr(np.array(i2c.costs_pf), g["costs_pf"]) < 1e-8
     assert relerr(np.array(i2c.alphas), g["alphas"]) < 1e-12  # tol = 1.0: alpha frozen, exact
     K, k, s = i2c.get_local_linear_policy()
-    assert relerr(K, g["final/K"], 1e-6) < 1e-5
+    assert relerr(K, g["final/K"], 1e-6) < 2e-8  # measured 1.4e-9
 
 
 def test_quadrature_inference_mirror(mirror):
@@ -222,10 +222,11 @@ def test_linearize_pendulum_flow(mirror):
     for _ in range(4):
         i2c.learn_msgs()
         ref.learn_msgs()
-    assert relerr(np.array(i2c.alphas), np.array([a[0] for a in ref.alphas])) < 1e-6
+    assert relerr(np.array(i2c.alphas), np.array([a[0] for a in ref.alphas])) < 1e-8
     K, k, s = i2c.get_local_linear_policy()
     Kr, kr, sr = ref.get_local_linear_policy()
-    assert relerr(K, Kr[0]) < 1e-4 and relerr(k, kr[0]) < 1e-4 and relerr(s, sr[0]) < 1e-5
+    # parity unpinned (central-difference Jacobians in the oracle): measured 1.1e-8
+    assert relerr(K, Kr[0]) < 2e-7 and relerr(k, kr[0]) < 2e-7 and relerr(s, sr[0]) < 1e-8
 
 
 def test_alpha_helpers_match_device_update(mirror):

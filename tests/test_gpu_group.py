@@ -31,11 +31,12 @@ class mode:
 
 
 CASES = [
-    ("PendulumKnown", 70, 40, np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), 100.0, 0.0, [0.3, 0.5], 2.0, 1e-9, 1e-7),
-    ("CartpoleKnown", 37, 30, np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0]), 80.0, 0.0, 0.05, 1.0, 1e-9, 1e-6),
+    # tolerances: see tests/test_gpu_parity.py (max(1e-9, ~10 x measured); gains per environment)
+    ("PendulumKnown", 70, 40, np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), 100.0, 0.0, [0.3, 0.5], 2.0, 1e-9, 2e-9),
+    ("CartpoleKnown", 37, 30, np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0]), 80.0, 0.0, 0.05, 1.0, 1e-9, 2e-8),
     ("DoubleCartpoleKnown", 33, 30, 1e-3 * np.diag([1.0, 1.0, 100.0, 1.0, 100.0, 10.0, 1.0, 1.0]), 1e-4 * np.eye(1), 0.05, 0.99,
-     0.02, 1.0, 1e-8, 1e-5),
-    ("LinearKnownMinimumEnergy", 9, 20, None, np.diag([1.0]), 10.0, 0.5, 0.3, 10.0, 1e-10, 1e-7),
+     0.02, 1.0, 1e-9, 5e-8),
+    ("LinearKnownMinimumEnergy", 9, 20, None, np.diag([1.0]), 10.0, 0.5, 0.3, 10.0, 1e-10, 5e-8),
 ]
 
 
@@ -88,7 +89,7 @@ def test_group_kernel_covariance_control_propagate_golden(i2c_b200):
         G.set_cell_flag(capi.CELL_EXPERT, bool(g["expert"]))
         G.run(1, capi.PH_PROPAGATE, False)
         for a in PF:
-            assert relerr(G.field(a)[0], g[f"it0/{a}"]) < 1e-8, a
+            assert relerr(G.field(a)[0], g[f"it0/{a}"]) < 1e-9, a
         n_dump, n_total = int(g["n_dump"]), int(g["n_total"])
         for it in range(1, n_total + 1):
             G.learn(1)
@@ -96,11 +97,11 @@ def test_group_kernel_covariance_control_propagate_golden(i2c_b200):
             if it <= n_dump:
                 for a in FIELDS[2:] + PF:
                     e = relerr(G.field(a)[0], g[f"it{it}/{a}"], floor=1e-6 if a in GAINS else 0.0)
-                    assert e < (1e-5 if a in GAINS else 1e-8), (it, a, e)
-    assert relerr(np.array([a[0] for a in G.alphas]), g["alphas"]) < 1e-8
-    assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-7
-    assert relerr(np.array(G.metrics["cost_pf"])[:, 0], g["costs_pf"]) < 1e-7
-    assert relerr(np.array(G.metrics["kl_term"])[:, 0], g["kl_terms"]) < 1e-6
+                    assert e < (5e-8 if a in GAINS else 3e-9), (it, a, e)  # measured 4.5e-9 / 3e-10
+    assert relerr(np.array([a[0] for a in G.alphas]), g["alphas"]) < 1e-9
+    assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-9
+    assert relerr(np.array(G.metrics["cost_pf"])[:, 0], g["costs_pf"]) < 1e-9
+    assert relerr(np.array(G.metrics["kl_term"])[:, 0], g["kl_terms"]) < 1e-9
 
 
 def test_group_kernel_expert_propagate_golden(i2c_b200):
@@ -117,9 +118,9 @@ def test_group_kernel_expert_propagate_golden(i2c_b200):
             if it <= int(g["n_dump"]):
                 for a in FIELDS[2:] + PF:
                     e = relerr(G.field(a)[0], g[f"it{it}/{a}"], floor=1e-6 if a in GAINS else 0.0)
-                    assert e < (1e-7 if a in GAINS else 1e-9), (it, a, e)
-    assert relerr(np.array([a[0] for a in G.alphas]), g["alphas"]) < 1e-8
-    assert relerr(np.array(G.metrics["cost_pf"])[:, 0], g["costs_pf"]) < 1e-8
+                    assert e < (3e-9 if a in GAINS else 1e-9), (it, a, e)  # measured 2.4e-10
+    assert relerr(np.array([a[0] for a in G.alphas]), g["alphas"]) < 1e-9
+    assert relerr(np.array(G.metrics["cost_pf"])[:, 0], g["costs_pf"]) < 1e-9
 
 
 def test_group_kernel_timing_report(i2c_b200):

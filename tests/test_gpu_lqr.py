@@ -36,6 +36,34 @@ def lqr_graph(m, g, B, A, xag, x0, aux=True):
     return G, a
 
 
+def riccati_noise_floor(g, n=6):
+    """Round-off floor of the reference's Riccati messages on the LQR config: largest change of each field over n runs
+    of the oracle with A perturbed by relative 2^-52 noise (a few ulps)."""
+    from oracle import envs as E
+    from oracle import i2c_oracle as O
+
+    H = int(g["H"])
+    rng = np.random.default_rng(0)
+
+    def run(A):
+        sys_ = E.Linear(A=A[None], B=g["B"], xg=g["xag"][None])
+        G = O.Graph(sys_, H, g["Q"], g["R"], g["Qf"], 1e-5, 0.0, np.zeros((H, 1)), 1e2 * np.eye(1), None, None,
+                    O.Linearize(), B=1, x0=g["x0"][None])
+        for c in G.cells:
+            c.state_action_independence = True
+        G._forward_backward_msgs()
+        G._backward_ricatti_msgs()
+        return {a: G.stack(a)[0] for a in ("lambda_x3_b", "K", "k")}
+
+    base = run(g["A"])
+    floor = {a: 0.0 for a in base}
+    for _ in range(n):
+        out = run(g["A"] * (1.0 + 2.0 ** -52 * rng.integers(-2, 3, size=g["A"].shape)))
+        for a in base:
+            floor[a] = max(floor[a], float(np.max(np.abs(out[a] - base[a])) / np.max(np.abs(base[a]))))
+    return floor
+
+
 def test_lqr_golden_single(i2c_b200):
     g = golden("lqr_linearize")
     capi = i2c_b200.capi
@@ -49,20 +77,25 @@ def test_lqr_golden_single(i2c_b200):
     G.z_graph[:] = zg
     G.forward_backward(1)  # lqr_compare.py:171 (all cells independent: the constructor state)
     assert np.all(G.status()[0] == 0), G.status()
-    for a, tol in [("mu_xu1_f", 1e-9), ("sig_xu1_f", 1e-6), ("mu_x3_f", 1e-9), ("sig_x3_f", 1e-6), ("mu_xu0_m", 1e-8),
-                   ("sig_xu0_m", 1e-6), ("K", 1e-6), ("k", 1e-6), ("sigK", 1e-8), ("J_dyn", 1e-6)]:
+    # sig_x0 = sig_eta = 1e-20 I, alpha = 1e-5: measured <= 5.8e-10 on every field
+    for a, tol in [("mu_xu1_f", 1e-9), ("sig_xu1_f", 5e-9), ("mu_x3_f", 1e-9), ("sig_x3_f", 5e-9), ("mu_xu0_m", 1e-9),
+                   ("sig_xu0_m", 5e-9), ("K", 5e-9), ("k", 5e-9), ("sigK", 1e-9), ("J_dyn", 5e-9)]:
         assert relerr(G.field(a)[0], g[f"fb/{a}"]) < tol, a
     K, k, _ = G.get_local_linear_policy()
     assert np.max(np.abs(K[0] - g["K_lqr"])) < 1e-5 * np.max(np.abs(g["K_lqr"]))
     assert np.max(np.abs(k[0] - g["k_lqr"])) < 1e-4 * np.max(np.abs(g["k_lqr"]))
     G.backward_ricatti()  # lqr_compare.py:175
-    assert relerr(G.field("lambda_x3_b")[0], g["ric/lambda_x3_b"]) < 1e-4
-    assert relerr(G.field("K")[0], g["ric/K"]) < 1e-3
-    assert relerr(G.field("k")[0], g["ric/k"]) < 1e-3
-    # value function: lambda_x3_b * alpha ~ P of the Riccati recursion (lqr_compare.py:85-110)
+    # The Riccati messages invert information matrices built from covariances of 1e-20 .. 1e2 (condition ~1e11): the
+    # noise floor is what the REFERENCE arithmetic itself moves by when its input A is perturbed by a few ulps.
+    # Tolerance = max(1e-9, 10 x that floor), measured on the oracle (same LAPACK calls as the reference).
+    floor = riccati_noise_floor(g)
+    assert relerr(G.field("lambda_x3_b")[0], g["ric/lambda_x3_b"]) < max(1e-9, 10 * floor["lambda_x3_b"])
+    assert relerr(G.field("K")[0], g["ric/K"]) < max(1e-9, 10 * floor["K"]), floor
+    assert relerr(G.field("k")[0], g["ric/k"]) < max(1e-9, 10 * floor["k"]), floor
+    # value function: lambda_x3_b * alpha ~ P of the Riccati recursion (lqr_compare.py:85-110): a limit (measured 2.8e-8)
     P = g["P"]
     lam = G.field("lambda_x3_b")[0] * 1e-5
-    assert relerr(lam, P) < 1e-3
+    assert relerr(lam, P) < 1e-6
 
 
 def test_lqr_batched_8192_vs_riccati(i2c_b200):
@@ -103,8 +136,9 @@ def test_lqr_batched_vs_oracle(i2c_b200):
                 B=B, x0=x0)
     G.forward_backward(1)
     R._forward_backward_msgs()
-    for name, tol in [("mu_xu1_f", 1e-8), ("sig_xu1_f", 1e-5), ("mu_xu0_m", 1e-7), ("sig_xu0_m", 1e-5), ("K", 1e-5),
-                      ("k", 1e-5), ("mu_z0_m", 1e-7), ("sig_z0_m", 1e-5), ("mu_x3_m", 1e-7)]:
+    # 48 perturbed systems (some nearly unstable): measured <= 2.2e-9 over all fields
+    for name, tol in [("mu_xu1_f", 1e-9), ("sig_xu1_f", 2e-8), ("mu_xu0_m", 1e-9), ("sig_xu0_m", 2e-8), ("K", 2e-8),
+                      ("k", 2e-8), ("mu_z0_m", 1e-9), ("sig_z0_m", 2e-8), ("mu_x3_m", 1e-9)]:
         assert relerr(G.field(name), R.stack(name)) < tol, name
 
 
@@ -123,9 +157,9 @@ def test_linear_covariance_control_linearize(i2c_b200):
         if it <= 2:
             for a in ["mu_xu1_f", "sig_xu1_f", "mu_x3_f", "sig_x3_f", "mu_xu0_m", "sig_xu0_m", "K", "k", "sigK", "mu_x3_pf",
                       "sig_x3_pf"]:
-                assert relerr(G.field(a)[0], g[f"it{it}/{a}"], floor=1e-9) < 1e-7, (it, a)
-    assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-7
-    assert relerr(np.array(G.metrics["kl_term"])[:, 0], g["kl_terms"]) < 1e-6
+                assert relerr(G.field(a)[0], g[f"it{it}/{a}"], floor=1e-9) < 1e-9, (it, a)  # measured <= 2e-11
+    assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-9
+    assert relerr(np.array(G.metrics["kl_term"])[:, 0], g["kl_terms"]) < 1e-9
 
 
 @pytest.mark.parametrize("env,Q,R,alpha,xs,T", [
@@ -152,8 +186,10 @@ def test_linearize_nonlinear_envs(i2c_b200, env, Q, R, alpha, xs, T):
         G.learn(1)
         ref.learn_msgs()
         assert np.all(G.status()[0] == 0), (it, G.status())
-        for a, tol in [("mu_xu1_f", 1e-6), ("sig_xu1_f", 1e-5), ("mu_x3_f", 1e-6), ("sig_x3_f", 1e-5), ("mu_xu0_m", 1e-6),
-                       ("sig_xu0_m", 1e-5), ("mu_z0_m", 1e-6), ("sig_z0_m", 1e-5), ("K", 1e-4), ("k", 1e-4), ("sigK", 1e-5)]:
+        # PARITY UNPINNED (autograd absent): the oracle takes the dynamics Jacobians by central differences
+        # (truncation + round-off ~1e-9 on the Jacobian), the kernel by forward-mode AD; measured 2.7e-8 on the gains
+        for a, tol in [("mu_xu1_f", 1e-8), ("sig_xu1_f", 1e-7), ("mu_x3_f", 1e-8), ("sig_x3_f", 1e-7), ("mu_xu0_m", 1e-8),
+                       ("sig_xu0_m", 1e-7), ("mu_z0_m", 1e-8), ("sig_z0_m", 1e-7), ("K", 3e-7), ("k", 3e-7), ("sigK", 1e-7)]:
             assert relerr(G.field(a), ref.stack(a), floor=1e-6) < tol, (it, a)
-        assert relerr(G.alpha, ref.alpha) < 1e-6
-    assert relerr(np.array(G.metrics["cost_m"]), np.array(ref.costs_m)) < 1e-6
+        assert relerr(G.alpha, ref.alpha) < 1e-8
+    assert relerr(np.array(G.metrics["cost_m"]), np.array(ref.costs_m)) < 1e-8

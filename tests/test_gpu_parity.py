@@ -104,13 +104,20 @@ def compare_cells(G, ref, names, tol_s, tol_g, tag=""):
         assert e < (tol_g if a in GAINS else tol_s), (tag, a, e)
 
 
+# Tolerances = max(1e-9, ~10 x the measured error) per environment (north star: 1e-9 on means, covariances and gains).
+# States / covariances / sigK: 1e-9 everywhere (measured <= 1e-10).  Gains J_dyn, K, k are solves against covariances of
+# ~1e-5 whose inputs cancel (sum_p w x y^T - m m^T): the reference's own round-off floor grows with the
+# state dimension; measured CUDA-vs-oracle errors (profiles/r02_parity_floors.txt): pendulum 2e-10, cart-pole 3.5e-9,
+# double cart-pole 9e-9, linear minimum-energy 8.7e-9.
+TOL_GAIN = {"PendulumKnown": 2e-9, "CartpoleKnown": 2e-8, "DoubleCartpoleKnown": 5e-8, "LinearKnownMinimumEnergy": 5e-8,
+            "LinearKnown": 5e-8, "PendulumKnownActReg": 2e-8}
 CASES = [
     # env, B, T, Q, R, alpha, tol, x0 scale, sig_u, iters, tol_state, tol_gain
-    ("PendulumKnown", 96, 60, np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), 100.0, 0.0, [0.3, 0.5], 2.0, 4, 1e-9, 1e-7),
-    ("CartpoleKnown", 64, 50, np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0]), 80.0, 0.0, 0.05, 1.0, 3, 1e-9, 1e-6),
+    ("PendulumKnown", 96, 60, np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), 100.0, 0.0, [0.3, 0.5], 2.0, 4, 1e-9, 2e-9),
+    ("CartpoleKnown", 64, 50, np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0]), 80.0, 0.0, 0.05, 1.0, 3, 1e-9, 2e-8),
     ("DoubleCartpoleKnown", 40, 40, 1e-3 * np.diag([1.0, 1.0, 100.0, 1.0, 100.0, 10.0, 1.0, 1.0]), 1e-3 * np.diag([0.1]),
-     0.05, 0.99, 0.02, 1.0, 3, 1e-8, 1e-5),
-    ("LinearKnownMinimumEnergy", 33, 30, None, np.diag([1.0]), 10.0, 0.5, 0.3, 10.0, 3, 1e-10, 1e-7),
+     0.05, 0.99, 0.02, 1.0, 3, 1e-9, 5e-8),
+    ("LinearKnownMinimumEnergy", 33, 30, None, np.diag([1.0]), 10.0, 0.5, 0.3, 10.0, 3, 1e-10, 5e-8),
 ]
 
 
@@ -156,8 +163,9 @@ def test_fused_iterations_equal_single_steps(i2c_b200):
     assert np.array_equal(np.array(G1.metrics["cost_m"]), np.array(G2.metrics["cost_m"]))
 
 
-@pytest.mark.parametrize("name,tol_s,tol_g", [("pendulum_known_quad_seed0", 1e-9, 1e-7), ("pendulum_T200_x0pert", 1e-9, 1e-7),
-                                              ("cartpole_T120", 1e-9, 1e-6), ("double_cartpole_T80", 1e-8, 1e-5)])
+# against the unmodified reference (measured: pendulum 7.5e-11, cart-pole 1.3e-9, double cart-pole 3.1e-9 on the gains)
+@pytest.mark.parametrize("name,tol_s,tol_g", [("pendulum_known_quad_seed0", 1e-9, 1e-9), ("pendulum_T200_x0pert", 1e-9, 1e-9),
+                                              ("cartpole_T120", 1e-9, 1e-8), ("double_cartpole_T80", 1e-9, 3e-8)])
 def test_em_against_reference_golden(i2c_b200, name, tol_s, tol_g):
     """B = 1 CUDA run against per-cell dumps of the unmodified reference."""
     g = golden(name)
@@ -177,13 +185,13 @@ def test_em_against_reference_golden(i2c_b200, name, tol_s, tol_g):
     assert np.all(G.status()[0] == 0)
     al = np.array([a[0] for a in G.alphas])
     # alpha schedule: bitwise where the ratio clip binds, else to round-off amplification
-    assert relerr(al, g["alphas"]) < 1e-8
-    assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-8
+    assert relerr(al, g["alphas"]) < 1e-9
+    assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-9
     K, k, sk = G.get_local_linear_policy()
-    assert relerr(K[0], g["final/K"], 1e-6) < 10 * tol_g
-    assert relerr(k[0], g["final/k"], 1e-6) < 10 * tol_g
-    assert relerr(sk[0], g["final/sigK"]) < 10 * tol_s
-    assert relerr(G.field("mu_xu0_m")[0], g["final/mu_xu0_m"]) < 100 * tol_s
+    assert relerr(K[0], g["final/K"], 1e-6) < tol_g
+    assert relerr(k[0], g["final/k"], 1e-6) < tol_g
+    assert relerr(sk[0], g["final/sigK"]) < tol_s
+    assert relerr(G.field("mu_xu0_m")[0], g["final/mu_xu0_m"]) < tol_s
 
 
 def test_em_general_cubature_parameters(i2c_b200):
@@ -205,5 +213,5 @@ def test_em_general_cubature_parameters(i2c_b200):
         G.learn(1)
         ref.learn_msgs()
         assert np.all(G.status()[0] == 0)
-        compare_cells(G, ref, FIELDS_F + FIELDS_B, 1e-9, 1e-6, tag=f"it{it}")
+        compare_cells(G, ref, FIELDS_F + FIELDS_B, 1e-9, 3e-8, tag=f"it{it}")  # measured 3.2e-9
     assert relerr(G.alpha, ref.alpha) < 1e-10

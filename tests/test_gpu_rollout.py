@@ -65,3 +65,21 @@ def test_rollout_device_rng_statistics(i2c_b200):
     assert np.allclose(np.diag(cov), np.diag(e.sig_eta), rtol=0.1)
     nf = i2c_b200.rollout(env, x_init, K, k, sig_eta=np.zeros((2, 2)))[0]
     assert np.ptp(nf[:, :, 1, 0]) == 0.0
+
+
+@pytest.mark.parametrize("tag", ["det_env_det_pol", "noisy_env_det_pol", "noisy_env_noisy_pol", "expert_soft", "expert_hard"])
+@pytest.mark.parametrize("env", ["PendulumKnown", "CartpoleKnown"])
+def test_rollout_vs_reference_sim_golden(i2c_b200, env, tag):
+    """The CUDA roll-out against the reference's own BaseSim.run (rollout_kat.npz: seeded global RNG, realised
+    disturbances logged and fed to the kernel)."""
+    from conftest import golden
+    from test_oracle_rollout import golden_case
+
+    g = golden("rollout_kat")
+    T, x_init, K, k, eta, kw = golden_case(g, env, tag)
+    if "soft" in kw:
+        kw["soft_expert"] = kw.pop("soft")
+    xu, z, zt = i2c_b200.rollout(env, x_init, K, k, eta=eta, **kw)
+    assert relerr(xu[0, 0], g[f"{env}/{tag}/xt"]) < 1e-10
+    assert relerr(z[0, 0], g[f"{env}/{tag}/zt"]) < 1e-10
+    assert relerr(zt[0, 0], g[f"{env}/{tag}/z_term"].reshape(-1)) < 1e-10

@@ -20,9 +20,12 @@ def graph_from_golden(m, g, B=1, **kw):
                         enable_aux=True, **kw)
 
 
-@pytest.mark.parametrize("name,tol_s,tol_g", [("pendulum_actreg_covctrl_T100", 5e-8, 1e-6),
-                                              ("double_cartpole_covctrl_T50", 1e-8, 1e-5),
-                                              ("pendulum_propagate_expert_T50", 1e-9, 1e-7)])
+# tolerances = max(1e-9, ~10 x measured).  pendulum_actreg_covctrl: cost on u only, alpha = 300, T = 100 with covariance
+# control -- the reference's own restatement (oracle, same LAPACK) only reproduces this golden to 2e-9 (tests/
+# test_oracle_golden.py); measured here: states 7.7e-9, gains 3.6e-9.  double cart-pole: 3e-10 / 4.5e-9.  pendulum expert: 2e-10.
+@pytest.mark.parametrize("name,tol_s,tol_g", [("pendulum_actreg_covctrl_T100", 5e-8, 5e-8),
+                                              ("double_cartpole_covctrl_T50", 3e-9, 5e-8),
+                                              ("pendulum_propagate_expert_T50", 1e-9, 3e-9)])
 def test_propagate_and_covariance_control_golden(i2c_b200, name, tol_s, tol_g):
     """nonlinear_covariance_control.py:81-115 flow against the unmodified reference (B = 1)."""
     capi = i2c_b200.capi
@@ -42,17 +45,17 @@ def test_propagate_and_covariance_control_golden(i2c_b200, name, tol_s, tol_g):
             assert e < (tol_g if a in GAINS else tol_s), (it, a, e)
     G.learn(n_total - n_dump)
     m = G.metrics
-    assert relerr(np.array(G.alphas)[:, 0], g["alphas"]) < 10 * tol_s
+    assert relerr(np.array(G.alphas)[:, 0], g["alphas"]) < tol_s
     for mine, ref in [("alpha_desired", "alphas_desired"), ("alpha_pf", "alphas_pf"), ("cost_m", "costs_m"),
                       ("cost_m_var", "costs_m_var"), ("cost_pf", "costs_pf"), ("cost_pf_var", "costs_pf_var"),
                       ("cost_pf_min", "cost_pf_min"), ("policy_entropy", "policy_entropy"),
                       ("x_prior_entropy", "x_prior_entropy"), ("propagate_entropy", "propagate_entropy")]:
         r = g[ref][1:] if ref.startswith("alphas") else g[ref]
-        assert relerr(np.array(m[mine])[:, 0], r) < 100 * tol_s, mine
+        assert relerr(np.array(m[mine])[:, 0], r) < 2 * tol_s, mine
     if "kl_terms" in g.files:
-        assert relerr(np.array(m["kl_term"])[:, 0], g["kl_terms"]) < 1000 * tol_s
+        assert relerr(np.array(m["kl_term"])[:, 0], g["kl_terms"]) < 2 * tol_s
     K, k, sk = G.get_local_linear_policy()
-    assert relerr(K[0], g["final/K"], 1e-6) < 10 * tol_g and relerr(k[0], g["final/k"], 1e-6) < 10 * tol_g
+    assert relerr(K[0], g["final/K"], 1e-6) < tol_g and relerr(k[0], g["final/k"], 1e-6) < tol_g
 
 
 def test_covariance_control_batched_vs_oracle(i2c_b200):
