@@ -1,14 +1,14 @@
 """Randomised parity sweep (the former tools/stress_parity.py, now part of `-m gpu`): seeds x environments x both kernel
 families against the oracle, long horizons (T = 200 / 120 / 60) and 10 EM iterations, random batch sizes.  Tolerances:
-tests/test_gpu_parity.py: TOL_GAIN (gains) and 1e-9 (means, covariances), relaxed by the factor the error grows over ten
-alpha-coupled iterations (measured, profiles/r02_parity_floors.txt)."""
+max(1e-9, ~10 x measured) per environment (profiles/r02_parity_floors.txt): ten alpha-coupled EM iterations of the pendulum
+swing-up over T = 200 amplify round-off to 3e-9 on the states (cart-pole / double cart-pole stay at 1e-11 / 4e-11)."""
 import os
 
 import numpy as np
 import pytest
 
 from conftest import relerr
-from test_gpu_parity import TOL_GAIN, i2c_b200  # noqa: F401
+from test_gpu_parity import i2c_b200  # noqa: F401
 from tools_inputs import HYP
 
 pytestmark = pytest.mark.gpu
@@ -17,8 +17,9 @@ FIELDS = ["mu_xu1_f", "sig_xu1_f", "mu_xu0_m", "sig_xu0_m", "K", "k", "sigK"]
 GAINS = ("K", "k")
 HORIZON = {"PendulumKnown": 200, "CartpoleKnown": 120, "DoubleCartpoleKnown": 60}
 ITERS = 10
-# growth of the error over 10 iterations relative to the 3-iteration cases of test_gpu_parity.py (measured)
-GROWTH_STATE, GROWTH_GAIN = 10.0, 10.0
+# measured worst errors over the sweep: states 3.2e-9 / 7e-12 / 4e-11, gains 1.7e-9 / 4.3e-10 / 4.9e-9
+TOL_STATE = {"PendulumKnown": 3e-8, "CartpoleKnown": 1e-9, "DoubleCartpoleKnown": 1e-9}
+TOL_GAINS = {"PendulumKnown": 2e-8, "CartpoleKnown": 5e-9, "DoubleCartpoleKnown": 5e-8}
 
 
 @pytest.mark.parametrize("seed", range(4))
@@ -51,7 +52,7 @@ def test_random_batches_long_horizon(i2c_b200, env, seed):
         assert np.all(G.status()[0] == 0), (grp, G.status())
         for f in FIELDS:
             err = relerr(G.field(f), ref.stack(f), floor=1e-6 if f in GAINS else 0.0)
-            tol = GROWTH_GAIN * TOL_GAIN[env] if f in GAINS else GROWTH_STATE * 1e-9
+            tol = TOL_GAINS[env] if f in GAINS else TOL_STATE[env]
             assert err < tol, (env, seed, grp, f, err)
         assert relerr(G.alpha, ref.alpha) < 1e-9
         assert relerr(np.array(G.metrics["cost_m"]), np.array(ref.costs_m)) < 1e-8
