@@ -556,7 +556,7 @@ struct Worker {
   unsigned ztab_s, ftab_s;  // HOT: shared addresses of the [T][DZ] cell targets and the [T] {flags, index} table
 
   __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_, uint64_t* bars_)
-      : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_), bars(bars_), bar_phase(0), ring_q(0), ring_ready(false) {
+      : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_), bars(bars_), bar_phase(0), ring_q(0), ring_ready(false), ring_ready2(false) {
     bars_s = (unsigned)__cvta_generic_to_shared(bars_);
     stage_s = (unsigned)__cvta_generic_to_shared(stage_);
     status = I2C_OK;
@@ -641,7 +641,7 @@ struct Worker {
   static constexpr int RING = LY::RING, RSTRIDE = LY::E_STAGE;
   unsigned ring_q;  // cells produced / consumed so far: slot = q % RING, phase parity = (q / RING) & 1
   unsigned bars_s, stage_s;  // 32-bit shared addresses of bars[0] and of this lane's column of the staging area
-  bool ring_ready;  // early probe of the slot the next ring_acquire() will take (hides the mbarrier round trip)
+  bool ring_ready, ring_ready2;  // early probes of the slots the next two ring_acquire() calls take (hide the mbarrier round trip)
   __device__ __forceinline__ void ring_init() {  // one thread, before the block-wide barrier that precedes any use
 #pragma unroll
     for (int i = 0; i < RING; ++i) {
@@ -667,10 +667,12 @@ struct Worker {
   __device__ __forceinline__ unsigned ring_acquire() {  // -> slot index
     const unsigned s = ring_q % RING;
     if (!ring_ready) mbar_wait_s(bars_s + 8u * s, (ring_q / RING) & 1u);
-    // probe the NEXT cell's slot now: an mbarrier query takes ~100 cycles to come back, and the copy warp runs several
-    // cells ahead, so the answer (consumed by the next acquire) is almost always "ready"
-    const unsigned q1 = ring_q + 1;
-    ring_ready = mbar_test_s(bars_s + 8u * (q1 % RING), (q1 / RING) & 1u);
+    // probe the slot TWO cells ahead now: an mbarrier query takes ~100 cycles to come back (more than half an RTS-head
+    // cell), and the copy warp runs several cells ahead, so the answer -- consumed two acquires later -- is almost always
+    // "ready"
+    const unsigned q2 = ring_q + 2;
+    ring_ready = ring_ready2;
+    ring_ready2 = mbar_test_s(bars_s + 8u * (q2 % RING), (q2 / RING) & 1u);
     return s;
   }
   __device__ __forceinline__ void ring_release() {

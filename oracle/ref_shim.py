@@ -1,11 +1,12 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the UNMODIFIED upstream reference.
 
-This module makes ``/root/reference`` (pure Python/NumPy, written for NumPy<1.23,
-Python 3.7) importable on this image's NumPy 2.x without touching its sources
-(recipe: SURVEY.md Appendix C).  It is used only by ``tests/golden/make_golden.py``
-to generate the committed golden vectors and by the optional "live reference"
-oracle-pinning tests that are skipped when ``/root/reference`` is absent (it does
-not exist on the GPU box).  Nothing in the product path may import this file.
+This module makes the reference tree (``/root/reference`` in the build container, or its
+byte-for-byte copy ``oracle/_ref`` made by ``oracle/install_ref.py``, which is what travels to
+the GPU box) importable on this image's NumPy 2.x without touching its sources (recipe:
+SURVEY.md Appendix C).  Users: ``tests/golden/make_golden.py`` (golden vectors), the
+reference arm of ``bench.py`` (``--impl reference`` / ``cpu_baseline``: the reference's own
+``I2cGraph.learn_msgs`` timed on the host cores) and ``tests/test_dropin_scripts.py``.
+Nothing in the product path may import this file.
 
 What it does, before any ``import i2c``:
   1. restores the NumPy aliases the reference still uses
@@ -21,7 +22,19 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("I2C_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """$I2C_REFERENCE_ROOT, else the byte-for-byte copy oracle/install_ref.py put under oracle/_ref/ (the only one that
+    exists on the GPU box), else the build container's /root/reference."""
+    env = os.environ.get("I2C_REFERENCE_ROOT")
+    if env:
+        return env
+    local = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    if os.path.isdir(os.path.join(local, "i2c")) or not os.path.isdir("/root/reference/i2c"):
+        return local
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _default_root()
 
 
 class _Stub(types.ModuleType):
