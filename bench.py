@@ -405,11 +405,11 @@ def run_cuda(args, rank, world, local_rank):
         cores = os.cpu_count() or 1
         kind = cpu_kind()
         if kind == "reference":
-            # ~15 s per core: 4 problems x (1 + 5) iterations x T at ~1.2e3 updates/s/core
-            rate, dt, wall, sample = cpu_rate("reference", B, T, 5, 1, 4, cores)
+            # ~15-25 s per core: 8 problems x (1 + 10) iterations x T at 1-2e3 updates/s/core
+            rate, dt, wall, sample = cpu_rate("reference", B, T, 10, 1, 8, cores)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
                                     "seconds": wall}
-        prate, pdt, pwall, psample = cpu_rate("port", B, T, 8, 1, 64, cores)
+        prate, pdt, pwall, psample = cpu_rate("port", B, T, 20, 1, 64, cores)
         port = {"value": prate, "unit": UNIT, "cores": cores, "kind": "port", "sample": psample, "seconds": pwall}
         if kind == "reference":
             line["cpu_baseline_port"] = port
