@@ -17,6 +17,8 @@ from i2c_b200 import capi
 from i2c.exp_types import CubatureQuadrature, GaussHermiteQuadrature, Linearize
 from i2c.inference.quadrature import QuadratureInference
 
+PLOT_TIKZ = False  # i2c/i2c.py:18 (imported by scripts/lqr_compare.py:12, nonlinear_covariance_control.py:6)
+
 # cell attribute -> (device field, slicer); x = state block, u = action block of a joint quantity
 _VEC = {
     "mu_xu0_m": ("mu_xu0_m", None), "mu_xu1_m": ("mu_xu0_m", None), "mu_x0_m": ("mu_xu0_m", "x"), "mu_u0_m": ("mu_xu0_m", "u"),

@@ -79,6 +79,47 @@ class KnownModel(object):
         return self._in_kernel()
 
 
+class BaseModel(object):
+    """Interface of the reference's model base class (i2c/model.py:47-150) as far as the known-model path uses it."""
+
+    model = None
+    data_driven = False
+
+    def init(self):
+        return np.asarray(self.x0, float).squeeze(), self.sig_x0
+
+    def observe_terminal_x(self, x):
+        return self.observe_terminal(x)
+
+    def calibrate_epistemic(self, y):
+        assert self.model is None, self.model
+
+    def save(self, path):
+        print("Known model, no saving")
+
+
+class BaseModelKnown(BaseModel):
+    """Base of the known models (i2c/model.py:146-175): mixed with an environment definition, e.g.
+    ``class QuadrotorKnown(QuadrotorDef, BaseModelKnown)`` (mpc_quad.py:386).  I2cGraph, QuadratureInference and the MPC
+    policies take the constants from the definition part and run the maps of the matching in-kernel environment
+    (env_def.BaseDef._b200_env); ``forward`` exists for API compatibility and evaluates the definition's own NumPy
+    ``dynamics`` if it has one (host-side simulation in the scripts), never on the inference path."""
+
+    data_driven = False
+
+    def __init__(self, model=None, model_def=None):
+        assert model is None
+        assert model_def is None
+        super().__init__()
+
+    def forward(self, xu):
+        _x = self.dynamics(xu)
+        return _x, np.repeat(self.sig_eta[None, :, :], xu.shape[0], axis=0)
+
+    def predict(self, xu):
+        return self.dynamics(xu)
+
+
 _LOOKUP = {  # i2c/model.py:25-36
     "LinearKnown": "LinearKnown",
     "LinearKnownMinimumEnergy": "LinearKnownMinimumEnergy",

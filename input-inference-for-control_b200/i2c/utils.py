@@ -12,8 +12,72 @@ def set_seed(seed):
     np.random.seed(seed)
 
 
+DATETIME = __import__("datetime").datetime.now().strftime("%Y-%m-%d-%H-%M-%S")
+
+
+def make_results_folder(config, seed, name, folder_name="_results", release=False):
+    """`_results/<release|timestamp>_<config>_<seed>_<name>` (i2c/utils.py:355-366)."""
+    import os
+
+    parts = [config.replace(" ", "-"), str(seed), name.replace(" ", "-")]
+    res_dir = os.path.join(folder_name, "_".join((["release"] if release else [DATETIME]) + parts))
+    os.makedirs(res_dir, exist_ok=True)
+    return res_dir
+
+
+def configure_plots():
+    """Plot styling of the reference (i2c/utils.py:369-377); a no-op without matplotlib (plotting is outside the path)."""
+    try:
+        import matplotlib
+
+        matplotlib.rcParams["font.family"] = "serif"
+        matplotlib.rcParams["figure.figsize"] = [16, 16]
+        matplotlib.rcParams["legend.fontsize"] = 16
+        matplotlib.rcParams["axes.titlesize"] = 22
+        matplotlib.rcParams["axes.labelsize"] = 22
+    except Exception:
+        pass
+
+
+def covariance_2d(covar, mean, axis, n_std=2.0, facecolor="b", **kwargs):
+    """n_std ellipse of a 2-D Gaussian added to a matplotlib axis (i2c/utils.py:380-397)."""
+    w, v = np.linalg.eig(np.asarray(covar, float))
+    width = 2 * n_std * np.sqrt(w)
+    assert not np.any(np.isnan(width))
+    theta = np.rad2deg(-np.arctan2(v[0, 1], v[0, 0]))
+    try:
+        from matplotlib.patches import Ellipse
+
+        return axis.add_patch(Ellipse(xy=np.asarray(mean).squeeze(), width=width[0], height=width[1], angle=theta,
+                                      edgecolor=facecolor, facecolor="none", **kwargs))
+    except Exception:
+        return None
+
+
+def write_commit(res_dir):
+    """git_commit.txt with the current revision (i2c/utils.py:423-430); skipped outside a git checkout."""
+    import os
+    import subprocess
+
+    try:
+        sha = subprocess.check_output(["git", "rev-parse", "HEAD"], stderr=subprocess.DEVNULL, text=True).strip()
+    except Exception:
+        sha = "unknown"
+    with open(os.path.join(res_dir, "git_commit.txt"), "w+") as f:
+        f.write(sha)
+
+
 def setup_logger(res_dir=None, level=logging.INFO):
-    logging.basicConfig(level=level)
+    """i2c/utils.py:400-408: log into <res_dir>/output.log (console when no folder is given)."""
+    import os
+
+    for handler in logging.root.handlers[:]:
+        logging.root.removeHandler(handler)
+    if res_dir:
+        logging.basicConfig(filename=os.path.join(res_dir, "output.log"), level=level,
+                            format="[%(asctime)s] %(pathname)s:%(lineno)d %(levelname)s- %(message)s")
+    else:
+        logging.basicConfig(level=level)
     return logging.getLogger()
 
 

@@ -58,10 +58,15 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "i2c"))
 
 
-def install():
-    """Idempotently install aliases, stubs and sys.path entries."""
+def install(paths=True, extra_stubs=()):
+    """Idempotently install aliases, stubs and (paths=True) the sys.path entries that make ``import i2c`` resolve to the
+    REFERENCE.  paths=False only installs the NumPy aliases and the stubs: used by tests/test_dropin_scripts.py to run the
+    reference's scripts against this repo's ``i2c`` package instead."""
     if not available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    for name in extra_stubs:
+        if name not in sys.modules:
+            sys.modules[name] = _Stub(name)
     if not hasattr(np, "asscalar"):
         np.asscalar = lambda a: np.asarray(a).item()
     if not hasattr(np, "NINF"):
@@ -112,9 +117,10 @@ def install():
         nd.Jacobian = Jacobian
         sys.modules["numdifftools"] = nd
 
-    for p in (os.path.join(REFERENCE_ROOT, "scripts"), REFERENCE_ROOT):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    if paths:
+        for p in (os.path.join(REFERENCE_ROOT, "scripts"), REFERENCE_ROOT):
+            if p not in sys.path:
+                sys.path.insert(0, p)
 
 
 def _purge(prefixes):
