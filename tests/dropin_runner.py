@@ -94,17 +94,26 @@ def setup(impl):
     return ref
 
 
+DUMP = {}
+
+
 def capture_graphs():
     import i2c.i2c as mod
 
     made = []
     orig = mod.I2cGraph.__init__
+    orig_close = mod.I2cGraph.close
 
     def init(self, *a, **k):
         orig(self, *a, **k)
         made.append(self)
 
+    def close(self):  # scripts/i2c_run.py:160 closes the graph: take the dump first (the mirror frees the device state)
+        graph_dump(self, DUMP, f"g{made.index(self)}")
+        return orig_close(self)
+
     mod.I2cGraph.__init__ = init
+    mod.I2cGraph.close = close
     # figures are outside the path, and the reference's own plot_traj raises on the Linearize path (mu_xu0_f_prev is never
     # set there: SURVEY.md section 2 "known-broken reference code"): no-ops on both sides (the mirror's already are)
     for name in dir(mod.I2cGraph):
@@ -204,7 +213,9 @@ def main():
         d["cost"] = np.load(os.path.join(res, "i2c_FB_low_3.npy"))
     d["n_graphs"] = len(made)
     for i, g in enumerate(made):
-        graph_dump(g, d, f"g{i}")
+        if f"g{i}/alphas" not in DUMP:
+            graph_dump(g, DUMP, f"g{i}")
+    d.update(DUMP)
     np.savez(a.out, **d)
     print("dropin_runner: ok", a.impl, a.script, "graphs:", len(made))
 
