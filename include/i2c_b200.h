@@ -203,6 +203,9 @@ int i2c_synchronize(i2c_handle_t h);
 /* Per-iteration scalars of the last i2c_run: out[n_iter][B]. */
 int i2c_get_metric(i2c_handle_t h, int32_t metric, double* out, int32_t n_iter);
 int i2c_get_status(i2c_handle_t h, int32_t* status /*[B]*/, int32_t* info /*[B]: (iter<<16 | cell)*/);
+/* The per-problem status / info words are sticky (the kernels only write them while they are OK): clear them, e.g. after the
+ * caller handled a failure (the reference raises LinAlgError once, quadrature.py:17-24; a later sweep starts clean). */
+int i2c_clear_status(i2c_handle_t h);
 
 /* Cell-attribute views (the attributes scripts read off `i2c.cells[t]`), cells [t0, t1). */
 int i2c_get_field(i2c_handle_t h, int32_t field, int32_t t0, int32_t t1, double* out);

@@ -80,6 +80,21 @@ static int set_err(int code, const std::string& msg) {
     if (!(c)) return set_err(-1, msg); \
   } while (0)
 
+// Every entry point that takes a handle runs on the handle's device, whatever device is current in the calling thread
+// (a second handle on another GPU, or torch switching devices), and restores the caller's device on return.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct EnvDims {
   int dx, du, dz, dzt, np, dy;
 };
@@ -436,6 +451,7 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
 
 int i2c_destroy(i2c_handle_t h) {
   if (!h) return 0;
+  DeviceGuard device_guard_(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamDestroy(h->copy_stream);
@@ -658,6 +674,7 @@ extern "C" {
 
 static int set_initial_state_impl(i2c_handle_t h, const double* x0, const double* sig_x0, bool sync) {
   REQUIRE(h && x0 && sig_x0, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   FieldMap fx{h->d.dx, 0, 0, h->d.dx, 1, 0, 0, 0};
   int rc = pack(h, h->x0, fx, 0, 1, x0, false, 0, false);
   if (rc) return rc;
@@ -675,6 +692,9 @@ int i2c_set_initial_state_async(i2c_handle_t h, const double* x0, const double* 
 
 int i2c_set_initial_state_dev(i2c_handle_t h, const double* x0_dev, const double* sig_x0_dev) {
   REQUIRE(h && x0_dev && sig_x0_dev, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
+  DeviceGuard device_guard_(h->cfg.device);
+  DeviceGuard device_guard_(h->cfg.device);
   FieldMap fx{h->d.dx, 0, 0, h->d.dx, 1, 0, 0, 0};
   size_t total = (size_t)h->Bpad * h->d.dx;
   pack_kernel<<<nblocks(total), 256, 0, h->stream>>>(h->x0, fx, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles, x0_dev, 0);
@@ -688,6 +708,7 @@ int i2c_set_initial_state_dev(i2c_handle_t h, const double* x0_dev, const double
 
 int i2c_get_initial_state(i2c_handle_t h, double* x0, double* sig_x0) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   int rc = 0;
   if (x0) {
     FieldMap fx{h->d.dx, 0, 0, h->d.dx, 1, 0, 0, 0};
@@ -706,6 +727,7 @@ int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, cons
                     const double* z_term, const double* alpha0, double alpha_update_tol, const double* mu_x_term,
                     const double* sig_x_term, double dtemp, const double* env_par) {
   REQUIRE(h && x0 && sig_x0 && sig_eta && mu_u && sig_u && QR && z && z_graph && alpha0, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   const int dx = h->d.dx, du = h->d.du, n = dx + du, dz = h->d.dz, dzt = h->d.dzt, T = h->T;
   REQUIRE(h->d.np == 0 || env_par != nullptr, "this env needs per-problem parameters (env_par)");
   REQUIRE((mu_x_term == nullptr) == (sig_x_term == nullptr), "covariance control needs both mu_x_term and sig_x_term");
@@ -811,26 +833,31 @@ int i2c_set_problem(i2c_handle_t h, const double* x0, const double* sig_x0, cons
 
 int i2c_set_cell_flags(i2c_handle_t h, const int32_t* flags) {
   REQUIRE(h && flags, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   for (int t = 0; t < h->T; ++t) h->flags[(t + h->cell_head) % h->T] = flags[t];
   return upload_flags(h);
 }
 int i2c_get_cell_flags(i2c_handle_t h, int32_t* flags) {
   REQUIRE(h && flags, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   for (int t = 0; t < h->T; ++t) flags[t] = h->flags[(t + h->cell_head) % h->T];
   return 0;
 }
 int i2c_set_cell_index(i2c_handle_t h, const int32_t* index) {
   REQUIRE(h && index, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   for (int t = 0; t < h->T; ++t) h->index[(t + h->cell_head) % h->T] = index[t];
   return upload_flags(h);
 }
 int i2c_set_tau(i2c_handle_t h, int32_t tau) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   h->tau = tau;
   return 0;
 }
 int i2c_set_cell_targets(i2c_handle_t h, const double* z) {
   REQUIRE(h && z, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   const int dz = h->d.dz, T = h->T;
   if (h->cfg.z_per_problem) {
     FieldMap fz{dz, 0, 0, dz, 1, 0, 0, 1};
@@ -846,6 +873,7 @@ int i2c_set_cell_targets(i2c_handle_t h, const double* z) {
 
 int i2c_set_alpha(i2c_handle_t h, const double* alpha) {
   REQUIRE(h && alpha, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   FieldMap fa{1, 0, 0, 1, 1, 0, 0, 0};
   int rc = pack(h, h->alpha, fa, 0, 1, alpha, false);
   if (rc) return rc;
@@ -854,17 +882,20 @@ int i2c_set_alpha(i2c_handle_t h, const double* alpha) {
 }
 int i2c_get_alpha(i2c_handle_t h, double* alpha) {
   REQUIRE(h && alpha, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   CUDA_OK(cudaMemcpyAsync(alpha, h->alpha, (size_t)h->B * 8, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 int i2c_set_temp(i2c_handle_t h, double temp) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   h->temp = temp;
   return 0;
 }
 int i2c_get_temp(i2c_handle_t h, double* temp) {
   REQUIRE(h && temp, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   *temp = h->temp;
   return 0;
 }
@@ -926,6 +957,7 @@ static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
 
 int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   REQUIRE(h->problem_set, "i2c_set_problem has not been called");
   REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "n_iter must be in [1, max_iters]");
   REQUIRE(!(phases & I2C_PH_STORE_AUX) || h->cfg.enable_aux, "I2C_PH_STORE_AUX needs enable_aux=1");
@@ -970,6 +1002,7 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
 // machine as i2c_run(FORWARD | BACKWARD [| MSTEP] [| UPDATE_PRIORS] [| STORE_AUX]).
 int i2c_run_scan(i2c_handle_t h, int32_t n_iter, int32_t phases, int32_t chunk_cells) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   REQUIRE(h->problem_set, "i2c_set_problem has not been called");
   REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "n_iter must be in [1, max_iters]");
   REQUIRE(!(phases & I2C_PH_STORE_AUX) || h->cfg.enable_aux, "I2C_PH_STORE_AUX needs enable_aux=1");
@@ -1054,12 +1087,14 @@ int i2c_run_scan(i2c_handle_t h, int32_t n_iter, int32_t phases, int32_t chunk_c
 
 int i2c_synchronize(i2c_handle_t h) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
 int i2c_get_metric(i2c_handle_t h, int32_t metric, double* out, int32_t n_iter) {
   REQUIRE(h && out, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   REQUIRE(metric >= 0 && metric < I2C_M_COUNT, "unknown metric id");
   REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "bad n_iter");
   const double* src = h->metrics + (size_t)metric * h->cfg.max_iters * h->Bpad;
@@ -1071,14 +1106,24 @@ int i2c_get_metric(i2c_handle_t h, int32_t metric, double* out, int32_t n_iter) 
 
 int i2c_get_status(i2c_handle_t h, int32_t* status, int32_t* info) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   if (status) CUDA_OK(cudaMemcpyAsync(status, h->status, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
   if (info) CUDA_OK(cudaMemcpyAsync(info, h->info, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
+int i2c_clear_status(i2c_handle_t h) {
+  REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
+  CUDA_OK(cudaMemsetAsync(h->status, 0, (size_t)h->Bpad * 4, h->stream));
+  CUDA_OK(cudaMemsetAsync(h->info, 0, (size_t)h->Bpad * 4, h->stream));
+  return 0;
+}
+
 int i2c_field_shape(i2c_handle_t h, int32_t field, int32_t* rows, int32_t* cols) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   FieldMap f;
   double* base = nullptr;
   // shape queries must work without aux buffers
@@ -1097,6 +1142,7 @@ int i2c_field_shape(i2c_handle_t h, int32_t field, int32_t* rows, int32_t* cols)
 
 int i2c_get_field(i2c_handle_t h, int32_t field, int32_t t0, int32_t t1, double* out) {
   REQUIRE(h && out, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   FieldMap f;
   double* base;
   int rc = field_map(h, field, &f, &base);
@@ -1111,6 +1157,7 @@ int i2c_get_field(i2c_handle_t h, int32_t field, int32_t t0, int32_t t1, double*
 
 int i2c_set_field(i2c_handle_t h, int32_t field, int32_t t0, int32_t t1, const double* in) {
   REQUIRE(h && in, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   FieldMap f;
   double* base;
   int rc = field_map(h, field, &f, &base);
@@ -1125,6 +1172,7 @@ int i2c_set_field(i2c_handle_t h, int32_t field, int32_t t0, int32_t t1, const d
 
 int i2c_get_policy(i2c_handle_t h, double* K, double* k, double* sigK) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   int rc = 0;
   if (K && (rc = i2c_get_field(h, I2C_F_K, 0, h->T, K))) return rc;
   if (k && (rc = i2c_get_field(h, I2C_F_KK, 0, h->T, k))) return rc;
@@ -1134,6 +1182,7 @@ int i2c_get_policy(i2c_handle_t h, double* K, double* k, double* sigK) {
 
 int i2c_get_policy_dev(i2c_handle_t h, double* K_dev, double* k_dev, double* sigK_dev) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   const int fields[3] = {I2C_F_K, I2C_F_KK, I2C_F_SIGK};
   double* outs[3] = {K_dev, k_dev, sigK_dev};
   for (int i = 0; i < 3; ++i) {
@@ -1152,6 +1201,7 @@ int i2c_get_policy_dev(i2c_handle_t h, double* K_dev, double* k_dev, double* sig
 
 int i2c_get_policy_async(i2c_handle_t h, double* K, double* k, double* sigK) {
   REQUIRE(h && K && k && sigK, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   const size_t BT = (size_t)h->B * h->T, nK = BT * h->d.du * h->d.dx, nk = BT * h->d.du, ns = BT * h->d.du * h->d.du;
   // the previous asynchronous copy must have drained before its device staging buffer is overwritten
   if (h->copy_pending) CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
@@ -1179,6 +1229,7 @@ int i2c_get_policy_async(i2c_handle_t h, double* K, double* k, double* sigK) {
 
 int i2c_copy_wait(i2c_handle_t h) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   if (h->copy_pending) CUDA_OK(cudaEventSynchronize(h->ev_copied));
   h->copy_pending = false;
   return 0;
@@ -1186,6 +1237,7 @@ int i2c_copy_wait(i2c_handle_t h) {
 
 int i2c_get_first_action(i2c_handle_t h, double* mu_u, double* sig_u) {
   REQUIRE(h, "NULL handle");
+  DeviceGuard device_guard_(h->cfg.device);
   const int dx = h->d.dx, du = h->d.du, n = dx + du;
   int rc = 0;
   if (mu_u) {
@@ -1202,6 +1254,7 @@ int i2c_get_first_action(i2c_handle_t h, double* mu_u, double* sig_u) {
 
 int i2c_shift_horizon(i2c_handle_t h, const double* z_new, const double* mu_u_init, double alpha_init) {
   REQUIRE(h && z_new && mu_u_init, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   const int dx = h->d.dx, du = h->d.du, n = dx + du, dz = h->d.dz, T = h->T;
   // cells.pop(0): advance the ring; the freed slot becomes the new last cell
   h->cell_head = (h->cell_head + 1) % T;
@@ -1237,6 +1290,7 @@ static int ckf_step_impl(i2c_handle_t h, const double* y, const double* u, const
 int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const double* u_prev, const double* sig_zeta,
                  int32_t n_iter, const double* z_new, const double* mu_u_init, double alpha_init, double* u_out) {
   REQUIRE(h && z_new && mu_u_init && u_out, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   REQUIRE(!h->cfg.z_per_problem, "i2c_mpc_step expects shared cell targets (z_per_problem = 0)");
   const int dx = h->d.dx, du = h->d.du, n = dx + du, dz = h->d.dz, T = h->T;
   REQUIRE(dz <= 16 && du <= 16, "internal: by-value setter too small");
@@ -1284,6 +1338,7 @@ int i2c_ckf_step(i2c_handle_t h, const double* y, const double* u, const double*
 // sync = false: the caller synchronises the stream before the borrowed host buffers go out of scope (i2c_mpc_step)
 static int ckf_step_impl(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta, bool sync) {
   REQUIRE(h && y && u && sig_zeta, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   REQUIRE(h->d.dy > 0, "this env defines no measurement map (only the quadrotor does)");
   const int dx = h->d.dx, du = h->d.du, dy = h->d.dy;
   // stage y and u in the scratch buffer in the caller's layout ([B][dy], [B][du]); the kernel reads them directly
@@ -1406,6 +1461,12 @@ static int quadrature_impl(int32_t env, int32_t fn, int32_t n_problems, const do
 }
 
 // ---- snapshot / restore: [host state blob][workspace bytes]
+// environment, inference kind, ABI version and batch size folded into one word of the snapshot header
+static int32_t snap_tag(i2c_handle_t h) {
+  return (int32_t)((((uint32_t)I2C_ABI_VERSION & 0xf) << 28) ^ (((uint32_t)h->cfg.env & 0xf) << 24) ^
+                   (((uint32_t)h->cfg.inference & 0xf) << 20) ^ ((uint32_t)h->B & 0xfffff));
+}
+
 struct SnapHeader {
   uint64_t magic, ws_bytes;
   int32_t prior_is_A, latest_is_A, cell_head, tau, last_n_iter, problem_set, T, pad;
@@ -1415,12 +1476,14 @@ struct SnapHeader {
 
 int i2c_snapshot_bytes(i2c_handle_t h, size_t* bytes) {
   REQUIRE(h && bytes, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   *bytes = sizeof(SnapHeader) + (size_t)h->T * 8 + 3 * 8 + h->ws_bytes;
   return 0;
 }
 
 int i2c_snapshot(i2c_handle_t h, void* host_buf, size_t bytes) {
   REQUIRE(h && host_buf, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   size_t need;
   i2c_snapshot_bytes(h, &need);
   REQUIRE(bytes >= need, "snapshot buffer too small");
@@ -1431,6 +1494,7 @@ int i2c_snapshot(i2c_handle_t h, void* host_buf, size_t bytes) {
   hd.prior_is_A = h->prior_is_A, hd.latest_is_A = h->latest_is_A, hd.cell_head = h->cell_head, hd.tau = h->tau;
   hd.last_n_iter = h->last_n_iter, hd.problem_set = h->problem_set, hd.T = h->T;
   hd.temp = h->temp, hd.dtemp = h->dtemp;
+  hd.pad = snap_tag(h);
   hd.kp = h->kp;
   char* p = (char*)host_buf;
   memcpy(p, &hd, sizeof(hd));
@@ -1450,12 +1514,16 @@ int i2c_snapshot(i2c_handle_t h, void* host_buf, size_t bytes) {
 
 int i2c_restore(i2c_handle_t h, const void* host_buf, size_t bytes) {
   REQUIRE(h && host_buf, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   REQUIRE(bytes >= sizeof(SnapHeader), "snapshot too small");
   SnapHeader hd;
   const char* p = (const char*)host_buf;
   memcpy(&hd, p, sizeof(hd));
   REQUIRE(hd.magic == 0x6932635f62323030ull && hd.ws_bytes == h->ws_bytes && hd.T == h->T,
           "snapshot does not match this handle's configuration");
+  REQUIRE(hd.pad == snap_tag(h), "snapshot was taken from a handle with another environment / inference / batch / ABI");
+  REQUIRE(bytes >= sizeof(SnapHeader) + (size_t)h->T * 8 + 3 * 8 + h->ws_bytes, "snapshot buffer is truncated");
+  REQUIRE(tri(h->d.du) <= 3, "internal: sig_u blob holds tri(du) <= 3 doubles");
   p += sizeof(hd);
   h->prior_is_A = hd.prior_is_A, h->latest_is_A = hd.latest_is_A, h->cell_head = hd.cell_head, h->tau = hd.tau;
   h->last_n_iter = hd.last_n_iter, h->problem_set = hd.problem_set != 0;
@@ -1622,12 +1690,14 @@ int i2c_dfma_peak(int32_t device, double* tflops) {
 
 int i2c_kernel_launches(i2c_handle_t h, int64_t* n) {
   REQUIRE(h && n, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   *n = h->launches;
   return 0;
 }
 
 int i2c_last_run_ms(i2c_handle_t h, float* ms) {
   REQUIRE(h && ms, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
   CUDA_OK(cudaEventSynchronize(h->ev1));
   CUDA_OK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return 0;

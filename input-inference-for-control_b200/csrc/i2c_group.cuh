@@ -1329,12 +1329,7 @@ static int launch_em_group(const KParams& p, cudaStream_t s) {
   constexpr int WPB = 2;
   constexpr int PPW = TILE / G;
   const size_t smem = (size_t)WPB * PPW * GroupLay<Env>::SIZE * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(em_group_kernel<Env, G, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  if (int e = allow_big_smem<em_group_kernel<Env, G, WPB>>()) return e;
   KParams q = p;
   q.stage_meta = 0;
   const int nwarps = p.ntiles * G;

@@ -2284,6 +2284,21 @@ struct Worker {
   __device__ void run() { run_impl<false>(0, 1, nullptr); }
 };
 
+// Opt a kernel in to > 48 KB of dynamic shared memory.  The attribute is per DEVICE: remembered per device ordinal (a
+// process-wide flag made the launch fail on every device after the first one).
+template <auto Kernel>
+static int allow_big_smem() {
+  static unsigned long long done = 0;  // one bit per device ordinal
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 64 && ((done >> dev) & 1ull)) return 0;
+  e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 64) done |= 1ull << dev;
+  return 0;
+}
+
 // MINB = minimum resident 128-thread blocks per SM: 1 lets ptxas use up to 255 registers (best per-warp latency,
 // used when the batch cannot fill the machine anyway); 4 caps the kernel at 128 registers so that 16 warps per SM
 // are resident (throughput regime, small envs only).
@@ -2326,12 +2341,7 @@ template <class Env, int W, bool HOT>
 static int launch_em_team_v(const KParams& p, cudaStream_t s) {
   // staging + mbarriers + reduction + progress counter (+ HOT: target / flag table of the horizon)
   const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars + 2 + (HOT ? (size_t)p.T * (Env::DZ + 1) : 0)) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(em_team_kernel<Env, W, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  if (int e = allow_big_smem<em_team_kernel<Env, W, HOT>>()) return e;
   KParams q = p;
   q.stage_meta = Lay<Env>::STAGED;
   em_team_kernel<Env, W, HOT><<<p.ntiles, W * TILE, smem, s>>>(q);
@@ -2348,12 +2358,7 @@ static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
   int wpb = threads / TILE;
   int blocks = (p.ntiles + wpb - 1) / wpb;
   const size_t smem = Lay<Env>::STAGED ? (size_t)wpb * (2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars) * sizeof(double) : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(em_kernel<Env, MINB, LAT, LIN, GH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  if (int e = allow_big_smem<em_kernel<Env, MINB, LAT, LIN, GH>>()) return e;
   KParams q = p;
   // staging the per-cell targets / flags removes their exposed load latency when a warp is alone on its
   // sub-partition; in the throughput regime the extra LDGSTS instructions cost more than they hide

@@ -280,6 +280,9 @@ class I2cGraph(object):
         if st[0] != 0:
             it, cell = int(info[0]) >> 16, int(info[0]) & 0xFFFF
             name = capi.STATUS_NAMES[st[0]]
+            # the device words are sticky: clear them so that a caller who catches the exception and repairs alpha / x0
+            # does not see this failure again on the next sweep (the reference raises once, at the failing call)
+            self._g.clear_status()
             msg = f"i2c failure {name} at EM iteration {it} of the call, cell {cell}"
             if name == "NAN_ALPHA":
                 raise ValueError("Alpha is NaN")
@@ -587,6 +590,10 @@ class I2cGraph(object):
 
     # ---- deepcopy / pickle: snapshot of the device state -------------------------------------------------
     def __getstate__(self):
+        # pending host-side cell edits (c.use_expert_controller = ..., c.z = ..., c.state_action_independence = ...) are
+        # pushed lazily at the next sweep: push them now so that the copy runs with what its cell objects report
+        if self._dirty_flags or self._dirty_targets:
+            self._push()
         self._pull_flags()
         d = {k: v for k, v in self.__dict__.items() if k not in ("_g", "_cache", "cells")}
         d["_snapshot"] = self._g.snapshot()

@@ -7,11 +7,31 @@ import numpy as np
 from i2c_b200 import envs as _envs
 
 
+# axis labels / units of the state-action and cost-feature components: read by the scripts' own plotting code
+# (e.g. nonlinear_covariance_control.py:63) -- data of the definitions, env_def.py:142-144, 237-239, 495-504, 619-639
+_LABELS = {
+    "LinearKnown": (["$x_1$", "$x_2$", "$u$"], None, [None] * 3),
+    "LinearKnownMinimumEnergy": (["$x_1$", "$x_2$", "$u$"], ["$u$"], [None] * 3),
+    "PendulumKnown": (["$\\theta$", "$\\dot{\\theta}$", "$u$"],
+                      ["$\\sin(\\theta)$", "$\\cos(\\theta)$", "$\\dot{\\theta}$", "$u$"], ["rad", "rad/s", "Nm"]),
+    "PendulumKnownActReg": (["$\\theta$", "$\\dot{\\theta}$", "$u$"], ["$u$"], ["rad", "rad/s", "Nm"]),
+    "CartpoleKnown": (["$x$", "$\\theta$", "$\\dot{x}$", "$\\dot{\\theta}$", "$u$"],
+                      ["$x$", "$\\sin(\\theta)$", "$\\cos(\\theta)$", "$\\dot{x}$", "$\\dot{\\theta}$", "$u$"],
+                      ["m", "rad", "m/s", "rad/s", "Nm"]),
+    "DoubleCartpoleKnown": (["$x$", "$\\theta_1$", "$\\theta_2$", "$\\dot{x}$", "$\\dot{\\theta}_1$", "$\\dot{\\theta}_2$", "$u$"],
+                            ["$x$", "$\\sin\\theta_1$", "$\\cos\\theta_1$", "$\\sin\\theta_2$", "$\\cos\\theta_2$", "$\\dot{x}$",
+                             "$\\dot{\\theta}_1$", "$\\dot{\\theta}_2$", "$u$"], ["m", "rad", "rad", "m/s", "rad/s", "rad/s", "Nm"]),
+    "Quadrotor": (["$x$", "$y$", "$\\psi$", "$\\dot{x}$", "$\\dot{y}$", "$\\dot{\\psi}$", "$u_1$", "$u_2$"], None, [None] * 8),
+}
+
+
 class KnownModel(object):
     data_driven = False
     model = None
 
     def __init__(self, env_name):
+        key, z_key, unit = _LABELS[env_name]
+        self.key, self.z_key, self.unit = list(key), list(z_key if z_key is not None else key), list(unit)
         c = _envs.make(env_name)
         self._b200_env = env_name
         self.name = env_name

@@ -1,5 +1,7 @@
 """i2c MPC controllers (mirror of i2c/policy/mpc.py) on the CUDA path: the planning graph stays on the device,
 the horizon shift is the O(1) ring rotation of ``i2c_shift_horizon`` instead of list pop/append + deepcopy."""
+import copy
+
 import numpy as np
 
 import i2c_b200
@@ -14,15 +16,30 @@ class MpcPolicy(object):
         self.model = i2c.sys
         self.n_iter = n_iter
         self.z_traj = None if z_traj is None else np.asarray(z_traj, float)
-        self._impl = i2c_b200.BatchedPartiallyObservedMpc(i2c._g, n_iter, sig_u, None, sig_zeta=None)
         if self.z_traj is not None:
             for i, c in enumerate(i2c.cells):
                 c.z = self.z_traj[i, :, None]
             self._z_last = self.z_traj[i2c.H - 1].copy()
         self.xu_history, self.z_history = [], []
+        self._snapshot_init = None  # device snapshot taken lazily by reset() users (i2c_init = deepcopy(i2c) upstream)
+        self.i2c_init = copy.deepcopy(i2c)  # policy/mpc.py:23
 
     def set_control(self, feedforward):
         self.i2c.tau = 0 if feedforward else self.i2c.H
+
+    def reset(self):
+        """policy/mpc.py:44-48: back to the graph the policy was built with."""
+        self.i2c.close()
+        self.i2c = copy.deepcopy(self.i2c_init)
+        self.model = self.i2c.sys
+        if self.z_traj is not None:
+            self._z_last = self.z_traj[self.i2c.H - 1].copy()
+        self.xu_history, self.z_history = [], []
+
+    def update_models(self, sys):
+        """policy/mpc.py:87-89 (the freshly appended cells take their constants from the graph's sys here)."""
+        self.i2c.sys = sys
+        self.model = sys
 
     def optimize(self, n_iter, x):
         assert x.shape == (self.dim_x, 1), f"{x.shape}, {(self.dim_x, 1)}"
@@ -47,6 +64,9 @@ class MpcPolicy(object):
 
     def __call__(self, i, x, deterministic=True):
         self.optimize(self.n_iter, x)
+        # policy/mpc.py:59.  In the reference this very call raises TypeError (compute_update_alpha takes no keyword
+        # arguments, i2c.py:921: SURVEY.md "known-broken reference code"); the intended alpha adaptation is done here.
+        self.i2c.compute_update_alpha(True, calc_evar=False, calc_propagate=False)
         self.xu_history.append(self.i2c.get_marginal_state_action())
         self.z_history.append(self.i2c.get_marginal_observed_trajectory()[0])
         mu, sig = self.i2c.cells[0].mu_u0_m.copy(), self.i2c.cells[0].sig_u0_m.copy()

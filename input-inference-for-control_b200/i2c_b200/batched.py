@@ -217,6 +217,10 @@ class BatchedI2c:
         capi.check(self.lib.i2c_get_status(self._h, capi.ptr(st), capi.ptr(info)))
         return st, info
 
+    def clear_status(self):
+        """Reset the (sticky) per-problem status / info words, e.g. after a failure has been handled."""
+        capi.check(self.lib.i2c_clear_status(self._h))
+
     def field(self, name, t0=0, t1=None):
         """Per-cell attribute for cells [t0, t1): [B, t1-t0, rows(, cols)] (vectors squeezed)."""
         fid = capi.FIELDS[name]
