@@ -693,8 +693,6 @@ int i2c_set_initial_state_async(i2c_handle_t h, const double* x0, const double* 
 int i2c_set_initial_state_dev(i2c_handle_t h, const double* x0_dev, const double* sig_x0_dev) {
   REQUIRE(h && x0_dev && sig_x0_dev, "NULL argument");
   DeviceGuard device_guard_(h->cfg.device);
-  DeviceGuard device_guard_(h->cfg.device);
-  DeviceGuard device_guard_(h->cfg.device);
   FieldMap fx{h->d.dx, 0, 0, h->d.dx, 1, 0, 0, 0};
   size_t total = (size_t)h->Bpad * h->d.dx;
   pack_kernel<<<nblocks(total), 256, 0, h->stream>>>(h->x0, fx, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles, x0_dev, 0);
