@@ -150,6 +150,24 @@ __device__ __forceinline__ int2 lds_i2_ro(unsigned addr_s) {
   asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr_s));
   return v;
 }
+// Progress counter of the team kernel (heads finished), in shared memory: published with a release exchange by one lane
+// after __syncwarp() (cumulative over the warp's record stores), polled with acquire loads by the helper warps.
+__device__ __forceinline__ void progress_publish(volatile int* prog, int v) {
+  int old;
+  asm volatile("atom.exch.release.cta.shared::cta.b32 %0, [%1], %2;"
+               : "=r"(old)
+               : "r"((unsigned)__cvta_generic_to_shared(const_cast<int*>(prog))), "r"(v)
+               : "memory");
+  (void)old;
+}
+__device__ __forceinline__ int progress_read(volatile int* prog) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];"
+               : "=r"(v)
+               : "r"((unsigned)__cvta_generic_to_shared(const_cast<int*>(prog)))
+               : "memory");
+  return v;
+}
 #ifdef I2C_NO_BULK
 constexpr bool kUseBulk = false;
 #else
@@ -2036,7 +2054,7 @@ struct Worker {
           const int r = PROD ? 4 : 7;
           const int nm = (T * (r - H)) / (r * (H + 1));
           n_main = nm > 0 ? nm : 0;
-          if (main_warp && lane == 0) *prog = 0;
+          if (main_warp && lane == 0) progress_publish(prog, 0);
           __syncthreads();  // forward sweep done; progress counter reset
         }
         if (main_warp) {
@@ -2061,16 +2079,14 @@ struct Worker {
               else frv = ring_view();
               // publish the PREVIOUS head here: its stores were issued a whole cell ago, so the fence does not wait for them
               // (fencing right after a cell's own stores cost ~90 cycles per cell)
-              asm volatile("fence.acq_rel.cta;" ::: "memory");
               __syncwarp();
-              if (lane == 0) *prog = T - 1 - t;
+              if (lane == 0) progress_publish(prog, T - 1 - t);
               double mu[N], Sig[TRI(N)];
               backward_head<RCOPY ? 1 : TILE>(it, t, aux, frv, m3m, S3m, mu, Sig);
               if constexpr (!RCOPY) ring_release();
             }
-            asm volatile("fence.acq_rel.cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) *prog = T;
+            if (lane == 0) progress_publish(prog, T);
           } else if constexpr (TEAM) {
             // RTS heads only: a head is a few hundred cycles, so the filtered records are streamed TEAM_DEPTH cells
             // ahead (a one-cell double buffer would expose the DRAM latency of every record)
@@ -2093,18 +2109,16 @@ struct Worker {
                 backward_head(it, t, aux, cur, m3m, S3m, mu, Sig);
                 if (t - DEPTH >= 0) rec_issue<LY::E_FILT>(cur, rec(p.filt, t - DEPTH, LY::E_FILT), t % DEPTH);
                 if constexpr (!BULK) stage_commit();
-                __threadfence_block();
                 __syncwarp();
-                if (lane == 0) *prog = T - t;
+                if (lane == 0) progress_publish(prog, T - t);
               }
               if constexpr (!BULK) stage_wait<0>();
             } else {
               for (int t = T - 1; t >= 0; --t) {
                 double mu[N], Sig[TRI(N)];
                 backward_head(it, t, aux, rec(p.filt, t, LY::E_FILT), m3m, S3m, mu, Sig);
-                __threadfence_block();
                 __syncwarp();
-                if (lane == 0) *prog = T - t;
+                if (lane == 0) progress_publish(prog, T - t);
               }
             }
           } else {
@@ -2130,8 +2144,7 @@ struct Worker {
           const int i1 = main_warp ? T : (copy_warp ? 0 : T - n_main);
           for (int i = i0; i < i1; i += di) {
             if (!main_warp) {
-              while (*prog <= i) __nanosleep(64);
-              asm volatile("fence.acq_rel.cta;" ::: "memory");
+              while (progress_read(prog) <= i) __nanosleep(64);
             }
             const int t = T - 1 - i;
             const double* po = rec(post, t, LY::E_POST);
