@@ -134,6 +134,13 @@ __device__ __forceinline__ void mbar_wait_s(unsigned bar_s, unsigned parity) {
 __device__ __forceinline__ void mbar_arrive_s(unsigned bar_s) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
 }
+// 32-bit shared address of a generic pointer, made OPAQUE to the compiler: otherwise ptxas rematerialises the conversion
+// (S2R SR_CgaCtaId + LEA, ~100 exposed cycles) at every use inside the cell loops instead of keeping the value in a register
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(p), r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+  return r;
+}
 __device__ __forceinline__ double lds_f64(unsigned addr_s) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr_s));
@@ -152,20 +159,16 @@ __device__ __forceinline__ int2 lds_i2_ro(unsigned addr_s) {
 }
 // Progress counter of the team kernel (heads finished), in shared memory: published with a release exchange by one lane
 // after __syncwarp() (cumulative over the warp's record stores), polled with acquire loads by the helper warps.
-__device__ __forceinline__ void progress_publish(volatile int* prog, int v) {
+// (prog_s = 32-bit shared address, converted once: a generic -> shared conversion inside the head loop costs an
+// S2R SR_CgaCtaId round trip of ~100 cycles per cell)
+__device__ __forceinline__ void progress_publish(unsigned prog_s, int v) {
   int old;
-  asm volatile("atom.exch.release.cta.shared::cta.b32 %0, [%1], %2;"
-               : "=r"(old)
-               : "r"((unsigned)__cvta_generic_to_shared(const_cast<int*>(prog))), "r"(v)
-               : "memory");
+  asm volatile("atom.exch.release.cta.shared::cta.b32 %0, [%1], %2;" : "=r"(old) : "r"(prog_s), "r"(v) : "memory");
   (void)old;
 }
-__device__ __forceinline__ int progress_read(volatile int* prog) {
+__device__ __forceinline__ int progress_read(unsigned prog_s) {
   int v;
-  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];"
-               : "=r"(v)
-               : "r"((unsigned)__cvta_generic_to_shared(const_cast<int*>(prog)))
-               : "memory");
+  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(prog_s) : "memory");
   return v;
 }
 #ifdef I2C_NO_BULK
@@ -575,8 +578,8 @@ struct Worker {
 
   __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_, uint64_t* bars_)
       : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_), bars(bars_), bar_phase(0), ring_q(0), ring_ready(false), ring_ready2(false) {
-    bars_s = (unsigned)__cvta_generic_to_shared(bars_);
-    stage_s = (unsigned)__cvta_generic_to_shared(stage_);
+    bars_s = smem_addr(bars_);
+    stage_s = smem_addr(stage_);
     status = I2C_OK;
     info = 0;
     prior = p.prior;
@@ -593,6 +596,33 @@ struct Worker {
   }
   __device__ __forceinline__ double* rec(double* base, int t, int E) const {
     return base + ((size_t)slot(t) * p.ntiles + tile) * (size_t)E * TILE + lane;
+  }
+  // Cursor over the records of consecutive cells of one per-cell array (ring layout): the address advances by a constant
+  // stride per cell and wraps once per sweep -- instead of rebuilding slot(t) and the 64-bit product for every cell.
+  struct Cursor {
+    double* ptr;
+    size_t stride, span;  // elements per cell slot, elements of the whole ring
+    int s, T;
+    // selects, not branches: a branch here would split the cell loop's basic block
+    __device__ __forceinline__ void next() {
+      const bool wrap = (s + 1 == T);
+      ptr += wrap ? (ptrdiff_t)stride - (ptrdiff_t)span : (ptrdiff_t)stride;
+      s = wrap ? 0 : s + 1;
+    }
+    __device__ __forceinline__ void prev() {
+      const bool wrap = (s == 0);
+      ptr += wrap ? (ptrdiff_t)span - (ptrdiff_t)stride : -(ptrdiff_t)stride;
+      s = wrap ? T - 1 : s - 1;
+    }
+  };
+  __device__ __forceinline__ Cursor cursor(double* base, int t, int E) const {
+    Cursor c;
+    c.stride = (size_t)p.ntiles * E * TILE;
+    c.span = c.stride * p.T;
+    c.s = slot(t);
+    c.T = p.T;
+    c.ptr = base + ((size_t)c.s * p.ntiles + tile) * (size_t)E * TILE + lane;
+    return c;
   }
   __device__ __forceinline__ void fail(int code, int it, int t) {
     if (status == I2C_OK) {
@@ -947,7 +977,7 @@ struct Worker {
   // NEXT cell at the end, from the outgoing message.  PS = element stride of the prior record at pr (1: register copy).
   template <bool PLAIN = false, int PS = TILE>
   __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, const double* pr,
-                                               Carry<DX>& c, LogAcc& ent_x, TrigT* octx = nullptr) {
+                                               Carry<DX>& c, LogAcc& ent_x, TrigT* octx = nullptr, double* fr_in = nullptr) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
     {
       double mu_u[DU], Suu[TRI(DU)], Kt[DU * DX];
@@ -1117,7 +1147,9 @@ struct Worker {
       staged_z(pr, t, z);
       if (!condition<N, DZ>(mu, Sig, Sz, Sxy, mz, z)) fail(I2C_FAIL_CHOL_OBS, it, t);
     }
-    double* fr = rec(p.filt, t, LY::E_FILT);
+    double* fr;  // PLAIN: the caller's record cursor (compile-time choice: a run-time test would be a branch in the cell)
+    if constexpr (PLAIN) fr = fr_in;
+    else fr = rec(p.filt, t, LY::E_FILT);
 #pragma unroll
     for (int i = 0; i < N; ++i) fr[(LY::F_MU1 + i) * TILE] = mu[i];
 #pragma unroll
@@ -1209,9 +1241,9 @@ struct Worker {
   // smoothed state; stores mu_xu0_m / sig_xu0_m and hands (mu_x0_m, sig_x0_m) to the previous cell.
   // FS = element stride of the filtered record at fr: TILE for the tiled layouts in shared / global memory, 1 for a copy
   // held in registers
-  template <int FS = TILE>
+  template <int FS = TILE, bool PO = false>
   __device__ __forceinline__ void backward_head(int it, int t, bool aux, const double* fr, double* m3m, double* S3m,
-                                                double* mu, double* Sig) {
+                                                double* mu, double* Sig, double* po_in = nullptr) {
     double J[N * DX];
     {
       double dm[DX], dS[TRI(DX)];
@@ -1254,7 +1286,9 @@ struct Worker {
           Sig[tix(i, j)] = s;
         }
     }
-    double* po = rec(post, t, LY::E_POST);
+    double* po;
+    if constexpr (PO) po = po_in;
+    else po = rec(post, t, LY::E_POST);
 #pragma unroll
     for (int i = 0; i < N; ++i) po[(LY::P_MU + i) * TILE] = mu[i];
 #pragma unroll
@@ -1999,15 +2033,17 @@ struct Worker {
           if (sweep_is_plain(flipped)) {
             TrigT octx;
             if constexpr (Env::OBS_NL > 0) obs_trig(c, octx);
+            Cursor fc = cursor(p.filt, 0, LY::E_FILT);
             for (; t < T - 1; ++t) {
               if constexpr (RCOPY) {
                 double pr[LY::E_STAGE_POST];
                 ring_read<LY::E_STAGE_POST>(pr);
-                forward_cell<true, 1>(it, t, 0, alpha, aux, pr, c, ent_x, &octx);
+                forward_cell<true, 1>(it, t, 0, alpha, aux, pr, c, ent_x, &octx, fc.ptr);
               } else {
-                forward_cell<true>(it, t, 0, alpha, aux, ring_view(), c, ent_x, &octx);
+                forward_cell<true>(it, t, 0, alpha, aux, ring_view(), c, ent_x, &octx, fc.ptr);
                 ring_release();
               }
+              fc.next();
             }
           }
           for (; t < T; ++t) {
@@ -2046,7 +2082,7 @@ struct Worker {
         // cells i = T-1-t with i mod H = w-1 and waits for head i; the last n_main cells are kept for warp 0, which
         // joins once its heads are done.  The assignment is static, so the per-warp partial sums -- and with them
         // alpha -- are bit-reproducible.  (Before: all heads, a barrier, then all tails: the tails were 11 % of an iteration.)
-        volatile int* prog = TEAM ? reinterpret_cast<volatile int*>(red + (size_t)7 * W * TILE) : nullptr;
+        const unsigned prog = TEAM ? smem_addr(red + (size_t)7 * W * TILE) : 0u;
         int n_main = 0;
         if constexpr (TEAM) {
           // tail : head cost is about r : 1 (7 with the per-thread record stream, 4 with the copy warp: profiles/r02); balance warp 0's
@@ -2072,6 +2108,7 @@ struct Worker {
           }
           backward_terminal(it, T - 1, temp, cell_alpha(T - 1, p.cell_flags[slot(T - 1)], alpha), c, m3m, S3m, tr_term);
           if constexpr (PROD) {
+            Cursor pc = cursor(post, T - 1, LY::E_POST);
             for (int t = T - 1; t >= 0; --t) {
               double fr[RCOPY ? LY::E_FILT : 1];
               const double* frv = fr;
@@ -2082,7 +2119,8 @@ struct Worker {
               __syncwarp();
               if (lane == 0) progress_publish(prog, T - 1 - t);
               double mu[N], Sig[TRI(N)];
-              backward_head<RCOPY ? 1 : TILE>(it, t, aux, frv, m3m, S3m, mu, Sig);
+              backward_head<RCOPY ? 1 : TILE, true>(it, t, aux, frv, m3m, S3m, mu, Sig, pc.ptr);
+              pc.prev();
               if constexpr (!RCOPY) ring_release();
             }
             __syncwarp();
@@ -2344,8 +2382,8 @@ __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_c
     for (int i = threadIdx.x; i < pin.T * DZ; i += W * TILE) ztab[i] = pin.z_cell[wk.slot(i / DZ) * DZ + i % DZ];
     for (int t = threadIdx.x; t < pin.T; t += W * TILE) ftab[t] = make_int2(pin.cell_flags[wk.slot(t)], pin.cell_index[wk.slot(t)]);
     __syncthreads();
-    wk.ztab_s = (unsigned)__cvta_generic_to_shared(ztab);
-    wk.ftab_s = (unsigned)__cvta_generic_to_shared(ftab);
+    wk.ztab_s = smem_addr(ztab);
+    wk.ftab_s = smem_addr(ftab);
   }
   wk.template run_impl<true>(w, W, red);
 }
