@@ -31,8 +31,8 @@ UNIT = "updates/s"
 F_ALG, B_ALG = 3192.0, 704.0
 # measured DRAM bytes per update of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
 # `ncu --set full` capture / updates in that launch): profiles/r01i_ncu_full_em_team_kernel_pendulum_4096.txt
-# latency kernel (em_team_kernel<EnvPendulum,8,HOT>, 4096 x 200): profiles/r02f_ncu_full_em_team_kernel_pendulum_4096.txt
-NCU_DRAM_BYTES_PER_UPDATE = (286.104832e6 + 404.079616e6) / (2 * 4096 * 200)
+# latency kernel (em_team_kernel<EnvPendulum,8,HOT>, 4096 x 200): profiles/r02l_ncu_full_em_team_kernel_pendulum_4096.txt
+NCU_DRAM_BYTES_PER_UPDATE = (286.220544e6 + 399.501568e6) / (2 * 4096 * 200)
 # throughput kernel (em_kernel<EnvPendulum,4>, 65 536 x 200): profiles/r01d_ncu_full_em_kernel_pendulum_65536.txt (13.35 GB / 26.2 M)
 NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT = 509.0
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
@@ -364,7 +364,7 @@ def run_cuda(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": NCU_DRAM_BYTES_PER_UPDATE * B * T * K if (B == 4096 and T == 200) else None,
-                     "traffic_source": "ncu dram bytes/update (profiles/r02f_ncu_full_em_team_kernel_pendulum_4096.txt) x updates "
+                     "traffic_source": "ncu dram bytes/update (profiles/r02l_ncu_full_em_team_kernel_pendulum_4096.txt) x updates "
                                        "per launch; algorithmic bytes per launch = %.4g" % (B_ALG * B * T * K),
                      "peak_source": peak_src,
                      "kernel": "em_team_kernel<EnvPendulum,8,HOT>" if B <= 148 * 32 else "em_kernel<EnvPendulum>",
