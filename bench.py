@@ -269,11 +269,12 @@ def run_cuda(args, rank, world, local_rank):
     h_K, h_k, h_s = h_pol[0]
     L = g.lib
 
+    m_ids = np.array([capi.METRICS["alpha"], capi.METRICS["cost_m"]], np.int32)
+
     def step_metrics_only():
         capi.check(L.i2c_set_initial_state_async(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))  # pinned, persistent buffers
         capi.check(L.i2c_run(g._h, 1, capi.PH_LEARN))
-        capi.check(L.i2c_get_metric(g._h, capi.METRICS["alpha"], capi.ptr(h_m[0:1]), 1))
-        capi.check(L.i2c_get_metric(g._h, capi.METRICS["cost_m"], capi.ptr(h_m[1:2]), 1))
+        capi.check(L.i2c_get_metrics(g._h, capi.ptr(m_ids), 2, capi.ptr(h_m), 1))  # alpha -> h_m[0], cost -> h_m[1]; one sync
 
     def final_gather():
         # the path's only collective: final gather of controllers and costs over NVLink
@@ -285,13 +286,20 @@ def run_cuda(args, rank, world, local_rank):
         assert gathered[0].shape[0] == world * B
         torch.cuda.synchronize(dev)
 
+    parts = {}
+
     def e2e_run(n):
+        ta = time.perf_counter()
         for _ in range(n):
             step_metrics_only()
+        tb = time.perf_counter()
         capi.check(L.i2c_get_policy_async(g._h, capi.ptr(h_K), capi.ptr(h_k), capi.ptr(h_s)))
         capi.check(L.i2c_copy_wait(g._h))
+        tc = time.perf_counter()
         if dist is not None:
             final_gather()
+        td = time.perf_counter()
+        parts.update(loop_ms=(tb - ta) * 1e3, final_d2h_ms=(tc - tb) * 1e3, gather_ms=(td - tc) * 1e3)
 
     e2e_run(2)  # warm-up (communicator buffers, allocator, pinned pages)
     barrier()
@@ -299,6 +307,7 @@ def run_cuda(args, rank, world, local_rank):
     e2e_run(Ke)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    parts = {k: max_over_ranks(v) for k, v in sorted(parts.items())}
     e2e_value = world * B * T * Ke / (e2e_ms * 1e-3)
     h2d = h_x0.nbytes + h_s0.nbytes
     d2h_step = h_m.nbytes
@@ -352,7 +361,7 @@ def run_cuda(args, rank, world, local_rank):
                    "failed_problems": n_fail},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step,
-                "d2h_bytes_once": d2h_once, "steps": Ke, "ms_per_step": e2e_ms / Ke,
+                "d2h_bytes_once": d2h_once, "steps": Ke, "ms_per_step": e2e_ms / Ke, "breakdown_ms_max_over_ranks": parts,
                 "what": "per step: H2D start-state belief (pinned), one learn_msgs through the C-ABI, D2H cost + alpha of every "
                         "problem (synchronous); after the last step, inside the timed region: D2H of K, k, sigK of this rank "
                         "(once)" + ("; + NCCL all_gather of controllers and costs over NVLink" if world > 1 else "")

@@ -1197,6 +1197,19 @@ int i2c_get_policy_dev(i2c_handle_t h, double* K_dev, double* k_dev, double* sig
   return 0;
 }
 
+int i2c_get_metrics(i2c_handle_t h, const int32_t* metrics, int32_t n_metrics, double* out, int32_t n_iter) {
+  REQUIRE(h && metrics && out && n_metrics >= 1, "bad argument");
+  DeviceGuard device_guard_(h->cfg.device);
+  REQUIRE(n_iter >= 1 && n_iter <= h->cfg.max_iters, "bad n_iter");
+  for (int i = 0; i < n_metrics; ++i) {
+    REQUIRE(metrics[i] >= 0 && metrics[i] < I2C_M_COUNT, "unknown metric id");
+    const double* src = h->metrics + (size_t)metrics[i] * h->cfg.max_iters * h->Bpad;
+    CUDA_OK(cudaMemcpy2DAsync(out + (size_t)i * n_iter * h->B, (size_t)h->B * 8, src, (size_t)h->Bpad * 8, (size_t)h->B * 8, n_iter,
+                              cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 int i2c_get_policy_async(i2c_handle_t h, double* K, double* k, double* sigK) {
   REQUIRE(h && K && k && sigK, "NULL argument");
   DeviceGuard device_guard_(h->cfg.device);

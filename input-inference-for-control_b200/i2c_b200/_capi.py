@@ -63,7 +63,7 @@ EXPORTS = [
     "i2c_env_dims", "i2c_workspace_bytes", "i2c_create", "i2c_destroy", "i2c_set_problem", "i2c_set_initial_state", "i2c_set_initial_state_async",
     "i2c_set_initial_state_dev", "i2c_set_cell_flags", "i2c_get_cell_flags", "i2c_set_cell_index", "i2c_set_tau",
     "i2c_set_cell_targets",
-    "i2c_set_alpha", "i2c_get_alpha", "i2c_set_temp", "i2c_get_temp", "i2c_run", "i2c_run_scan", "i2c_synchronize", "i2c_get_metric",
+    "i2c_set_alpha", "i2c_get_alpha", "i2c_set_temp", "i2c_get_temp", "i2c_run", "i2c_run_scan", "i2c_synchronize", "i2c_get_metric", "i2c_get_metrics",
     "i2c_get_status", "i2c_clear_status", "i2c_get_field", "i2c_set_field", "i2c_field_shape", "i2c_get_policy", "i2c_get_policy_async", "i2c_copy_wait", "i2c_get_policy_dev",
     "i2c_shift_horizon", "i2c_ckf_step", "i2c_mpc_step", "i2c_get_initial_state", "i2c_get_first_action", "i2c_quadrature", "i2c_quadrature_gh", "i2c_gauss_hermite",
     "i2c_rollout", "i2c_snapshot_bytes", "i2c_snapshot", "i2c_restore", "i2c_kernel_launches", "i2c_last_run_ms", "i2c_dfma_peak", "i2c_fastmath_probe",
@@ -110,6 +110,7 @@ def lib():
     L.i2c_run.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     L.i2c_synchronize.argtypes = [C.c_void_p]
     L.i2c_get_metric.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    L.i2c_get_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
     L.i2c_get_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.i2c_clear_status.argtypes = [C.c_void_p]
     L.i2c_get_field.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]

@@ -20,6 +20,12 @@ def gather_problem_axis(local, n_problems, group=None):
     world = dist.get_world_size(group)
     sizes = [shard_range(n_problems, world, r) for r in range(world)]
     max_b = max(e - s for s, e in sizes)
+    if all(e - s == max_b for s, e in sizes) and hasattr(dist, "all_gather_into_tensor"):
+        # even shards (the usual case): ONE collective straight into the final [B, ...] tensor -- no padding, no
+        # per-rank receive buffers, no concatenation copy
+        out = torch.empty((n_problems,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = torch.zeros((max_b,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     outs = [torch.empty_like(pad) for _ in range(world)]
