@@ -260,7 +260,7 @@ def run_cuda(args, rank, world, local_rank):
     # and cross once, after the last step: each rank reads its own K, k, sigK into pinned memory and (N > 1) the ranks
     # all_gather controllers and costs over NVLink -- the design BASELINE.json's north star describes ("NCCL ... solely for
     # the final gather of controllers and costs").  All of it is inside the timed region.
-    Ke = max(3, K)
+    Ke = args.e2e_steps if args.e2e_steps > 0 else max(3, K)  # default 100 = the EM iterations of BASELINE configs[2]'s job
     pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
     h_x0, h_s0 = pin(B, 2), pin(B, 2, 2)
     h_x0[:], h_s0[:] = g.x0, g.sig_x0
@@ -763,6 +763,9 @@ def main():
                     help="extra large-batch measurement at N=1 (0 = off); default = 148 SMs x 12 warps x 32 problems")
     ap.add_argument("--mpc-rollouts", type=int, default=8192, help="roll-outs per GPU of the MPC leg (0 = off)")
     ap.add_argument("--scan-horizon", type=int, default=4096, help="horizon of the parallel-in-time leg at N=1 (0 = off)")
+    ap.add_argument("--e2e-steps", type=int, default=100,
+                    help="EM iterations of the end-to-end leg (default 100: the whole job of BASELINE configs[2], SURVEY.md 8d; "
+                         "0 = --steps); the controllers are read back / gathered once after the last one")
     ap.add_argument("--workload", default="pendulum", choices=["pendulum", "dcp", "quadrotor"],
                     help="pendulum = BASELINE configs[2] (the judged line); dcp / quadrotor = per-GPU shards of configs[3] / [4]")
     args = ap.parse_args()
