@@ -398,7 +398,8 @@ def run_cuda(args, rank, world, local_rank):
         ms_s = gs.last_run_ms()
         rate_s = Bs * T * 5 / (ms_s * 1e-3)
         line["saturation"] = {"problems": Bs, "value": rate_s, "unit": UNIT, "ms_per_step": ms_s / 5,
-                              "hbm_frac": B_ALG * rate_s / 1e9 / hbm_peak,
+                              "hbm_frac_by_algorithmic_bytes": B_ALG * rate_s / 1e9 / hbm_peak,
+                              "hbm_frac_by_measured_traffic": NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT * rate_s / 1e9 / hbm_peak,
                               "hbm_frac_note": "by ALGORITHMIC bytes (704 B/update); the throughput kernel moves 509 B/update "
                                                "(ncu r01d, packed triangles), i.e. %.2f of the measured copy bandwidth"
                                                % (NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT * rate_s / 1e9 / hbm_peak),
@@ -717,7 +718,7 @@ def run_workload(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": F * rate_gpu / 1e12, "peak": fp64, "unit": "TFLOP/s",
                          "frac": F * rate_gpu / 1e12 / fp64, "traffic": None, "peak_source": src,
-                         "kernel": "em_group_kernel<EnvDoubleCartpole,8> (8 lanes per problem)" if B <= 160 * 32 else "em_kernel<EnvDoubleCartpole>",
+                         "kernel": "em_team_kernel<EnvDoubleCartpole,8,HOT>" if B <= 148 * 32 else "em_kernel<EnvDoubleCartpole>",
                          "kernel_ms_per_launch": kernel_ms, "algorithmic_flops_per_update": F,
                          "algorithmic_bytes_per_update": Bb, "hbm_frac": Bb * rate_gpu / 1e9 / hbm}}
     print(json.dumps(line), flush=True)
