@@ -52,9 +52,12 @@ struct Lay {
   // team kernel: depth of the filtered-record stream of the RTS head loop, and the staging area it needs
   static constexpr int TEAM_DEPTH = 6;
   // team kernel, HOT: producer / consumer ring of RING slots (E_STAGE doubles per lane each) filled by a copy warp
-  static constexpr int RING = E_FILT > 32 ? 4 : 8;
-  static constexpr int E_TEAM_A = (TEAM_DEPTH * E_FILT > 2 * E_STAGE_TOT) ? TEAM_DEPTH * E_FILT : 2 * E_STAGE_TOT;
-  static constexpr int E_TEAM_STAGE = !STAGED ? 0 : (E_TEAM_A > RING * E_STAGE ? E_TEAM_A : RING * E_STAGE);
+  // (the big records of the double cart-pole / quadrotor -- 27-30 KB per slot -- get a ring of 2: their cells take thousands of
+  // cycles, one cell of look-ahead hides the DRAM latency that cost those kernels a third of their time when they read the
+  // records straight from global memory)
+  static constexpr int RING = E_FILT > 64 ? 2 : (E_FILT > 32 ? 4 : 8);
+  static constexpr int E_TEAM_A = !STAGED ? 0 : ((TEAM_DEPTH * E_FILT > 2 * E_STAGE_TOT) ? TEAM_DEPTH * E_FILT : 2 * E_STAGE_TOT);
+  static constexpr int E_TEAM_STAGE = E_TEAM_A > RING * E_STAGE ? E_TEAM_A : RING * E_STAGE;
 
 };
 
@@ -2008,7 +2011,7 @@ struct Worker {
   __device__ void run_impl(const int w, const int W, double* red) {
     const bool main_warp = !TEAM || w == 0;
     // PROD: the last warp of the team is the copy warp of the record ring (see ring_init); H = warps that run tails
-    constexpr bool PROD = TEAM && HOT && LY::STAGED;
+    constexpr bool PROD = TEAM && HOT;
     const bool copy_warp = PROD && w == W - 1;
     const int H = PROD ? W - 2 : W - 1;
     if (main_warp && !PROD) pipe_init();
@@ -2374,7 +2377,7 @@ __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_c
   Worker<Env, true, false, false, HOT> wk(pin, blockIdx.x, lane, stage_smem + lane,
                        reinterpret_cast<uint64_t*>(stage_smem + Lay<Env>::E_TEAM_STAGE * TILE));
   if constexpr (HOT) {
-    if (Lay<Env>::STAGED && threadIdx.x == 0) wk.ring_init();
+    if (threadIdx.x == 0) wk.ring_init();
     // cell targets and {flags, index} of the whole horizon, in logical cell order (the ring offset is fixed during a launch)
     constexpr int DZ = Env::DZ;
     double* ztab = red + (size_t)7 * W * TILE + 2;
