@@ -944,9 +944,7 @@ static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   kp.temp0 = h->temp;
   kp.dtemp = h->dtemp;
   {
-    bool own = false;
-    for (int f : h->flags) own = own || (f & I2C_CELL_OWN_ALPHA);
-    kp.hot = kp.fast_obs && !kp.z_per_problem && !own && !(phases & I2C_PH_STORE_AUX) && !kp.linearize && kp.gh.degree == 0 &&
+    kp.hot = kp.fast_obs && !kp.z_per_problem && !(phases & I2C_PH_STORE_AUX) && !kp.linearize && kp.gh.degree == 0 &&
              (size_t)h->T * (h->d.dz + 1) * 8 <= 64 * 1024 /* shared-memory table of the horizon */ &&
              getenv("I2C_B200_NO_HOT") == nullptr;
   }

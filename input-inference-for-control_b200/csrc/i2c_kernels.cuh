@@ -545,8 +545,7 @@ struct Carry {
 // LIN = Linearize inference compiled in (separate instantiation: keeps the cubature kernels small).
 // GH = Gauss-Hermite tensor-grid rule instead of the cubature points (separate instantiation as well).
 // HOT = the common configuration is compiled in instead of tested per cell (launcher: KParams::hot): cubature rule with
-// zero centre weight (structured cost-feature moments), no auxiliary records, shared cell targets staged with the records,
-// no per-cell alpha.  Every one of these run-time switches was a (uniform) branch in the cell loops: ~10 basic-block
+// zero centre weight (structured cost-feature moments), no auxiliary records, shared cell targets staged with the records.  Every one of these run-time switches was a (uniform) branch in the cell loops: ~10 basic-block
 // boundaries per forward cell that stop ptxas from overlapping the independent dependency chains across them.
 template <class Env, bool META, bool LIN = false, bool GH = false, bool HOT = false>
 struct Worker {
@@ -740,7 +739,7 @@ struct Worker {
   __device__ __forceinline__ bool sweep_is_plain(bool flipped) const {
     bool bad = false;
     for (int t = lane; t < p.T - 1; t += TILE)
-      bad = bad || (staged_flags(nullptr, t, flipped) & (I2C_CELL_INDEPENDENT | I2C_CELL_TERMINAL)) != 0;
+      bad = bad || (staged_flags(nullptr, t, flipped) & (I2C_CELL_INDEPENDENT | I2C_CELL_TERMINAL | I2C_CELL_OWN_ALPHA)) != 0;
     return !__any_sync(0xffffffffu, bad);
   }
   // init of this warp's mbarriers (call once, all lanes)
@@ -820,7 +819,8 @@ struct Worker {
     }
   }
   __device__ __forceinline__ double cell_alpha(int t, int flags, double alpha) const {
-    if constexpr (HOT) return alpha;
+    // (PLAIN cells pass flags = 0: this folds to `alpha`; sweeps that contain a cell with its own alpha -- MPC: the cell
+    // appended by the horizon shift -- take the generic-flag loop, see sweep_is_plain)
     return ((flags & I2C_CELL_OWN_ALPHA) && own_alpha_valid) ? p.alpha_cell[(size_t)slot(t) * p.Bpad + b] : alpha;
   }
 

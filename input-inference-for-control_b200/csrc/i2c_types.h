@@ -70,7 +70,7 @@ struct KParams {
   int32_t group_mode;      // -1 auto, 0 never, 1 always: G-lanes-per-problem kernel (i2c_group.cuh)
   int32_t group_max_tiles; // auto: use it up to this many tiles (0 = built-in policy)
   int32_t minb;            // A/B: resident 128-thread blocks per SM of the small-env throughput variant (0 = default 4)
-  int32_t hot;             // the common configuration (Worker<..., HOT>): fast_obs, shared targets, no aux records, no per-cell alpha
+  int32_t hot;             // the common configuration (Worker<..., HOT>): fast_obs, shared targets, no aux records
 };
 
 // element counts of the records for given dims
