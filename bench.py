@@ -488,7 +488,7 @@ def mpc_leg(args, dev, rank, world, max_over_ranks, barrier, n_timed=20, with_em
     u_init = 0.5 * 9.81 * i2c_b200.envs.QUAD_MASS * np.ones((T_plan, 2))
     g = i2c_b200.BatchedI2c("Quadrotor", B, T_plan, Q, R, Q / 1e3, 1.0, 1.0, u_init, 1e-2 * np.eye(2), device=dev)
     g._propagate = True
-    pol = i2c_b200.BatchedPartiallyObservedMpc(g, mpc_iter, 1e-2 * np.eye(2), z_traj, sig_zeta=sig_zeta)
+    pol = i2c_b200.BatchedPartiallyObservedMpc(g, mpc_iter, 1e-2 * np.eye(2), z_traj, sig_zeta=sig_zeta, pinned_io=True)
     pol.set_control(feedforward=False)
     g.calibrate_alpha()
     pol.optimize(25)

@@ -277,6 +277,12 @@ int i2c_snapshot_bytes(i2c_handle_t h, size_t* bytes);
 int i2c_snapshot(i2c_handle_t h, void* host_buf, size_t bytes);
 int i2c_restore(i2c_handle_t h, const void* host_buf, size_t bytes);
 
+/* Page-locked host buffers for the per-step traffic of the closed loop (measurements / applied actions in, actions out of
+ * i2c_mpc_step; beliefs of i2c_set_initial_state_async): copies from / to them are truly asynchronous, whereas pageable NumPy
+ * arrays (the reference passes those: policy/mpc.py:156-166) are staged by the driver, ~40 us per 128 KB array and step. */
+int i2c_host_alloc(size_t bytes, void** out);
+int i2c_host_free(void* p);
+
 /* Introspection used by bench.py / tests. */
 int i2c_kernel_launches(i2c_handle_t h, int64_t* n); /* kernels launched by this handle so far */
 int i2c_last_run_ms(i2c_handle_t h, float* ms);      /* CUDA-event time of the last i2c_run kernel */

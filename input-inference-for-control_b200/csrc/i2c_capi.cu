@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -249,14 +250,22 @@ __global__ void fill_kernel(double* p, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// Horizon shift of the MPC step in one launch (policy/mpc.py:174-181): the recycled ring slot becomes a fresh last cell
-// (constructor state with the initial action mean), its flags / index / target / alpha are reset.
-__global__ void mpc_shift_kernel(double* recA, double* recB, InitArgs a, const double* __restrict__ x0,
-                                 const double* __restrict__ sig_x0, SmallVals mu, int B, int slot, int32_t* flags, int32_t* index,
-                                 int32_t f, double* alpha_cell, double alpha_init, double* z_cell, SmallVals z, int dz) {
+// Tail of the MPC step in one launch (policy/mpc.py:166, 174-181): the first planned action = mu_u of the posterior of
+// cells[0] is copied to `u_out` ([B][du], caller's layout), then the ring slot of that very cell -- cells.pop(0) -- becomes
+// the fresh last cell (constructor state with the initial action mean, its index / target / alpha reset).  The cell flags
+// of the whole horizon arrive by value (state after this step's _update_priors): no host staging, no extra copy.
+struct SmallInts {
+  int32_t v[64];
+};
+__global__ void mpc_tail_kernel(double* recA, double* recB, const double* latest /* aliases recA or recB */, InitArgs a,
+                                const double* __restrict__ x0, const double* __restrict__ sig_x0, SmallVals mu, int B, int slot,
+                                int32_t* flags, int32_t* index, SmallInts f, int nflags, double* alpha_cell, double alpha_init,
+                                double* z_cell, SmallVals z, int dz, double* __restrict__ u_out) {
   const int n = a.n, dx = a.dx, du = a.du;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.Bpad; b += gridDim.x * blockDim.x) {
     size_t base = (((size_t)slot * a.ntiles + b / TILE) * a.E) * TILE + (b % TILE);
+    if (b < B)
+      for (int k = 0; k < du; ++k) u_out[(size_t)b * du + k] = latest[base + (size_t)(dx + k) * TILE];
     size_t xb = ((size_t)(b / TILE) * dx) * TILE + (b % TILE);
     size_t sb = ((size_t)(b / TILE) * (dx * (dx + 1) / 2)) * TILE + (b % TILE);
     int e = 0;
@@ -274,7 +283,7 @@ __global__ void mpc_shift_kernel(double* recA, double* recB, InitArgs a, const d
     for (int k = 0; k < du * (du + 1) / 2; ++k, ++e) recA[base + (size_t)e * TILE] = recB[base + (size_t)e * TILE] = a.sig_u[k];
     alpha_cell[(size_t)slot * a.Bpad + b] = alpha_init;
     if (b == 0) {
-      flags[slot] = f;
+      for (int k = 0; k < nflags; ++k) flags[k] = f.v[k];
       index[slot] = 0;
       for (int k = 0; k < dz; ++k) z_cell[(size_t)slot * dz + k] = z.v[k];
     }
@@ -951,7 +960,8 @@ static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   return kp;
 }
 
-int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
+// upload = false: the caller takes care of the device copy of the cell flags (i2c_mpc_step: they ride in its tail kernel)
+static int run_core(i2c_handle_t h, int32_t n_iter, int32_t phases, bool upload) {
   REQUIRE(h, "NULL handle");
   DeviceGuard device_guard_(h->cfg.device);
   REQUIRE(h->problem_set, "i2c_set_problem has not been called");
@@ -988,10 +998,12 @@ int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) {
       changed = changed || h->flags[s] != before;
     }
     // (a pageable H2D copy serialises with the stream: only when a flag really changed, i.e. after the first iteration)
-    if (changed) CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
+    if (changed && upload) CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), h->T * 4, cudaMemcpyHostToDevice, h->stream));
   }
   return 0;
 }
+
+int i2c_run(i2c_handle_t h, int32_t n_iter, int32_t phases) { return run_core(h, n_iter, phases, true); }
 
 // Parallel-in-time variant of i2c_run (csrc/i2c_scan.cuh): the horizon is cut into chunks of `chunk_cells` cells that are
 // processed concurrently; exact for Linearize inference on the linear environments.  Same records, metrics and state
@@ -1294,6 +1306,28 @@ int i2c_shift_horizon(i2c_handle_t h, const double* z_new, const double* mu_u_in
 }
 
 static int ckf_step_impl(i2c_handle_t h, const double* y, const double* u, const double* sig_zeta, bool sync);
+// I2C_B200_TRACE=1: host-side time of the phases of i2c_mpc_step (filter issue, sweeps issue, tail issue, wait), printed every
+// 16 calls on stderr -- where a control step's time goes outside the kernels
+struct StepTrace {
+  static constexpr int N = 5;
+  std::chrono::steady_clock::time_point t[N];
+  bool on;
+  StepTrace() : on(getenv("I2C_B200_TRACE") != nullptr) {}
+  void mark(int i) {
+    if (on) t[i] = std::chrono::steady_clock::now();
+  }
+  void done() {
+    if (!on) return;
+    static double acc[N] = {0, 0, 0, 0, 0};
+    static int calls = 0;
+    for (int i = 1; i < N; ++i) acc[i] += std::chrono::duration<double, std::micro>(t[i] - t[i - 1]).count();
+    if (++calls % 16 == 0) {
+      fprintf(stderr, "[i2c_mpc_step] us per call: filter issue %.1f, sweeps issue %.1f, tail issue %.1f, wait %.1f\n", acc[1] / 16,
+              acc[2] / 16, acc[3] / 16, acc[4] / 16);
+      for (double& a : acc) a = 0;
+    }
+  }
+};
 // One closed-loop MPC step with a single synchronisation: PartiallyObservedMpcPolicy.__call__
 // (policy/mpc.py:156-182) = [filter] -> n_iter x (forward, backward, _update_priors) -> first action -> horizon shift.
 int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const double* u_prev, const double* sig_zeta,
@@ -1304,39 +1338,45 @@ int i2c_mpc_step(i2c_handle_t h, int32_t do_filter, const double* y, const doubl
   const int dx = h->d.dx, du = h->d.du, n = dx + du, dz = h->d.dz, T = h->T;
   REQUIRE(dz <= 16 && du <= 16, "internal: by-value setter too small");
   int rc = 0;
+  StepTrace tr;
+  tr.mark(0);
   if (do_filter) {
     REQUIRE(y && u_prev && sig_zeta, "filter step needs y, u_prev, sig_zeta");
     rc = ckf_step_impl(h, y, u_prev, sig_zeta, false);  // stream-ordered; the single synchronisation is at the end
     if (rc) return rc;
   }
-  rc = i2c_run(h, n_iter, I2C_PH_FORWARD | I2C_PH_BACKWARD | I2C_PH_UPDATE_PRIORS);
+  tr.mark(1);
+  const bool by_value = T <= 64;  // the cell flags ride in the tail kernel's arguments
+  rc = run_core(h, n_iter, I2C_PH_FORWARD | I2C_PH_BACKWARD | I2C_PH_UPDATE_PRIORS, !by_value);
   if (rc) return rc;
-  // first action = cells[0].mu_u0_m (policy/mpc.py:166) -> scratch -> host (async)
-  {
-    FieldMap f{h->r.e_post(), dx, 0, du, 1, 0, 0, 1};
-    size_t total = (size_t)h->B * du;
-    unpack_kernel<<<nblocks(total), 256, 0, h->stream>>>(rec_latest(h), f, 0, 1, h->T, h->cell_head, h->B, h->ntiles, h->scratch);
-    CUDA_OK(cudaMemcpyAsync(u_out, h->scratch, total * 8, cudaMemcpyDeviceToHost, h->stream));
-    h->launches++;
-  }
-  // horizon shift (policy/mpc.py:174-181) without host staging
+  tr.mark(2);
+  // first action = cells[0].mu_u0_m (policy/mpc.py:166) and the horizon shift (policy/mpc.py:174-181) in one launch: the popped
+  // cell's ring slot IS the slot of the appended cell
+  const double* latest = rec_latest(h);
   h->cell_head = (h->cell_head + 1) % T;
   const int slot = (T - 1 + h->cell_head) % T;
   h->flags[slot] = I2C_CELL_INDEPENDENT | I2C_CELL_EXPERT | I2C_CELL_OWN_ALPHA;
   h->index[slot] = 0;
   {
     SmallVals mu_v, z_v;
+    SmallInts f_v;
     for (int i = 0; i < du; ++i) mu_v.v[i] = mu_u_init[i];
     for (int i = 0; i < dz; ++i) z_v.v[i] = z_new[i];
+    for (int i = 0; i < T && i < 64; ++i) f_v.v[i] = h->flags[i];
+    if (!by_value) CUDA_OK(cudaMemcpyAsync(h->cell_flags_dev, h->flags.data(), T * 4, cudaMemcpyHostToDevice, h->stream));
     InitArgs ia{dx, du, n, h->r.e_post(), T, h->cell_head, h->Bpad, h->ntiles, 1, {0, 0, 0}};
     for (int i = 0; i < tri(du); ++i) ia.sig_u[i] = h->sig_u_host[i];
-    mpc_shift_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->recA, h->recB, ia, h->x0, h->sig_x0, mu_v, h->B, slot,
-                                                                     h->cell_flags_dev, h->cell_index_dev, h->flags[slot],
-                                                                     h->alpha_cell, alpha_init, h->z_cell, z_v, dz);
+    mpc_tail_kernel<<<nblocks((size_t)h->Bpad), 256, 0, h->stream>>>(h->recA, h->recB, latest, ia, h->x0, h->sig_x0, mu_v, h->B, slot,
+                                                                    h->cell_flags_dev, h->cell_index_dev, f_v, by_value ? T : 0,
+                                                                    h->alpha_cell, alpha_init, h->z_cell, z_v, dz, h->scratch);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(u_out, h->scratch, (size_t)h->B * du * 8, cudaMemcpyDeviceToHost, h->stream));
   }
   h->launches += 1;
-  CUDA_OK(cudaGetLastError());
+  tr.mark(3);
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  tr.mark(4);
+  tr.done();
   return 0;
 }
 
@@ -1694,6 +1734,17 @@ int i2c_dfma_peak(int32_t device, double* tflops) {
   cudaFree(out);
   CUDA_OK(cudaGetLastError());
   *tflops = best;
+  return 0;
+}
+
+int i2c_host_alloc(size_t bytes, void** out) {
+  REQUIRE(out && bytes > 0, "bad argument");
+  CUDA_OK(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return 0;
+}
+
+int i2c_host_free(void* p) {
+  if (p) CUDA_OK(cudaFreeHost(p));
   return 0;
 }
 

@@ -145,11 +145,12 @@ def test_snapshot_restore(i2c_b200):
     assert np.array_equal(G.field("K"), K5) and np.array_equal(G.alpha, a5)
 
 
-def quad_setup(m, g, B, sig_zeta):
+def quad_setup(m, g, B, sig_zeta, pinned_io=False):
     G = m.BatchedI2c("Quadrotor", B, int(g["T_plan"]), g["Q"], g["R"], g["Qf"], 1.0, 1.0, g["u_init"], g["sig_u"],
                      enable_aux=True)
     G._propagate = True
-    pol = m.BatchedPartiallyObservedMpc(G, int(g["mpc_iter"]), g["sig_u"], g["z_traj"].copy(), sig_zeta=sig_zeta)
+    pol = m.BatchedPartiallyObservedMpc(G, int(g["mpc_iter"]), g["sig_u"], g["z_traj"].copy(), sig_zeta=sig_zeta,
+                                        pinned_io=pinned_io)
     pol.set_control(bool(g["feedforward"]))
     return G, pol
 
@@ -210,18 +211,32 @@ def test_mpc_batched_rollouts_vs_oracle(i2c_b200):
     pol2.optimize(25)
     G2.calibrate_alpha()
     u2 = np.zeros((B, 2))
+    # ... and through the fused call with page-locked I/O (i2c_host_alloc): measurements from a pinned array, the returned
+    # actions (views into the policy's pinned ring) fed back as they are
+    G3, pol3 = quad_setup(i2c_b200, g, B, sig_zeta, pinned_io=True)
+    G3.calibrate_alpha()
+    pol3.optimize(25)
+    G3.calibrate_alpha()
+    y3 = i2c_b200.capi.pinned_empty((B, 8))
+    u3 = np.zeros((B, 2))
     for t in range(n_steps):
         y = sys_.measure(x) + rng.multivariate_normal(np.zeros(8), sig_zeta, B)
         u2 = np.clip(pol2(t, y, u2, fused=False), 0.0, 30.0)
         u = np.clip(pol(t, y, u), 0.0, 30.0)
         assert np.array_equal(u, u2), t
+        y3[:] = y
+        u3 = pol3(t, y3, u3)
+        np.clip(u3, 0.0, 30.0, out=u3)
+        assert np.array_equal(u, u3), t
         ur = np.clip(rp(t, y, ur), 0.0, 30.0)
         assert relerr(u, ur) < 1e-6, t
         mu, cov = pol.belief
         assert relerr(mu, rp.mu) < 1e-7 and relerr(cov, rp.covar) < 1e-6, t
         x = sys_.dynamics(np.concatenate((x, ur), axis=-1)) + rng.multivariate_normal(np.zeros(6), sys_.sig_eta, B)
         u = u2 = ur
+        u3[:] = ur
     assert np.all(G.status()[0] == 0)
+    assert np.array_equal(G.get_cell_flags(), G3.get_cell_flags()) and np.array_equal(G.get_cell_flags(), G2.get_cell_flags())
 
 
 def test_async_policy_copy(i2c_b200):
