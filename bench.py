@@ -384,28 +384,44 @@ def run_cuda(args, rank, world, local_rank):
                               "peak_nominal_tflops": FP64_NOMINAL_TFLOPS, "frac_of_nominal": fp64_ach / FP64_NOMINAL_TFLOPS}},
     }
     if world == 1 and args.saturation > B:
-        # same kernel at a batch that fills the machine (the 4096-problem headline is bound by the latency of the
-        # sequential recursion over t: 128 warps on 592 sub-partitions)
-        Bs = args.saturation
-        x0s, mu_us = make_inputs(Bs, T, 99)
+        # same path at batches that fill the machine (the 4096-problem headline is bound by the latency of the sequential
+        # recursion over t: 128 warps on 592 sub-partitions): the B at which >= 50 % of the roofline is reached, and the
+        # saturated rate.  Kernel by batch size: <= 4736 team kernel (8 warps per tile), <= 9472 team kernel (4 warps),
+        # < 56832 one warp per tile (255 registers), >= 56832 em_ticket_kernel ((tile, iteration) work items, no wave edges)
         del g
         torch.cuda.empty_cache()
-        gs = i2c_b200.BatchedI2c("PendulumKnown", Bs, T, HYPER["Q"], HYPER["R"], HYPER["Q"], HYPER["alpha"], HYPER["tol"],
-                                 mu_us, HYPER["sig_u"], x0=x0s, device=dev, max_iters=8)
-        gs.run(3, capi.PH_LEARN, collect=False)
-        gs.run(5, capi.PH_LEARN, collect=False)
-        torch.cuda.synchronize(dev)
-        ms_s = gs.last_run_ms()
-        rate_s = Bs * T * 5 / (ms_s * 1e-3)
-        line["saturation"] = {"problems": Bs, "value": rate_s, "unit": UNIT, "ms_per_step": ms_s / 5,
+
+        def at_batch(Bs, n):
+            x0s, mu_us = make_inputs(Bs, T, 99)
+            gs = i2c_b200.BatchedI2c("PendulumKnown", Bs, T, HYPER["Q"], HYPER["R"], HYPER["Q"], HYPER["alpha"], HYPER["tol"],
+                                     mu_us, HYPER["sig_u"], x0=x0s, device=dev, max_iters=max(8, n))
+            gs.run(3, capi.PH_LEARN, collect=False)
+            gs.run(n, capi.PH_LEARN, collect=False)
+            torch.cuda.synchronize(dev)
+            ms_s = gs.last_run_ms()
+            failed = int(np.count_nonzero(gs.status()[0]))
+            gs.close()
+            del gs
+            torch.cuda.empty_cache()
+            return ms_s / n, Bs * T * n / (ms_s * 1e-3), failed
+
+        sweep = []
+        for Bs in args.b_sweep:
+            ms_i, rate_i, failed = at_batch(Bs, 10)
+            sweep.append({"problems": Bs, "ms_per_step": ms_i, "value": rate_i, "hbm_frac": B_ALG * rate_i / 1e9 / hbm_peak,
+                          "failed_problems": failed})
+        line["b_sweep"] = {"unit": UNIT, "horizon": T, "em_iterations_timed": 10, "hbm_frac": "algorithmic bytes (704 B/update) x "
+                           "rate / measured HBM peak", "points": sweep}
+        Bs = args.saturation
+        ms_i, rate_s, failed = at_batch(Bs, 10)
+        line["saturation"] = {"problems": Bs, "value": rate_s, "unit": UNIT, "ms_per_step": ms_i,
                               "hbm_frac_by_algorithmic_bytes": B_ALG * rate_s / 1e9 / hbm_peak,
                               "hbm_frac_by_measured_traffic": NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT * rate_s / 1e9 / hbm_peak,
                               "hbm_frac_note": "by ALGORITHMIC bytes (704 B/update); the throughput kernel moves 509 B/update "
                                                "(ncu r01d, packed triangles), i.e. %.2f of the measured copy bandwidth"
                                                % (NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT * rate_s / 1e9 / hbm_peak),
                               "fp64_frac_of_measured": (F_ALG * rate_s / 1e12 / fp64_peak) if fp64_peak else None,
-                              "failed_problems": int(np.count_nonzero(gs.status()[0]))}
-        del gs
+                              "failed_problems": failed}
     if mpc is not None:
         line["mpc"] = mpc
     line["em_iterations_per_s"] = {"batch_sweeps_per_s": 1e3 * K / ms, "problem_iterations_per_s": world * B * K / (ms * 1e-3)}
@@ -760,8 +776,11 @@ def main():
     ap.add_argument("--problems", type=int, default=4096, help="problems per GPU")
     ap.add_argument("--horizon", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--saturation", type=int, default=56832,
-                    help="extra large-batch measurement at N=1 (0 = off); default = 148 SMs x 12 warps x 32 problems")
+    ap.add_argument("--b-sweep", type=lambda v: [int(x) for x in v.split(",") if x], default=[8192, 16384, 32768, 56832],
+                    help="extra batch sizes of the judged workload timed after the headline (N=1 only; '' = none)")
+    ap.add_argument("--saturation", type=int, default=65536,
+                    help="extra large-batch measurement at N=1 (0 = off); 65536 problems = 2048 tiles on the 1776 resident warps of "
+                         "em_ticket_kernel (no wave quantisation)")
     ap.add_argument("--mpc-rollouts", type=int, default=8192, help="roll-outs per GPU of the MPC leg (0 = off)")
     ap.add_argument("--scan-horizon", type=int, default=4096, help="horizon of the parallel-in-time leg at N=1 (0 = off)")
     ap.add_argument("--e2e-steps", type=int, default=100,

@@ -120,7 +120,7 @@ struct i2c_handle_s {
   // device buffers (inside ws)
   double *recA, *recB, *filt, *auxf, *auxb, *pf, *ric, *term, *x0, *sig_x0, *alpha, *alpha_cell, *z_cell, *z_term_pp, *envpar, *metrics,
       *scratch, *policy_out;
-  int32_t *cell_flags_dev, *cell_index_dev, *status, *info;
+  int32_t *cell_flags_dev, *cell_index_dev, *status, *info, *tickets;
   size_t scratch_elems;
   // host state
   int prior_is_A;   // forward reads recA (1) or recB (0)
@@ -298,7 +298,7 @@ static inline int nblocks(size_t total) {
 // ----------------------------------------------------------------------------------------- layout
 struct WsLayout {
   size_t recA, recB, filt, auxf, auxb, pf, ric, term, x0, sig_x0, alpha, alpha_cell, z_cell, z_term_pp, envpar, metrics, scratch, policy_out, flags,
-      index, status, info, total, scratch_elems;
+      index, status, info, tickets, total, scratch_elems;
 };
 
 static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
@@ -338,6 +338,7 @@ static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
   w.index = take(T, 4);
   w.status = take(Bpad, 4);
   w.info = take(Bpad, 4);
+  w.tickets = take(nt + 1, 4);  // em_ticket_kernel: ticket counter + finished iterations per tile
   w.total = off;
   return w;
 }
@@ -443,6 +444,7 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
   h->cell_index_dev = (int32_t*)(h->ws + w.index);
   h->status = (int32_t*)(h->ws + w.status);
   h->info = (int32_t*)(h->ws + w.info);
+  h->tickets = (int32_t*)(h->ws + w.tickets);
   h->problem_set = false;
   h->launches = 0;
   h->last_n_iter = 0;
@@ -940,6 +942,7 @@ static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   kp.metrics = h->metrics;
   kp.status = h->status;
   kp.info = h->info;
+  kp.tickets = h->tickets;
   kp.B = h->B;
   kp.Bpad = h->Bpad;
   kp.ntiles = h->ntiles;
@@ -953,9 +956,14 @@ static KParams run_params(i2c_handle_t h, int32_t n_iter, int32_t phases) {
   kp.temp0 = h->temp;
   kp.dtemp = h->dtemp;
   {
-    kp.hot = kp.fast_obs && !kp.z_per_problem && !(phases & I2C_PH_STORE_AUX) && !kp.linearize && kp.gh.degree == 0 &&
-             (size_t)h->T * (h->d.dz + 1) * 8 <= 64 * 1024 /* shared-memory table of the horizon */ &&
-             getenv("I2C_B200_NO_HOT") == nullptr;
+    bool own = false;
+    for (int f : h->flags) own = own || (f & I2C_CELL_OWN_ALPHA);
+    const bool hot = kp.fast_obs && !kp.z_per_problem && !(phases & I2C_PH_STORE_AUX) && !kp.linearize && kp.gh.degree == 0 &&
+                     (size_t)h->T * (h->d.dz + 1) * 8 <= 64 * 1024 /* shared-memory table of the horizon */ &&
+                     getenv("I2C_B200_NO_HOT") == nullptr;
+    // cells with their own alpha (MPC horizon shift): the HOT = 2 instantiation, built for the environments with a measurement
+    // model (the partially observed MPC loop); elsewhere the generic kernels
+    kp.hot = !hot ? 0 : (!own ? 1 : (h->d.dy > 0 ? 2 : 0));
   }
   return kp;
 }

@@ -1354,7 +1354,7 @@ static int launch_em_group_maybe(const KParams& p, cudaStream_t s) {
   // round 2: with the HOT specialisation (branch-free + angle-addition trig: 11 instead of 34 sincos per double cart-pole
   // dynamics transform, no per-cell flag branches) the per-thread team kernel overtook this one on the config-4 shard:
   // 6.9 ms against 10.6 ms per EM iteration at 2048 x 500 (profiles/r02_env_sweep.jsonl).  Auto mode keeps the group kernel
-  // for the configurations the HOT kernels do not cover (auxiliary records, per-problem targets).
+  // for the configurations the HOT kernels do not cover (auxiliary records, per-problem targets, per-cell alpha).
   if (p.group_mode < 0 && p.hot) return kGroupNotTaken;
   return launch_em_group<Env, G>(p, s);
 }

@@ -545,9 +545,13 @@ struct Carry {
 // LIN = Linearize inference compiled in (separate instantiation: keeps the cubature kernels small).
 // GH = Gauss-Hermite tensor-grid rule instead of the cubature points (separate instantiation as well).
 // HOT = the common configuration is compiled in instead of tested per cell (launcher: KParams::hot): cubature rule with
-// zero centre weight (structured cost-feature moments), no auxiliary records, shared cell targets staged with the records.  Every one of these run-time switches was a (uniform) branch in the cell loops: ~10 basic-block
+// zero centre weight (structured cost-feature moments), no auxiliary records, shared cell targets staged with the records,
+// no per-cell alpha.  Every one of these run-time switches was a (uniform) branch in the cell loops: ~10 basic-block
 // boundaries per forward cell that stop ptxas from overlapping the independent dependency chains across them.
-template <class Env, bool META, bool LIN = false, bool GH = false, bool HOT = false>
+// HOT = 2: as 1, but cells may carry their own alpha (MPC: the cell appended by the horizon shift).  A separate instantiation
+// (environments with a measurement model only): compiling the per-cell alpha into the HOT = 1 kernels changed their register
+// allocation throughout and cost the judged pendulum line 12 % (0.2115 -> 0.237 ms per iteration).
+template <class Env, bool META, bool LIN = false, bool GH = false, int HOT = 0>
 struct Worker {
   // HOT moves the records with bulk copies as well: targets / flags come from a shared-memory table built once per launch
   // (team kernel), so the per-thread LDGSTS stream (17 + 20 instructions and ~25 of address arithmetic per cell) is gone
@@ -739,7 +743,7 @@ struct Worker {
   __device__ __forceinline__ bool sweep_is_plain(bool flipped) const {
     bool bad = false;
     for (int t = lane; t < p.T - 1; t += TILE)
-      bad = bad || (staged_flags(nullptr, t, flipped) & (I2C_CELL_INDEPENDENT | I2C_CELL_TERMINAL | I2C_CELL_OWN_ALPHA)) != 0;
+      bad = bad || (staged_flags(nullptr, t, flipped) & (I2C_CELL_INDEPENDENT | I2C_CELL_TERMINAL | (HOT == 2 ? I2C_CELL_OWN_ALPHA : 0))) != 0;
     return !__any_sync(0xffffffffu, bad);
   }
   // init of this warp's mbarriers (call once, all lanes)
@@ -819,8 +823,9 @@ struct Worker {
     }
   }
   __device__ __forceinline__ double cell_alpha(int t, int flags, double alpha) const {
-    // (PLAIN cells pass flags = 0: this folds to `alpha`; sweeps that contain a cell with its own alpha -- MPC: the cell
-    // appended by the horizon shift -- take the generic-flag loop, see sweep_is_plain)
+    if constexpr (HOT == 1) return alpha;
+    // (HOT = 2: PLAIN cells pass flags = 0 and this folds to `alpha`; sweeps that contain a cell with its own alpha -- MPC: the
+    // cell appended by the horizon shift -- take the generic-flag loop, see sweep_is_plain)
     return ((flags & I2C_CELL_OWN_ALPHA) && own_alpha_valid) ? p.alpha_cell[(size_t)slot(t) * p.Bpad + b] : alpha;
   }
 
@@ -2007,8 +2012,11 @@ struct Worker {
   // backward pass that does not feed the recursion (backward_tail) runs on the W-1 helper warps WHILE warp 0 walks the
   // RTS heads (static cell -> warp map, progress counter in shared memory), and the M-step statistics are reduced through
   // shared memory in a fixed order.
+  // [it0, it1): the iterations this call runs.  it0 > 0 (em_ticket_kernel: one iteration of one tile per work item) rebuilds
+  // the loop-carried state of a launch that started at iteration 0: record roles, cleared independence flags, covariance-control
+  // temperature, validity of the per-cell alphas; alpha and the status words travel through global memory.
   template <bool TEAM>
-  __device__ void run_impl(const int w, const int W, double* red) {
+  __device__ void run_impl(const int w, const int W, double* red, const int it0, const int it1) {
     const bool main_warp = !TEAM || w == 0;
     // PROD: the last warp of the team is the copy warp of the record ring (see ring_init); H = warps that run tails
     constexpr bool PROD = TEAM && HOT;
@@ -2021,7 +2029,24 @@ struct Worker {
     bool flipped = false;  // _update_priors has cleared state_action_independence for index <= tau
     double temp = p.temp0;
     const int T = p.T;
-    for (int it = 0; it < p.n_iter; ++it) {
+    if (it0 > 0) {
+      if (p.phases & I2C_PH_BACKWARD) {
+        if (p.phases & I2C_PH_UPDATE_PRIORS) {
+          if (it0 & 1) {
+            prior = p.post;
+            post = p.prior;
+          }
+          latest = prior;
+        } else {
+          latest = post;
+        }
+        if (p.cov_ctrl)
+          for (int i = 0; i < it0; ++i) temp += p.dtemp;
+      }
+      flipped = (p.phases & I2C_PH_UPDATE_PRIORS) != 0;
+      if (p.phases & I2C_PH_MSTEP) own_alpha_valid = false;
+    }
+    for (int it = it0; it < it1; ++it) {
       Carry<DX> c;
       LogAcc ent_x;
       ent_x.reset();
@@ -2335,7 +2360,8 @@ struct Worker {
       p.info[b] = info;
     }
   }
-  __device__ void run() { run_impl<false>(0, 1, nullptr); }
+  __device__ void run() { run_impl<false>(0, 1, nullptr, 0, p.n_iter); }
+  __device__ void run_one(int it) { run_impl<false>(0, 1, nullptr, it, it + 1); }
 };
 
 // Opt a kernel in to > 48 KB of dynamic shared memory.  The attribute is per DEVICE: remembered per device ordinal (a
@@ -2368,8 +2394,55 @@ __global__ void __launch_bounds__(128, MINB) em_kernel(const __grid_constant__ K
   w.run();
 }
 
+// Throughput regime without wave quantisation: a work item is ONE EM iteration of one tile; the resident warps (148 x 3
+// blocks x 4 warps = one full wave of the spill-free 168-register variant) draw items from a ticket counter, ticket k =
+// (iteration k / ntiles, tile k % ntiles).  Iteration `it` of a tile needs iteration it-1 of the same tile: its ticket was
+// drawn ntiles tickets earlier, i.e. more than a full wave ago, so the acquire-spin on the tile's finished-iteration counter
+// almost never waits; it cannot deadlock (tickets are only held by running warps and only wait for smaller tickets).
+// A batch of 65 536 problems x 20 iterations is 40 960 items on 1 776 warps = 23.06 rounds instead of two waves of the
+// whole 20-iteration job at 115 % / 15 % fill.  The loop-carried state is rebuilt per item (Worker::run_impl, it0 > 0); records
+// written by the previous item of the tile -- possibly on another SM -- are ordered by fence + release / acquire at gpu scope.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <class Env>
+__global__ void __launch_bounds__(128, 3) em_ticket_kernel(const __grid_constant__ KParams pin) {
+  const int lane = threadIdx.x % TILE;
+  extern __shared__ __align__(128) double stage_smem[];
+  constexpr int PER_WARP = 2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars;  // staging buffers + mbarriers
+  double* base = stage_smem + (size_t)(threadIdx.x / TILE) * PER_WARP;
+  int* const ticket = pin.tickets;
+  int* const done = pin.tickets + 1;
+  const int total = pin.ntiles * pin.n_iter;
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(ticket, 1);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= total) break;
+    const int it = k / pin.ntiles, tile = k - it * pin.ntiles;
+    if (it > 0) {
+      if (lane == 0)
+        while (ld_acquire_gpu(done + tile) < it) __nanosleep(256);
+      __syncwarp();
+      asm volatile("fence.proxy.async;" ::: "memory");  // the records are read back with bulk copies
+    }
+    {
+      Worker<Env, false> w(pin, tile, lane, base + lane, reinterpret_cast<uint64_t*>(base + 2 * Lay<Env>::E_STAGE_TOT * TILE));
+      w.run_one(it);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_gpu(done + tile, it + 1);
+  }
+}
+
 // Latency-regime kernel: one block of W warps per tile (see Worker::run_impl<true>).
-template <class Env, int W, bool HOT>
+template <class Env, int W, int HOT>
 __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_constant__ KParams pin) {
   const int w = threadIdx.x / TILE, lane = threadIdx.x % TILE;
   extern __shared__ __align__(128) double stage_smem[];
@@ -2388,10 +2461,10 @@ __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_c
     wk.ztab_s = smem_addr(ztab);
     wk.ftab_s = smem_addr(ftab);
   }
-  wk.template run_impl<true>(w, W, red);
+  wk.template run_impl<true>(w, W, red, 0, pin.n_iter);
 }
 
-template <class Env, int W, bool HOT>
+template <class Env, int W, int HOT>
 static int launch_em_team_v(const KParams& p, cudaStream_t s) {
   // staging + mbarriers + reduction + progress counter (+ HOT: target / flag table of the horizon)
   const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars + 2 + (HOT ? (size_t)p.T * (Env::DZ + 1) : 0)) * sizeof(double);
@@ -2403,8 +2476,11 @@ static int launch_em_team_v(const KParams& p, cudaStream_t s) {
 }
 template <class Env, int W>
 static int launch_em_team(const KParams& p, cudaStream_t s) {
-  if (p.hot) return launch_em_team_v<Env, W, true>(p, s);
-  return launch_em_team_v<Env, W, false>(p, s);
+  if constexpr (Env::DY > 0) {
+    if (p.hot == 2) return launch_em_team_v<Env, W, 2>(p, s);
+  }
+  if (p.hot == 1) return launch_em_team_v<Env, W, 1>(p, s);
+  return launch_em_team_v<Env, W, 0>(p, s);
 }
 
 template <class Env, int MINB, bool LAT, bool LIN = false, bool GH = false>
@@ -2418,6 +2494,21 @@ static int launch_em_v(const KParams& p, cudaStream_t s, int threads) {
   // sub-partition; in the throughput regime the extra LDGSTS instructions cost more than they hide
   q.stage_meta = Lay<Env>::STAGED && LAT;
   em_kernel<Env, MINB, LAT, LIN, GH><<<blocks, threads, smem, s>>>(q);
+  return (int)cudaGetLastError();
+}
+
+template <class Env>
+static int launch_em_ticket(const KParams& p, cudaStream_t s) {
+  constexpr int WPB = 4, RESIDENT = 148 * 3;  // blocks of the full wave
+  const size_t smem = Lay<Env>::STAGED ? (size_t)WPB * (2 * Lay<Env>::E_STAGE_TOT * TILE + kNumBars) * sizeof(double) : 0;
+  if (int e = allow_big_smem<em_ticket_kernel<Env>>()) return e;
+  cudaError_t ce = cudaMemsetAsync(p.tickets, 0, (size_t)(p.ntiles + 1) * sizeof(int32_t), s);
+  if (ce != cudaSuccess) return (int)ce;
+  KParams q = p;
+  q.stage_meta = 0;
+  const long long items = (long long)p.ntiles * p.n_iter;
+  const int blocks = (int)((items + WPB - 1) / WPB < RESIDENT ? (items + WPB - 1) / WPB : RESIDENT);
+  em_ticket_kernel<Env><<<blocks, WPB * TILE, smem, s>>>(q);
   return (int)cudaGetLastError();
 }
 
@@ -2435,6 +2526,12 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
   if (p.linearize) return launch_em_v<Env, 1, true, true>(p, s, threads);
   // Gauss-Hermite grids: degree^n points per transform, one variant as well
   if (p.gh.degree > 0) return launch_em_v<Env, 1, true, false, true>(p, s, threads);
+  // A/B and tests: I2C_B200_MINB = 3 / 4 / 5 forces a throughput variant (5 = ticket kernel) whatever the batch size
+  if constexpr (Lay<Env>::N <= 3) {
+    if (p.minb == 5 && p.tickets && !(p.phases & I2C_PH_CALIBRATE)) return launch_em_ticket<Env>(p, s);
+    if (p.minb == 3) return launch_em_v<Env, 3, false>(p, s, 128);
+    if (p.minb == 4) return launch_em_v<Env, 4, false>(p, s, 128);
+  }
   // small batches: G lanes per problem (i2c_group.cuh); the launcher there decides
   {
     const int rc = launch_em_group_maybe<Env>(p, s);
@@ -2451,7 +2548,17 @@ static int launch_em_t(const KParams& p, cudaStream_t s) {
       // 8.8e9 updates/s at 56 832 and 113 664 problems, 10.3e9 against 9.7e9 at 262 144; 7.0e9 against 8.9e9 at 65 536)
       const int waves3 = (p.ntiles + 148 * 12 - 1) / (148 * 12);
       const bool fills3 = (long long)waves3 * 148 * 12 * 100 <= (long long)p.ntiles * 115;
-      const int minb = p.minb ? p.minb : (fills3 ? 3 : 4);
+      // several iterations in one launch: (tile, iteration) work items from a ticket counter keep the 1776 resident warps of the
+      // spill-free variant busy whatever the batch size (em_ticket_kernel).  Estimated rounds, in units of one full 168-register
+      // wave: items / 1776 (rounded up) against the static choice below (a 128-register wave holds 2368 warps and takes 1.56 x
+      // as long).  (I2C_B200_MINB = 5 forces it, 3 / 4 force the static variants: see above.)
+      if (p.tickets && !(p.phases & I2C_PH_CALIBRATE) && p.n_iter >= 2) {
+        const long long items = (long long)p.ntiles * p.n_iter;
+        const double rounds_ticket = (double)((items + 148 * 12 - 1) / (148 * 12));
+        const double rounds_static = fills3 ? (double)waves3 * p.n_iter : 1.56 * ((p.ntiles + 148 * 16 - 1) / (148 * 16)) * p.n_iter;
+        if (rounds_ticket <= rounds_static) return launch_em_ticket<Env>(p, s);  // (equal: measured 6 % faster, no wave edges)
+      }
+      const int minb = fills3 ? 3 : 4;
       if (minb == 3) return launch_em_v<Env, 3, false>(p, s, 128);
       return launch_em_v<Env, 4, false>(p, s, 128);
     }

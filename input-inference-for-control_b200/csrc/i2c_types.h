@@ -70,7 +70,8 @@ struct KParams {
   int32_t group_mode;      // -1 auto, 0 never, 1 always: G-lanes-per-problem kernel (i2c_group.cuh)
   int32_t group_max_tiles; // auto: use it up to this many tiles (0 = built-in policy)
   int32_t minb;            // A/B: resident 128-thread blocks per SM of the small-env throughput variant (0 = default 4)
-  int32_t hot;             // the common configuration (Worker<..., HOT>): fast_obs, shared targets, no aux records
+  int32_t hot;             // the common configuration (Worker<..., HOT>): fast_obs, shared targets, no aux records; 2 = cells with their own alpha allowed
+  int32_t* tickets;        // [1 + ntiles]: ticket counter and per-tile finished-iteration counters of em_ticket_kernel
 };
 
 // element counts of the records for given dims

@@ -30,9 +30,11 @@ class EnvSpec:
         return self.observe_terminal(x)
 
     # ---- linearisations for the Linearize inference on nonlinear envs.  The reference takes the dynamics Jacobian
-    # with autograd (env_autograd.py:22,57,170; model.py:158-164) -- absent from this image, PARITY UNPINNED -- here:
-    # central differences of the restated dynamics (relative accuracy ~1e-9); the cost-feature Jacobians are the
-    # analytic ones of env_def.py:278-298, 541-570, 700-761 written generically from the feature structure.
+    # with autograd (env_autograd.py:22,57,170; model.py:158-164) -- absent from this image -- here: the complex-step
+    # derivative of the restated dynamics (no truncation, no cancellation: the exact derivative to rounding, like autograd's).
+    # Pinned by tests/golden/*_linearize_*.npz: the unmodified reference run with the same complex-step stand-in for
+    # autograd.jacobian (oracle/ref_shim.py).  The cost-feature Jacobians are the analytic ones of env_def.py:278-298,
+    # 541-570, 700-761 written generically from the feature structure.
     def _obs_jac(self, z_fn, x, dim_in):
         z = z_fn(x)
         H = np.zeros(x.shape[:-1] + (z.shape[-1], dim_in))
@@ -48,13 +50,13 @@ class EnvSpec:
     def observe_terminal_jac(self, x):
         return self._obs_jac(self.observe_terminal, x, self.dim_x)
 
-    def forward_jac(self, xu, h=1e-6):
+    def forward_jac(self, xu, h=1e-30):
         f0 = self.dynamics(xu)
         J = np.zeros(xu.shape[:-1] + (self.dim_x, self.dim_xu))
         for i in range(self.dim_xu):
-            d = np.zeros(self.dim_xu)
-            d[i] = h
-            J[..., :, i] = (self.dynamics(xu + d) - self.dynamics(xu - d)) / (2 * h)
+            d = np.zeros(self.dim_xu, dtype=complex)
+            d[i] = 1j * h
+            J[..., :, i] = np.imag(self.dynamics(xu + d)) / h
         return f0, J
 
 

@@ -95,10 +95,26 @@ def install(paths=True, extra_stubs=()):
         ag.numpy = np
 
         def jacobian(fn, argnum=0):
-            def _raise(*a, **k):
-                raise NotImplementedError("autograd is not available in this image")
+            """Stand-in for ``autograd.jacobian`` (env_autograd.py:22,57,170), which is absent from this image: the
+            complex-step derivative Im f(x + i h e_j) / h with h = 1e-30.  For the reference's dynamics functions (sums,
+            products, sin / cos, np.power, np.linalg.inv, np.clip away from the limits -- all analytic) it has no
+            truncation and no cancellation error: it equals the exact derivative, which is what autograd returns, to
+            rounding.  The reference's OWN dynamics functions are differentiated, unmodified.  Result shape as
+            autograd's: ``fn(x).shape + x.shape``."""
+            def jac(*args):
+                x = np.asarray(args[argnum], dtype=float)
+                y0 = np.asarray(fn(*args))
+                out = np.empty(y0.shape + x.shape)
+                h = 1e-30
+                for idx in np.ndindex(*x.shape):
+                    xc = x.astype(complex)
+                    xc[idx] += 1j * h
+                    a = list(args)
+                    a[argnum] = xc
+                    out[(Ellipsis,) + idx] = np.imag(np.asarray(fn(*a))) / h
+                return out
 
-            return _raise
+            return jac
 
         ag.jacobian = jacobian
         sys.modules["autograd"] = ag

@@ -276,6 +276,27 @@ def lqr():
     save("linear_covctrl_linearize", d)
 
 
+def linearize_nonlinear():
+    """Linearize inference on the nonlinear envs (experiments pendulum_known.py, cartpole_known.py,
+    double_cartpole_known(_lin).py): the reference's I2cCell._forward_msgs_linearize / _backward_msgs_linearize with the
+    Jacobians of its OWN env_autograd.py dynamics.  autograd is absent from this image; oracle/ref_shim.py supplies
+    autograd.jacobian as the complex-step derivative (exact to rounding for these analytic functions).  Same inputs as
+    tests/test_gpu_lqr.py::test_linearize_nonlinear_envs, problem 0."""
+    cases = [
+        ("pendulum_linearize_T40", "PendulumKnown", np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), 100.0, [0.3, 0.5], 40),
+        ("cartpole_linearize_T40", "CartpoleKnown", np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0]), 80.0, 0.05, 40),
+        ("double_cartpole_linearize_T30", "DoubleCartpoleKnown",
+         1e-3 * np.diag([1.0, 1.0, 100.0, 1.0, 100.0, 10.0, 1.0, 1.0]), 1e-4 * np.eye(1), 0.05, 0.02, 30),
+    ]
+    for name, env, Q, R, alpha, xs, T in cases:
+        rng = np.random.default_rng(4)
+        e = oenvs.make(env)
+        B = 16  # the GPU test draws a batch of 16 with this seed; the golden is its problem 0
+        x0 = e.x0 + np.asarray(xs) * rng.normal(size=(B, e.dim_x))
+        mu_u = 1e-2 * rng.normal(size=(B, T, e.dim_u))
+        em_run(name, env, T, Q, R, Q, alpha, 0.5, mu_u[0], np.eye(e.dim_u), n_dump=3, n_total=3, x0=x0[0], inference=Lin())
+
+
 # ----------------------------------------------------------------------------- 4. MPC (quadrotor, fp64 stand-in)
 def mpc():
     """policy/mpc.py:115-182 driven as mpc_quad.py:538-652 does, with the fp64 quadrotor restatement
@@ -490,13 +511,15 @@ def rollouts():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quad", "em", "lqr", "mpc", "gh", "eval", "ll", "roll"]
+    which = sys.argv[1:] or ["quad", "em", "lqr", "linnl", "mpc", "gh", "eval", "ll", "roll"]
     if "quad" in which:
         quad_kat()
     if "em" in which:
         em_runs()
     if "lqr" in which:
         lqr()
+    if "linnl" in which:
+        linearize_nonlinear()
     if "mpc" in which:
         mpc()
     if "gh" in which:

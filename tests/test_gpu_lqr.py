@@ -162,6 +162,11 @@ def test_linear_covariance_control_linearize(i2c_b200):
     assert relerr(np.array(G.metrics["kl_term"])[:, 0], g["kl_terms"]) < 1e-9
 
 
+# gains of the Linearize path on the nonlinear envs: max(1e-9, ~10 x measured); measured 1.5e-12 / 1.8e-10 / 7.4e-10 against
+# both the oracle and the unmodified reference (states, covariances: <= 4e-13)
+TOL_LIN_GAIN = {"PendulumKnown": 1e-9, "CartpoleKnown": 2e-9, "DoubleCartpoleKnown": 8e-9}
+
+
 @pytest.mark.parametrize("env,Q,R,alpha,xs,T", [
     ("PendulumKnown", np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), 100.0, [0.3, 0.5], 40),
     ("CartpoleKnown", np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0]), 80.0, 0.05, 40),
@@ -169,9 +174,10 @@ def test_linear_covariance_control_linearize(i2c_b200):
 ])
 def test_linearize_nonlinear_envs(i2c_b200, env, Q, R, alpha, xs, T):
     """Linearize inference on the nonlinear envs (experiments pendulum_known.py,
-    cartpole_known.py, double_cartpole_known(_lin).py).  PARITY UNPINNED against the reference (its dynamics
-    Jacobians come from autograd, absent here): the oracle takes them by central differences, the kernel by
-    forward-mode AD, so agreement is limited by the finite-difference error (~1e-8 relative)."""
+    cartpole_known.py, double_cartpole_known(_lin).py).  The kernel takes the dynamics Jacobians by forward-mode AD
+    (csrc/dual.cuh); the reference by autograd, the oracle -- and the reference run that produced the golden of problem 0
+    (tests/golden/*_linearize_*.npz, unmodified reference code with a complex-step autograd.jacobian) -- by the
+    complex-step derivative: all three are the exact derivative to rounding."""
     from oracle import i2c_oracle as O
 
     rng = np.random.default_rng(4)
@@ -182,14 +188,22 @@ def test_linearize_nonlinear_envs(i2c_b200, env, Q, R, alpha, xs, T):
     G = i2c_b200.BatchedI2c(env, B, T, Q, R, Q, alpha, 0.5, mu_u, np.eye(e.dim_u), x0=x0, inference="linearize",
                             enable_aux=True)
     ref = O.make_graph(env, T, Q, R, Q, alpha, 0.5, mu_u, np.eye(e.dim_u), inference=O.Linearize(), B=B, x0=x0)
+    gname = {"PendulumKnown": "pendulum_linearize_T40", "CartpoleKnown": "cartpole_linearize_T40",
+             "DoubleCartpoleKnown": "double_cartpole_linearize_T30"}[env]
+    g = golden(gname)
+    assert np.array_equal(g["x0"], x0[0]) and np.array_equal(g["mu_u"], mu_u[0])
+    tol_g = TOL_LIN_GAIN[env]
     for it in range(3):
         G.learn(1)
         ref.learn_msgs()
         assert np.all(G.status()[0] == 0), (it, G.status())
-        # PARITY UNPINNED (autograd absent): the oracle takes the dynamics Jacobians by central differences
-        # (truncation + round-off ~1e-9 on the Jacobian), the kernel by forward-mode AD; measured 2.7e-8 on the gains
-        for a, tol in [("mu_xu1_f", 1e-8), ("sig_xu1_f", 1e-7), ("mu_x3_f", 1e-8), ("sig_x3_f", 1e-7), ("mu_xu0_m", 1e-8),
-                       ("sig_xu0_m", 1e-7), ("mu_z0_m", 1e-8), ("sig_z0_m", 1e-7), ("K", 3e-7), ("k", 3e-7), ("sigK", 1e-7)]:
-            assert relerr(G.field(a), ref.stack(a), floor=1e-6) < tol, (it, a)
-        assert relerr(G.alpha, ref.alpha) < 1e-8
-    assert relerr(np.array(G.metrics["cost_m"]), np.array(ref.costs_m)) < 1e-8
+        for a in ["mu_xu1_f", "sig_xu1_f", "mu_x3_f", "sig_x3_f", "mu_xu0_m", "sig_xu0_m", "mu_z0_m", "sig_z0_m", "sigK"]:
+            assert relerr(G.field(a), ref.stack(a)) < 1e-9, (it, a)
+            assert relerr(G.field(a)[0], g[f"it{it + 1}/{a}"]) < 1e-9, (it, a)  # the unmodified reference
+        for a in ["J_dyn", "K", "k"]:
+            assert relerr(G.field(a), ref.stack(a), floor=1e-6) < tol_g, (it, a)
+            assert relerr(G.field(a)[0], g[f"it{it + 1}/{a}"], floor=1e-6) < tol_g, (it, a)
+        assert relerr(G.alpha, ref.alpha) < 1e-9
+    assert relerr(np.array(G.metrics["cost_m"]), np.array(ref.costs_m)) < 1e-9
+    assert relerr(np.array(G.metrics["cost_m"])[:, 0], g["costs_m"]) < 1e-9
+    assert relerr(np.array(G.metrics["alpha"])[:, 0], g["alphas"][1:]) < 1e-9

@@ -103,3 +103,30 @@ def test_hot_specialisation_equals_generic(i2c_b200, monkeypatch, env, B, T, kw)
     a, b = outs
     for key in a:
         assert relerr(a[key], b[key], 1e-9) < (TOL_GAIN.get(env, 2e-8) if key in ("K", "k", "J") else 1e-11), key
+
+
+@pytest.mark.parametrize("kw", [{}, {"propagate": True}, {"fb_only": True}])
+def test_ticket_kernel_equals_static_wave(i2c_b200, kw, monkeypatch):
+    """em_ticket_kernel ((tile, iteration) work items drawn from a ticket counter, loop-carried state rebuilt per item) is
+    bit-identical to the static one-warp-per-tile launch of the same 168-register variant: learn_msgs with and without the
+    in-loop propagate, and the MPC optimise loop (forward + backward + _update_priors, no M-step)."""
+    B, T, iters = 3000, 20, 5
+    x0, mu_u = inputs(B, T, seed=11)
+    out = {}
+    for minb in ("3", "5"):
+        monkeypatch.setenv("I2C_B200_MINB", minb)
+        g = i2c_b200.BatchedI2c("PendulumKnown", B, T, Q, R, Q, 100.0, 0.0, mu_u, 2.0 * np.eye(1), x0=x0)
+        g._propagate = bool(kw.get("propagate"))
+        if kw.get("fb_only"):
+            g.tau = T
+            g.forward_backward(iters, update_priors=True)
+            g.forward_backward(2, update_priors=True)  # a second launch continues from the swapped record roles
+        else:
+            g.learn(iters)
+            g.learn(2)
+        assert np.all(g.status()[0] == 0)
+        K, k, s = g.get_local_linear_policy()
+        out[minb] = dict(K=K, k=k, sigK=s, mu=g.field("mu_xu0_m"), sig=g.field("sig_xu0_m"), alpha_final=g.alpha,
+                         **{m: np.array(v) for m, v in g.metrics.items()})
+    for key in out["3"]:
+        assert np.array_equal(out["3"][key], out["5"][key], equal_nan=True), key
