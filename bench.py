@@ -33,8 +33,8 @@ F_ALG, B_ALG = 3192.0, 704.0
 # `ncu --set full` capture / updates in that launch): profiles/r01i_ncu_full_em_team_kernel_pendulum_4096.txt
 # latency kernel (em_team_kernel<EnvPendulum,8,HOT>, 4096 x 200): profiles/r02l_ncu_full_em_team_kernel_pendulum_4096.txt
 NCU_DRAM_BYTES_PER_UPDATE = (286.220544e6 + 399.501568e6) / (2 * 4096 * 200)
-# throughput kernel (em_kernel<EnvPendulum,4>, 65 536 x 200): profiles/r01d_ncu_full_em_kernel_pendulum_65536.txt (13.35 GB / 26.2 M)
-NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT = 509.0
+# throughput kernel: round 1 em_kernel<EnvPendulum,4> 509 B/update (profiles/r01d_ncu_full_em_kernel_pendulum_65536.txt); round 2:
+NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT = 507.0  # em_ticket_kernel, profiles/r02_ncu_full_em_ticket_kernel_pendulum_65536.txt (16.61 GB / 32.768 M updates)
 FP64_NOMINAL_TFLOPS = 37.2  # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
 
 
@@ -264,7 +264,8 @@ def run_cuda(args, rank, world, local_rank):
     pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
     h_x0, h_s0 = pin(B, 2), pin(B, 2, 2)
     h_x0[:], h_s0[:] = g.x0, g.sig_x0
-    h_m = pin(2, B)
+    h_m2 = [pin(2, B), pin(2, B)]
+    h_m = h_m2[0]
     h_pol = [(pin(B, T, 1, 2), pin(B, T, 1), pin(B, T, 1, 1)) for _ in range(2)]
     h_K, h_k, h_s = h_pol[0]
     L = g.lib
@@ -276,12 +277,24 @@ def run_cuda(args, rank, world, local_rank):
         capi.check(L.i2c_run(g._h, 1, capi.PH_LEARN))
         capi.check(L.i2c_get_metrics(g._h, capi.ptr(m_ids), 2, capi.ptr(h_m), 1))  # alpha -> h_m[0], cost -> h_m[1]; one sync
 
+    log = np.zeros((2, 2))  # what the host does with a step's result (scripts/i2c_run.py:84-88 prints cost and alpha)
+
+    def step_pipelined(i):
+        # step i is queued (belief upload, learn_msgs, read-back of cost + alpha through staging slot i & 1) BEFORE the host
+        # collects step i-1: the stream never drains, the D2H of a step overlaps the next step's kernel
+        capi.check(L.i2c_set_initial_state_async(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))
+        capi.check(L.i2c_run(g._h, 1, capi.PH_LEARN))
+        capi.check(L.i2c_get_last_metrics_async(g._h, capi.ptr(m_ids), 2, capi.ptr(h_m2[i & 1]), i & 1))
+        if i > 0:
+            capi.check(L.i2c_metrics_wait(g._h, (i - 1) & 1))
+            log[(i - 1) & 1] = h_m2[(i - 1) & 1][:, 0]
+
     def final_gather():
         # the path's only collective: final gather of controllers and costs over NVLink
         from i2c_b200 import dist as idist
 
         Kd, kd, sd = g.policy_device_tensors()
-        cost = torch.from_numpy(np.ascontiguousarray(h_m[1])).to(Kd.device)
+        cost = torch.from_numpy(np.ascontiguousarray(h_m2[(Ke - 1) & 1][1])).to(Kd.device)
         gathered = idist.gather_controllers(Kd, kd, sd, world * B, extra=(cost,))
         assert gathered[0].shape[0] == world * B
         torch.cuda.synchronize(dev)
@@ -290,8 +303,10 @@ def run_cuda(args, rank, world, local_rank):
 
     def e2e_run(n):
         ta = time.perf_counter()
-        for _ in range(n):
-            step_metrics_only()
+        for i in range(n):
+            step_pipelined(i)
+        capi.check(L.i2c_metrics_wait(g._h, (n - 1) & 1))
+        log[(n - 1) & 1] = h_m2[(n - 1) & 1][:, 0]
         tb = time.perf_counter()
         # the rank's own controllers go to pinned host memory on the copy stream (PCIe) WHILE the ranks gather over NVLink
         capi.check(L.i2c_get_policy_async(g._h, capi.ptr(h_K), capi.ptr(h_k), capi.ptr(h_s)))
@@ -313,6 +328,17 @@ def run_cuda(args, rank, world, local_rank):
     h2d = h_x0.nbytes + h_s0.nbytes
     d2h_step = h_m.nbytes
     d2h_once = h_K.nbytes + h_k.nbytes + h_s.nbytes
+
+    # the same loop with a host synchronisation in every step (i2c_get_metrics: the host sees cost / alpha before it queues the
+    # next step), side key
+    Ks = max(3, min(Ke, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ks):
+        step_metrics_only()
+    barrier()
+    e2es_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2es_value = world * B * T * Ks / (e2es_ms * 1e-3)
 
     # The reference's scripts/i2c_run.py additionally reads the controller after EVERY iteration (:89-98, for its roll-out
     # evaluation on the host); the same loop with that per-step 26 MB read-back, for comparison (side key):
@@ -364,9 +390,12 @@ def run_cuda(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_step,
                 "d2h_bytes_once": d2h_once, "steps": Ke, "ms_per_step": e2e_ms / Ke, "breakdown_ms_max_over_ranks": parts,
                 "what": "per step: H2D start-state belief (pinned), one learn_msgs through the C-ABI, D2H cost + alpha of every "
-                        "problem (synchronous); after the last step, inside the timed region: D2H of K, k, sigK of this rank "
+                        "problem (pipelined: step i+1 is queued before the host collects step i, i2c_get_last_metrics_async); after the last step, inside the timed region: D2H of K, k, sigK of this rank "
                         "(once, on the copy stream)" + ("; concurrently the NCCL all_gather of controllers and costs over NVLink" if world > 1 else "")
                         + (f"; process bound to the {numa} CPUs local to its GPU" if numa else "")},
+        "e2e_synchronous_steps": {"value": e2es_value, "unit": UNIT, "steps": Ks, "ms_per_step": e2es_ms / Ks,
+                                  "what": "as e2e without the final controller read-back, but the host waits for cost + alpha of "
+                                          "step i before it queues step i+1 (i2c_get_metrics): one stream drain per step"},
         "e2e_policy_every_step": {"value": e2ep_value, "unit": UNIT, "steps": Kp, "h2d_bytes_per_step": h2d,
                                   "d2h_bytes_per_step": d2h_step + d2h_once,
                                   "what": "as e2e, but K, k, sigK are read back after EVERY step (scripts/i2c_run.py:89-98 does "
@@ -418,8 +447,8 @@ def run_cuda(args, rank, world, local_rank):
         line["saturation"] = {"problems": Bs, "value": rate_s, "unit": UNIT, "ms_per_step": ms_i,
                               "hbm_frac_by_algorithmic_bytes": B_ALG * rate_s / 1e9 / hbm_peak,
                               "hbm_frac_by_measured_traffic": NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT * rate_s / 1e9 / hbm_peak,
-                              "hbm_frac_note": "by ALGORITHMIC bytes (704 B/update); the throughput kernel moves 509 B/update "
-                                               "(ncu r01d, packed triangles), i.e. %.2f of the measured copy bandwidth"
+                              "hbm_frac_note": "by ALGORITHMIC bytes (704 B/update); em_ticket_kernel moves 507 B/update "
+                                               "(ncu r02, packed triangles), i.e. %.2f of the measured copy bandwidth"
                                                % (NCU_DRAM_BYTES_PER_UPDATE_THROUGHPUT * rate_s / 1e9 / hbm_peak),
                               "fp64_frac_of_measured": (F_ALG * rate_s / 1e12 / fp64_peak) if fp64_peak else None,
                               "failed_problems": failed}

@@ -205,6 +205,12 @@ int i2c_get_metric(i2c_handle_t h, int32_t metric, double* out, int32_t n_iter);
 /* Several metrics with ONE synchronisation: out[n_metrics][n_iter][B] (e.g. cost and alpha of the last iteration, the
  * per-step read-back of an EM loop: i2c_run.py:109-113 reads i2c.costs_m[-1], i2c.alphas[-1] every iteration). */
 int i2c_get_metrics(i2c_handle_t h, const int32_t* metrics, int32_t n_metrics, double* out, int32_t n_iter);
+/* Pipelined variant for host loops that log a step's cost / alpha (scripts/i2c_run.py:84-88 prints them per iteration) but do
+ * not feed them back: gathers the metrics of the LAST iteration of the most recent i2c_run into staging slot `slot` (0 / 1) and
+ * copies them to the page-locked `out` [n_metrics][B] on the copy stream.  i2c_metrics_wait(slot) blocks until that copy has
+ * landed.  With two slots the host queues step i+1 before it collects step i: the stream never drains. */
+int i2c_get_last_metrics_async(i2c_handle_t h, const int32_t* metrics, int32_t n_metrics, double* out, int32_t slot);
+int i2c_metrics_wait(i2c_handle_t h, int32_t slot);
 int i2c_get_status(i2c_handle_t h, int32_t* status /*[B]*/, int32_t* info /*[B]: (iter<<16 | cell)*/);
 /* The per-problem status / info words are sticky (the kernels only write them while they are OK): clear them, e.g. after the
  * caller handled a failure (the reference raises LinAlgError once, quadrature.py:17-24; a later sweep starts clean). */

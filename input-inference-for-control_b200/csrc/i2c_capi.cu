@@ -132,7 +132,9 @@ struct i2c_handle_s {
   KParams kp;  // constants + pointers template
   int last_n_iter;
   long long launches;
-  cudaEvent_t ev0, ev1, ev_unpacked, ev_copied;
+  cudaEvent_t ev0, ev1, ev_unpacked, ev_copied, ev_mstaged[2], ev_mcopied[2];
+  bool mpending[2];
+  double* mstage;  // [2][I2C_M_COUNT][Bpad]: staging slots of i2c_get_last_metrics_async
   cudaStream_t copy_stream;
   bool copy_pending;
   bool problem_set;
@@ -235,6 +237,19 @@ __global__ void dfma_peak_kernel(double* out, int iters, double b, double c) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// rows of the metrics table -> one contiguous [n][B] block (i2c_get_last_metrics_async)
+struct MetricIds {
+  int32_t v[16];
+};
+__global__ void gather_metrics_kernel(const double* __restrict__ metrics, MetricIds ids, int n, int it, int max_iters, int B, int Bpad,
+                                      double* __restrict__ out) {
+  const size_t total = (size_t)n * B;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / B), b = (int)(i % B);
+    out[i] = metrics[((size_t)ids.v[m] * max_iters + it) * Bpad + b];
+  }
+}
+
 // tiny by-value setters: let the MPC step update one cell's metadata without host staging / synchronisation
 struct SmallVals {
   double v[16];
@@ -298,7 +313,7 @@ static inline int nblocks(size_t total) {
 // ----------------------------------------------------------------------------------------- layout
 struct WsLayout {
   size_t recA, recB, filt, auxf, auxb, pf, ric, term, x0, sig_x0, alpha, alpha_cell, z_cell, z_term_pp, envpar, metrics, scratch, policy_out, flags,
-      index, status, info, tickets, total, scratch_elems;
+      index, status, info, tickets, mstage, total, scratch_elems;
 };
 
 static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
@@ -338,6 +353,7 @@ static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
   w.index = take(T, 4);
   w.status = take(Bpad, 4);
   w.info = take(Bpad, 4);
+  w.mstage = take(2 * (size_t)I2C_M_COUNT * Bpad, 8);
   w.tickets = take(nt + 1, 4);  // em_ticket_kernel: ticket counter + finished iterations per tile
   w.total = off;
   return w;
@@ -445,6 +461,7 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
   h->status = (int32_t*)(h->ws + w.status);
   h->info = (int32_t*)(h->ws + w.info);
   h->tickets = (int32_t*)(h->ws + w.tickets);
+  h->mstage = (double*)(h->ws + w.mstage);
   h->problem_set = false;
   h->launches = 0;
   h->last_n_iter = 0;
@@ -453,6 +470,11 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
   cudaEventCreate(&h->ev1);
   cudaEventCreateWithFlags(&h->ev_unpacked, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_mstaged[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_mcopied[i], cudaEventDisableTiming);
+    h->mpending[i] = false;
+  }
   cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
   h->copy_pending = false;
   CUDA_OK(cudaMemsetAsync(h->ws, 0, w.total, h->stream));
@@ -470,6 +492,10 @@ int i2c_destroy(i2c_handle_t h) {
   cudaEventDestroy(h->ev1);
   cudaEventDestroy(h->ev_unpacked);
   cudaEventDestroy(h->ev_copied);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(h->ev_mstaged[i]);
+    cudaEventDestroy(h->ev_mcopied[i]);
+  }
   if (h->own_ws) cudaFree(h->ws);
   delete h;
   return 0;
@@ -1228,6 +1254,45 @@ int i2c_get_metrics(i2c_handle_t h, const int32_t* metrics, int32_t n_metrics, d
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
+// Pipelined read of a step's result: the metrics of the LAST iteration of the most recent i2c_run are gathered into staging
+// slot `slot` (0 / 1) on the handle's stream and copied to `out` ([n_metrics][B], page-locked) on the copy stream; the
+// caller may queue the next step at once and collects the numbers later with i2c_metrics_wait(slot).  With two slots the
+// host stays one step ahead of the device: no per-step drain of the stream (the synchronous i2c_get_metrics costs one).
+int i2c_get_last_metrics_async(i2c_handle_t h, const int32_t* metrics, int32_t n_metrics, double* out, int32_t slot) {
+  REQUIRE(h && metrics && out && n_metrics >= 1 && n_metrics <= I2C_M_COUNT && n_metrics <= 16, "bad argument");
+  REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  REQUIRE(h->last_n_iter >= 1, "no i2c_run yet");
+  DeviceGuard device_guard_(h->cfg.device);
+  MetricIds ids;
+  for (int i = 0; i < n_metrics; ++i) {
+    REQUIRE(metrics[i] >= 0 && metrics[i] < I2C_M_COUNT, "unknown metric id");
+    ids.v[i] = metrics[i];
+  }
+  // the previous copy out of this slot must have drained before the slot is overwritten
+  if (h->mpending[slot]) CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_mcopied[slot], 0));
+  double* st = h->mstage + (size_t)slot * I2C_M_COUNT * h->Bpad;
+  const size_t total = (size_t)n_metrics * h->B;
+  gather_metrics_kernel<<<nblocks(total), 256, 0, h->stream>>>(h->metrics, ids, n_metrics, h->last_n_iter - 1, h->cfg.max_iters, h->B,
+                                                             h->Bpad, st);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(h->ev_mstaged[slot], h->stream));
+  CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_mstaged[slot], 0));
+  CUDA_OK(cudaMemcpyAsync(out, st, total * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_OK(cudaEventRecord(h->ev_mcopied[slot], h->copy_stream));
+  h->mpending[slot] = true;
+  return 0;
+}
+
+int i2c_metrics_wait(i2c_handle_t h, int32_t slot) {
+  REQUIRE(h, "NULL handle");
+  REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  DeviceGuard device_guard_(h->cfg.device);
+  if (h->mpending[slot]) CUDA_OK(cudaEventSynchronize(h->ev_mcopied[slot]));
+  h->mpending[slot] = false;
+  return 0;
+}
+
 int i2c_get_policy_async(i2c_handle_t h, double* K, double* k, double* sigK) {
   REQUIRE(h && K && k && sigK, "NULL argument");
   DeviceGuard device_guard_(h->cfg.device);

@@ -67,7 +67,7 @@ EXPORTS = [
     "i2c_get_status", "i2c_clear_status", "i2c_get_field", "i2c_set_field", "i2c_field_shape", "i2c_get_policy", "i2c_get_policy_async", "i2c_copy_wait", "i2c_get_policy_dev",
     "i2c_shift_horizon", "i2c_ckf_step", "i2c_mpc_step", "i2c_get_initial_state", "i2c_get_first_action", "i2c_quadrature", "i2c_quadrature_gh", "i2c_gauss_hermite",
     "i2c_rollout", "i2c_snapshot_bytes", "i2c_snapshot", "i2c_restore", "i2c_kernel_launches", "i2c_last_run_ms", "i2c_dfma_peak", "i2c_fastmath_probe",
-    "i2c_host_alloc", "i2c_host_free",
+    "i2c_host_alloc", "i2c_host_free", "i2c_get_last_metrics_async", "i2c_metrics_wait",
     "i2c_last_error",
     "i2c_build_info",
 ]
@@ -142,6 +142,8 @@ def lib():
     L.i2c_dfma_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     L.i2c_fastmath_probe.argtypes = [C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp]
     L.i2c_env_dims.argtypes = [C.c_int32, _ip, _ip, _ip, _ip, _ip, _ip]
+    L.i2c_get_last_metrics_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    L.i2c_metrics_wait.argtypes = [C.c_void_p, C.c_int32]
     L.i2c_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.i2c_host_free.argtypes = [C.c_void_p]
     _lib = L

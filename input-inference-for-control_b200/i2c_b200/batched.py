@@ -261,6 +261,18 @@ class BatchedI2c:
     def wait_copies(self):
         capi.check(self.lib.i2c_copy_wait(self._h))
 
+    def last_metrics_async(self, names, out, slot):
+        """Queue the read-back of the given metrics of the LAST iteration of the most recent sweep into the page-locked array
+        ``out`` [len(names), B] (capi.pinned_empty) through staging slot 0 / 1 and return at once; ``metrics_wait(slot)``
+        blocks until the numbers have landed.  Lets a logging loop (scripts/i2c_run.py:84-88) queue step i+1 before it
+        collects step i."""
+        ids = np.array([capi.METRICS[n] for n in names], np.int32)
+        assert out.shape == (len(names), self.B) and out.dtype == np.float64 and out.flags.c_contiguous
+        capi.check(self.lib.i2c_get_last_metrics_async(self._h, capi.ptr(ids), len(names), capi.ptr(out), int(slot)))
+
+    def metrics_wait(self, slot):
+        capi.check(self.lib.i2c_metrics_wait(self._h, int(slot)))
+
     def get_cell_flags(self):
         f = np.zeros(self.H, np.int32)
         capi.check(self.lib.i2c_get_cell_flags(self._h, capi.ptr(f)))

@@ -282,3 +282,28 @@ def test_initial_state_async_upload(i2c_b200):
     assert np.array_equal(Ga.field("K"), Gb.field("K")) and np.array_equal(Ga.alpha, Gb.alpha)
     xa, sa = Ga.get_initial_state()
     assert np.array_equal(xa, x0) and relerr(sa, s0) < 1e-15
+
+
+def test_pipelined_metrics_read(i2c_b200):
+    """i2c_get_last_metrics_async / i2c_metrics_wait (two staging slots, copy stream): a loop that queues step i+1 before it
+    collects step i sees exactly the numbers of the synchronous getter."""
+    capi = i2c_b200.capi
+    Q, R = np.diag([1.0, 100.0, 1.0]), np.diag([2.0])
+    Ga, _ = make_pair(i2c_b200, "PendulumKnown", 500, 30, Q, R, Q, 100.0, 0.0, 5, np.array([0.3, 0.5]), 2.0 * np.eye(1), enable_aux=False)
+    Gb, _ = make_pair(i2c_b200, "PendulumKnown", 500, 30, Q, R, Q, 100.0, 0.0, 5, np.array([0.3, 0.5]), 2.0 * np.eye(1), enable_aux=False)
+    names = ["alpha", "cost_m", "policy_entropy"]
+    out = [capi.pinned_empty((3, 500)), capi.pinned_empty((3, 500))]
+    got = []
+    n = 7
+    for i in range(n):
+        Ga.run(1 if i % 3 else 2, capi.PH_LEARN, collect=False)  # (the async getter reads the LAST iteration of the run)
+        Ga.last_metrics_async(names, out[i & 1], i & 1)
+        if i > 0:
+            Ga.metrics_wait((i - 1) & 1)
+            got.append(out[(i - 1) & 1].copy())
+    Ga.metrics_wait((n - 1) & 1)
+    got.append(out[(n - 1) & 1].copy())
+    for i in range(n):
+        Gb.run(1 if i % 3 else 2, capi.PH_LEARN, collect=True)
+        ref = np.stack([np.array(Gb.metrics[m][-1]) for m in names])
+        assert np.array_equal(got[i], ref), i
