@@ -473,9 +473,73 @@ def run_cuda(args, rank, world, local_rank):
             line["cpu_baseline"] = port
         if mpc is not None:
             line["mpc"]["cpu_baseline"] = mpc_cpu_baseline(cores)
+        line["config1"] = config1_leg()
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def config1_leg(n_iter=200, n_ref=5):
+    """BASELINE configs[0]: scripts/i2c_run.py pendulum_known_quad -- ONE problem, T = 100, the script's own loop
+    (i2c_run.py:84-98: learn_msgs, then both controller getters, every iteration) through the drop-in mirror
+    (`from i2c.i2c import I2cGraph`, B = 1: one tile, one block) against the unmodified reference on one host core.
+    A single problem cannot fill a GPU: this is the latency of the drop-in path, not a throughput number."""
+    import sys as _sys
+
+    pkg = os.path.join(ROOT, "input-inference-for-control_b200")
+    if pkg not in _sys.path:
+        _sys.path.insert(0, pkg)
+    from i2c.exp_types import CubatureQuadrature
+    from i2c.i2c import I2cGraph
+    from i2c.model import make_env_model
+    from i2c.policy.linear import ExpertTimeIndexedLinearGaussianPolicy, TimeIndexedLinearGaussianPolicy
+
+    T = 100
+    Q, R, Qf = np.diag([1.0, 100.0, 1.0]), np.diag([2.0]), np.diag([1.0, 100.0, 1.0])  # experiments/pendulum_known_quad.py
+    rng = np.random.default_rng(0)
+    mu_u = 1e-2 * rng.normal(size=(T, 1))
+    model = make_env_model("PendulumKnown", None)
+    g = I2cGraph(model, T, Q, R, Qf, 100.0, 0.0, mu_u, 2.0 * np.eye(1), None, None, CubatureQuadrature(1, 0, 0), res_dir=None)
+    pl = TimeIndexedLinearGaussianPolicy(0.0 * np.eye(1), T, 1, 2)
+    pe = ExpertTimeIndexedLinearGaussianPolicy(0.0 * np.eye(1), T, 1, 2, soft=False)
+    g.reset_metrics()
+
+    def it():
+        g.learn_msgs()
+        pl.write(*g.get_local_linear_policy())
+        pe.write(*g.get_local_expert_linear_policy())
+
+    for _ in range(3):
+        it()
+    t0 = time.perf_counter()
+    for _ in range(n_iter):
+        it()
+    ms = (time.perf_counter() - t0) * 1e3 / n_iter
+    t0 = time.perf_counter()
+    for _ in range(n_iter):
+        g.learn_msgs()
+    ms_learn = (time.perf_counter() - t0) * 1e3 / n_iter
+    out = {"workload": "scripts/i2c_run.py pendulum_known_quad: 1 problem x T=100, learn_msgs + both controller getters per "
+                       "iteration through the drop-in mirror (BASELINE configs[0])",
+           "ms_per_em_iteration": ms, "ms_per_learn_msgs_only": ms_learn, "em_iterations_timed": n_iter,
+           "final_alpha": float(g.alphas[-1])}
+    if cpu_kind() == "reference":
+        from oracle import ref_shim
+
+        ns = ref_shim.load()
+        sys_ = ns.model.make_env_model("PendulumKnown", None)
+        r = ns.i2c.I2cGraph(sys_, T, Q, R, Qf, 100.0, 0.0, mu_u, 2.0 * np.eye(1), None, None, ns.exp_types.CubatureQuadrature(1, 0, 0))
+        r.learn_msgs()
+        t0 = time.perf_counter()
+        for _ in range(n_ref):
+            r.learn_msgs()
+            r.get_local_linear_policy()
+            r.get_local_expert_linear_policy()
+        out["cpu_baseline"] = {"value": (time.perf_counter() - t0) * 1e3 / n_ref, "unit": "ms per EM iteration", "cores": 1,
+                               "kind": "reference", "sample": f"{n_ref} iterations of the unmodified reference after 1 warm-up"}
+        out["speedup_vs_reference"] = out["cpu_baseline"]["value"] / ms
+        ref_shim.unload()
+    return out
 
 
 def scan_leg(args, dev):

@@ -2444,6 +2444,11 @@ __global__ void __launch_bounds__(128, 3) em_ticket_kernel(const __grid_constant
 // Latency-regime kernel: one block of W warps per tile (see Worker::run_impl<true>).
 template <class Env, int W, int HOT>
 __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_constant__ KParams pin) {
+  // (W = 4, two blocks per SM: warp k of either block sits on sub-partition k, so both main warps share sub-partition 0.
+  // Tried in round 2: rotating the second block's warp roles by two (its main warp on sub-partition 2, next to a tail warp of
+  // the first block): 0.337 instead of 0.328 ms per iteration at 8192 pendulum problems; reversing them (each main warp next to
+  // the other block's copy warp, whose mbarrier polling takes issue slots): 0.411 ms.  The W = 4 regime is bound by its two
+  // tail warps per tile, not by the main warps' placement.)
   const int w = threadIdx.x / TILE, lane = threadIdx.x % TILE;
   extern __shared__ __align__(128) double stage_smem[];
   double* red = stage_smem + Lay<Env>::E_TEAM_STAGE * TILE + kNumBars;
