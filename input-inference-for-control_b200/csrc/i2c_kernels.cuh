@@ -580,6 +580,7 @@ struct Worker {
   double* stage;  // this warp's double buffer: [2][E_STAGE][32], already offset by lane
   uint64_t* bars; // this warp's mbarriers (bulk-copy completion), kNumBars of them
   unsigned bar_phase;  // one parity bit per mbarrier
+  bool pipe_ready = false;  // the warp's mbarriers are initialised already (em_ticket_kernel: once per warp, not per work item)
   unsigned ztab_s, ftab_s;  // HOT: shared addresses of the [T][DZ] cell targets and the [T] {flags, index} table
 
   __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_, uint64_t* bars_)
@@ -2022,7 +2023,7 @@ struct Worker {
     constexpr bool PROD = TEAM && HOT;
     const bool copy_warp = PROD && w == W - 1;
     const int H = PROD ? W - 2 : W - 1;
-    if (main_warp && !PROD) pipe_init();
+    if (main_warp && !PROD && !pipe_ready) pipe_init();
     const double HALF_LOG_2PIE = 1.4189385332046727;  // 0.5 * log(2 pi e)
     double alpha = p.alpha[b];
     const bool aux = !HOT && (p.phases & I2C_PH_STORE_AUX);
@@ -2419,6 +2420,8 @@ __global__ void __launch_bounds__(128, 3) em_ticket_kernel(const __grid_constant
   int* const ticket = pin.tickets;
   int* const done = pin.tickets + 1;
   const int total = pin.ntiles * pin.n_iter;
+  unsigned phase = 0;
+  bool inited = false;
   for (;;) {
     int k = 0;
     if (lane == 0) k = atomicAdd(ticket, 1);
@@ -2432,8 +2435,14 @@ __global__ void __launch_bounds__(128, 3) em_ticket_kernel(const __grid_constant
       asm volatile("fence.proxy.async;" ::: "memory");  // the records are read back with bulk copies
     }
     {
+      // the warp's mbarriers are initialised by its first item and keep their phases across items (re-initialising them per
+      // item is legal -- every copy has been waited for -- but hides the ordering from compute-sanitizer's racecheck)
       Worker<Env, false> w(pin, tile, lane, base + lane, reinterpret_cast<uint64_t*>(base + 2 * Lay<Env>::E_STAGE_TOT * TILE));
+      w.bar_phase = phase;
+      w.pipe_ready = inited;
       w.run_one(it);
+      phase = w.bar_phase;
+      inited = true;
     }
     __threadfence();
     __syncwarp();

@@ -336,6 +336,13 @@ class I2cGraph(object):
         capi.check(self._g.lib.i2c_get_metric(self._g._h, capi.METRICS[name], capi.ptr(buf), n))
         return [float(v) for v in buf[:, 0]]
 
+    def _metrics(self, names, n=1):
+        """Several metrics of the last ``n`` iterations with ONE synchronisation (i2c_get_metrics): {name: [n floats]}."""
+        ids = np.array([capi.METRICS[m] for m in names], np.int32)
+        buf = np.empty((len(names), n, 1))
+        capi.check(self._g.lib.i2c_get_metrics(self._g._h, capi.ptr(ids), len(names), capi.ptr(buf), n))
+        return {m: [float(v) for v in buf[i, :, 0]] for i, m in enumerate(names)}
+
     def calibrate_alpha(self, only_decrease=False):
         assert self._propagate
         before = self.alpha
@@ -352,25 +359,31 @@ class I2cGraph(object):
             n = min(n_iter - done, self._g.max_iters)
             self._run(n, ph)
             self.em_iter += n
-            self.costs_m += self._metric("cost_m", n)
-            self.costs_m_var += self._metric("cost_m_var", n)
-            self.alphas_desired += self._metric("alpha_desired", n)
-            self.alphas += self._metric("alpha", n)
-            self.policy_entropy += self._metric("policy_entropy", n)
-            xe = self._metric("x_prior_entropy", n)
+            names = ["cost_m", "cost_m_var", "alpha_desired", "alpha", "policy_entropy", "x_prior_entropy"]
+            if self._propagate:
+                names += ["cost_pf", "cost_pf_var", "cost_pf_min", "alpha_pf", "propagate_entropy"]
+                if self.sig_x_terminal is not None and self.mu_x_terminal is not None:
+                    names += ["kl_term"]
+            m = self._metrics(names, n)  # one read-back for the whole iteration's bookkeeping (i2c.py:1004-1133)
+            self.costs_m += m["cost_m"]
+            self.costs_m_var += m["cost_m_var"]
+            self.alphas_desired += m["alpha_desired"]
+            self.alphas += m["alpha"]
+            self.policy_entropy += m["policy_entropy"]
+            xe = m["x_prior_entropy"]
             self.x_prior_entropy += xe
             self.x_prior_neg_entropy += [-v for v in xe]
             se = 0.5 * np.log(np.linalg.det(2 * np.pi * np.e * np.asarray(self.sys.sig_eta, float))) * self.H
             self.sig_eta_entropy += [float(se)] * n
             self.sig_eta_pf_entropy += [float(se)] * n
             if self._propagate:
-                self.costs_pf += self._metric("cost_pf", n)
-                self.costs_pf_var += self._metric("cost_pf_var", n)
-                self.cost_pf_min += self._metric("cost_pf_min", n)
-                self.alphas_pf += self._metric("alpha_pf", n)
-                self.propagate_entropy += self._metric("propagate_entropy", n)
-                if self.sig_x_terminal is not None and self.mu_x_terminal is not None:
-                    self.kl_terms += self._metric("kl_term", n)
+                self.costs_pf += m["cost_pf"]
+                self.costs_pf_var += m["cost_pf_var"]
+                self.cost_pf_min += m["cost_pf_min"]
+                self.alphas_pf += m["alpha_pf"]
+                self.propagate_entropy += m["propagate_entropy"]
+                if "kl_term" in m:
+                    self.kl_terms += m["kl_term"]
             else:
                 self.costs_pf += [-1.0] * n
             done += n
@@ -523,8 +536,12 @@ class I2cGraph(object):
 
     # ---- getters ----------------------------------------------------------------------------------------
     def get_local_linear_policy(self):
-        K, k, s = self._g.get_local_linear_policy()
-        return K[0], k[0], s[0]
+        # (cached until the next sweep: scripts/i2c_run.py:89-98 calls both getters after every iteration)
+        if "policy" not in self._cache:
+            K, k, s = self._g.get_local_linear_policy()
+            self._cache["policy"] = (K[0], k[0], s[0])
+        K, k, s = self._cache["policy"]
+        return K.copy(), k.copy(), s.copy()
 
     def get_local_expert_linear_policy(self):
         K, k, s = self.get_local_linear_policy()

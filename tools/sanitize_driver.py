@@ -45,6 +45,8 @@ run("Quadrotor", 64, 10)                                      # HOT without stag
 run("PendulumKnown", 300 * 32, 8)                             # em_kernel<.,1,LAT> cp.async
 run("PendulumKnown", 700 * 32, 6)                             # em_kernel<.,1> TMA bulk
 run("PendulumKnown", 148 * 12 * 32, 4)                        # em_kernel<.,3/4> throughput variants
+run("PendulumKnown", 200 * 32, 5, iters=4, I2C_B200_MINB=5)   # em_ticket_kernel: (tile, iteration) work items, gpu-scope release / acquire
+run("PendulumKnown", 64 * 32, 6, iters=3, propagate=True, I2C_B200_MINB=5)
 run("DoubleCartpoleKnown", 64, 12)                            # em_group_kernel<.,8>
 run("DoubleCartpoleKnown", 64, 12, I2C_B200_GROUP=0)          # per-thread kernel for the large system
 # parallel-in-time scan
@@ -68,4 +70,33 @@ i2c_b200.quadrature("PendulumKnown", "observe", m, S)
 i2c_b200.quadrature("PendulumKnown", "forward", m, S)
 K, k = np.zeros((2, 5, 1, 2)), np.zeros((2, 5, 1))
 i2c_b200.rollout("PendulumKnown", np.zeros((2, 8, 2)), K, k, seed=1)
+# closed-loop MPC step: CKF kernel, HOT = 2 team kernel (cells with their own alpha), tail kernel (first action + horizon shift),
+# page-locked action ring; pipelined metric read-back
+W_, H_ = i2c_b200.envs.QUAD_W, i2c_b200.envs.QUAD_H
+Tm = 30
+z_traj = np.zeros((Tm, 8))
+z_traj[:, 0] = np.linspace(W_ / 4, 3 * W_ / 4, Tm)
+z_traj[:, 1] = H_ / 2
+Qm, Rm = np.diag([1e3, 1e3, 1e3, 1, 1, 1]), np.diag([1e-3, 1e-3])
+u_init = 0.5 * 9.81 * i2c_b200.envs.QUAD_MASS * np.ones((6, 2))
+gq = i2c_b200.BatchedI2c("Quadrotor", 48, 6, Qm, Rm, Qm / 1e3, 1.0, 1.0, u_init, 1e-2 * np.eye(2))
+gq._propagate = True
+pol = i2c_b200.BatchedPartiallyObservedMpc(gq, 2, 1e-2 * np.eye(2), z_traj, sig_zeta=np.diag([1e-6] * 8), pinned_io=True)
+pol.set_control(feedforward=False)
+gq.calibrate_alpha()
+pol.optimize(3)
+e = gq.env
+y0 = np.array([e.x0[0] - 0.8, e.x0[1], e.x0[0] + 0.8, e.x0[1], 0, 0, 0.8, 0.8])
+u = np.zeros((48, 2))
+for t in range(4):
+    u = pol(t, y0 + 1e-3 * rng.normal(size=(48, 8)), u)
+print("mpc ok", bool(np.all(gq.status()[0] == 0)), flush=True)
+gp = make_case(i2c_b200, "PendulumKnown", 96, 12)
+out = [capi.pinned_empty((2, 96)), capi.pinned_empty((2, 96))]
+for i in range(3):
+    gp.run(1, capi.PH_LEARN, collect=False)
+    gp.last_metrics_async(["alpha", "cost_m"], out[i & 1], i & 1)
+    if i:
+        gp.metrics_wait((i - 1) & 1)
+gp.metrics_wait(0)
 print("done", flush=True)
