@@ -1342,6 +1342,11 @@ struct Worker {
         po[(LY::P_SIGK + tix(r, q)) * TILE] = s;
       }
     }
+    // HOT = 2 (closed-loop MPC sweeps: forward + backward + _update_priors, policy/mpc.py:147-154): without the M-step phase
+    // nobody reads the entropy / cost / alpha statistics below -- the tail is the controller extraction only
+    bool stats = true;
+    if constexpr (HOT == 2) stats = (p.phases & I2C_PH_MSTEP) != 0;
+    if (!stats) return;
     // policy entropy needs det(sig_u0_m) (i2c.py:1072-1081)
     {
       double Su[TRI(DU)], iu[DU];
