@@ -105,7 +105,7 @@ def test_hot_specialisation_equals_generic(i2c_b200, monkeypatch, env, B, T, kw)
         assert relerr(a[key], b[key], 1e-9) < (TOL_GAIN.get(env, 2e-8) if key in ("K", "k", "J") else 1e-11), key
 
 
-@pytest.mark.parametrize("kw", [{}, {"propagate": True}, {"fb_only": True}])
+@pytest.mark.parametrize("kw", [{}, {"propagate": True}, {"fb_only": True}, {"covctrl": True}])
 def test_ticket_kernel_equals_static_wave(i2c_b200, kw, monkeypatch):
     """em_ticket_kernel ((tile, iteration) work items drawn from a ticket counter, loop-carried state rebuilt per item) is
     bit-identical to the static one-warp-per-tile launch of the same 168-register variant: learn_msgs with and without the
@@ -115,8 +115,17 @@ def test_ticket_kernel_equals_static_wave(i2c_b200, kw, monkeypatch):
     out = {}
     for minb in ("3", "5"):
         monkeypatch.setenv("I2C_B200_MINB", minb)
-        g = i2c_b200.BatchedI2c("PendulumKnown", B, T, Q, R, Q, 100.0, 0.0, mu_u, 2.0 * np.eye(1), x0=x0)
-        g._propagate = bool(kw.get("propagate"))
+        if kw.get("covctrl"):
+            # covariance control (pendulum_known_act_reg_quad.py:22-33): terminal distribution, temperature schedule carried
+            # across the iterations, in-loop propagate, KL metric
+            g = i2c_b200.BatchedI2c("PendulumKnownActReg", B, T, None, np.diag([1.0]), None, 300.0, 1.0, 0.0 * mu_u,
+                                    0.5 * np.eye(1), np.array([0.0, 0.0]), np.diag([1e-3, 1e-3]),
+                                    x0=np.array([np.pi, 0.0]) + 0.05 * (x0 - np.array([np.pi, 0.0])))
+            g._propagate = True
+            g.set_cell_flag(i2c_b200.capi.CELL_EXPERT, False)
+        else:
+            g = i2c_b200.BatchedI2c("PendulumKnown", B, T, Q, R, Q, 100.0, 0.0, mu_u, 2.0 * np.eye(1), x0=x0)
+            g._propagate = bool(kw.get("propagate"))
         if kw.get("fb_only"):
             g.tau = T
             g.forward_backward(iters, update_priors=True)
@@ -124,9 +133,11 @@ def test_ticket_kernel_equals_static_wave(i2c_b200, kw, monkeypatch):
         else:
             g.learn(iters)
             g.learn(2)
-        assert np.all(g.status()[0] == 0)
+        if not kw.get("covctrl"):
+            assert np.all(g.status()[0] == 0)
         K, k, s = g.get_local_linear_policy()
         out[minb] = dict(K=K, k=k, sigK=s, mu=g.field("mu_xu0_m"), sig=g.field("sig_xu0_m"), alpha_final=g.alpha,
+                         status=g.status()[0], temp=np.array(g.temp),
                          **{m: np.array(v) for m, v in g.metrics.items()})
     for key in out["3"]:
         assert np.array_equal(out["3"][key], out["5"][key], equal_nan=True), key
