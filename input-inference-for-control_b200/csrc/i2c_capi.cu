@@ -9,6 +9,7 @@
 
 #include <chrono>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "i2c_types.h"
@@ -136,6 +137,12 @@ struct i2c_handle_s {
   bool mpending[2];
   double* mstage;  // [2][I2C_M_COUNT][Bpad]: staging slots of i2c_get_last_metrics_async
   cudaStream_t copy_stream;
+  // overlapped belief upload (i2c_set_initial_state_async): alternate x0 / sig_x0 buffers filled on their own stream while the
+  // running sweep reads the current ones; the pointers swap when the upload has been queued
+  cudaStream_t up_stream;
+  cudaEvent_t ev_uploaded, ev_alt_free;
+  double *x0_alt, *sig_x0_alt, *ustage;
+  bool belief_swapped;
   bool copy_pending;
   bool problem_set;
   bool has_z_term_pp;
@@ -313,7 +320,7 @@ static inline int nblocks(size_t total) {
 // ----------------------------------------------------------------------------------------- layout
 struct WsLayout {
   size_t recA, recB, filt, auxf, auxb, pf, ric, term, x0, sig_x0, alpha, alpha_cell, z_cell, z_term_pp, envpar, metrics, scratch, policy_out, flags,
-      index, status, info, tickets, mstage, total, scratch_elems;
+      index, status, info, tickets, mstage, x0_alt, sig_x0_alt, ustage, total, scratch_elems;
 };
 
 static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
@@ -354,6 +361,9 @@ static WsLayout plan(const i2c_config_t& c, const EnvDims& d) {
   w.status = take(Bpad, 4);
   w.info = take(Bpad, 4);
   w.mstage = take(2 * (size_t)I2C_M_COUNT * Bpad, 8);
+  w.x0_alt = take(nt * d.dx * TILE, 8);
+  w.sig_x0_alt = take(nt * tri(d.dx) * TILE, 8);
+  w.ustage = take(Bpad * (size_t)(d.dx + d.dx * d.dx), 8);
   w.tickets = take(nt + 1, 4);  // em_ticket_kernel: ticket counter + finished iterations per tile
   w.total = off;
   return w;
@@ -462,6 +472,10 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
   h->info = (int32_t*)(h->ws + w.info);
   h->tickets = (int32_t*)(h->ws + w.tickets);
   h->mstage = (double*)(h->ws + w.mstage);
+  h->x0_alt = (double*)(h->ws + w.x0_alt);
+  h->sig_x0_alt = (double*)(h->ws + w.sig_x0_alt);
+  h->ustage = (double*)(h->ws + w.ustage);
+  h->belief_swapped = false;
   h->problem_set = false;
   h->launches = 0;
   h->last_n_iter = 0;
@@ -476,6 +490,10 @@ int i2c_create(const i2c_config_t* cfg, void* workspace_dev, size_t workspace_by
     h->mpending[i] = false;
   }
   cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_uploaded, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_alt_free, cudaEventDisableTiming);
+  cudaEventRecord(h->ev_alt_free, h->stream);
   h->copy_pending = false;
   CUDA_OK(cudaMemsetAsync(h->ws, 0, w.total, h->stream));
   *out = h;
@@ -488,6 +506,10 @@ int i2c_destroy(i2c_handle_t h) {
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamDestroy(h->copy_stream);
+  cudaStreamSynchronize(h->up_stream);
+  cudaStreamDestroy(h->up_stream);
+  cudaEventDestroy(h->ev_uploaded);
+  cudaEventDestroy(h->ev_alt_free);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaEventDestroy(h->ev_unpacked);
@@ -722,9 +744,48 @@ int i2c_set_initial_state(i2c_handle_t h, const double* x0, const double* sig_x0
   return set_initial_state_impl(h, x0, sig_x0, true);
 }
 // Asynchronous variant: the (pinned) host buffers must stay valid and unchanged until the next synchronising call on this
-// handle (i2c_synchronize, any getter); the copies are ordered before the next i2c_run on the handle's stream.
+// handle (i2c_synchronize, any getter).  The belief is uploaded and packed into the ALTERNATE x0 / sig_x0 buffers on the
+// handle's upload stream -- concurrently with a sweep that is still reading the current ones -- and the buffers swap roles:
+// everything queued on the handle's stream after this call waits for the upload (one event) and sees the new belief.
 int i2c_set_initial_state_async(i2c_handle_t h, const double* x0, const double* sig_x0) {
-  return set_initial_state_impl(h, x0, sig_x0, false);
+  REQUIRE(h && x0 && sig_x0, "NULL argument");
+  DeviceGuard device_guard_(h->cfg.device);
+  const int dx = h->d.dx;
+  const size_t nx = (size_t)h->B * dx, ns = (size_t)h->B * dx * dx;
+  // the alternate buffers were the current ones until the previous swap: wait for the work that used them
+  CUDA_OK(cudaStreamWaitEvent(h->up_stream, h->ev_alt_free, 0));
+  CUDA_OK(cudaMemcpyAsync(h->ustage, x0, nx * 8, cudaMemcpyHostToDevice, h->up_stream));
+  CUDA_OK(cudaMemcpyAsync(h->ustage + nx, sig_x0, ns * 8, cudaMemcpyHostToDevice, h->up_stream));
+  FieldMap fx{dx, 0, 0, dx, 1, 0, 0, 0};
+  pack_kernel<<<nblocks((size_t)h->Bpad * dx), 256, 0, h->up_stream>>>(h->x0_alt, fx, 0, 1, h->T, 0, h->B, h->Bpad, h->ntiles,
+                                                                      h->ustage, 0);
+  FieldMap fs{tri(dx), 0, 1, dx, dx, 0, 0, 0};
+  pack_kernel<<<nblocks((size_t)h->Bpad * dx * dx), 256, 0, h->up_stream>>>(h->sig_x0_alt, fs, 0, 1, h->T, 0, h->B, h->Bpad,
+                                                                           h->ntiles, h->ustage + nx, 0);
+  h->launches += 2;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(h->ev_uploaded, h->up_stream));
+  // swap: what is queued on the handle's stream so far used the old buffers (they become the alternates, free once that work
+  // is done); what follows waits for the upload
+  CUDA_OK(cudaEventRecord(h->ev_alt_free, h->stream));
+  CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_uploaded, 0));
+  std::swap(h->x0, h->x0_alt);
+  std::swap(h->sig_x0, h->sig_x0_alt);
+  h->belief_swapped = !h->belief_swapped;
+  return 0;
+}
+
+// snapshots serialise the workspace with the belief in its primary buffers
+static int normalise_belief(i2c_handle_t h) {
+  if (!h->belief_swapped) return 0;
+  const size_t nt = h->ntiles;
+  CUDA_OK(cudaMemcpyAsync(h->x0_alt, h->x0, nt * h->d.dx * TILE * 8, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(h->sig_x0_alt, h->sig_x0, nt * tri(h->d.dx) * TILE * 8, cudaMemcpyDeviceToDevice, h->stream));
+  std::swap(h->x0, h->x0_alt);
+  std::swap(h->sig_x0, h->sig_x0_alt);
+  h->belief_swapped = false;
+  CUDA_OK(cudaEventRecord(h->ev_alt_free, h->stream));
+  return 0;
 }
 
 int i2c_set_initial_state_dev(i2c_handle_t h, const double* x0_dev, const double* sig_x0_dev) {
@@ -1609,6 +1670,7 @@ int i2c_snapshot(i2c_handle_t h, void* host_buf, size_t bytes) {
   size_t need;
   i2c_snapshot_bytes(h, &need);
   REQUIRE(bytes >= need, "snapshot buffer too small");
+  if (int rc = normalise_belief(h)) return rc;
   SnapHeader hd;
   memset(&hd, 0, sizeof(hd));
   hd.magic = 0x6932635f62323030ull;
@@ -1661,6 +1723,13 @@ int i2c_restore(i2c_handle_t h, const void* host_buf, size_t bytes) {
   memcpy(su, p, 24);
   p += 24;
   h->sig_u_host.assign(su, su + tri(h->d.du));
+  // the snapshot holds the belief in the primary buffers (normalise_belief): point this handle at them
+  CUDA_OK(cudaStreamSynchronize(h->up_stream));
+  if (h->belief_swapped) {
+    std::swap(h->x0, h->x0_alt);
+    std::swap(h->sig_x0, h->sig_x0_alt);
+    h->belief_swapped = false;
+  }
   CUDA_OK(cudaMemcpyAsync(h->ws, p, h->ws_bytes, cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;

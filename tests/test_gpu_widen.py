@@ -282,6 +282,29 @@ def test_initial_state_async_upload(i2c_b200):
     assert np.array_equal(Ga.field("K"), Gb.field("K")) and np.array_equal(Ga.alpha, Gb.alpha)
     xa, sa = Ga.get_initial_state()
     assert np.array_equal(xa, x0) and relerr(sa, s0) < 1e-15
+    xb, sb = Gb.get_initial_state()
+    assert np.array_equal(xb, xa) and np.array_equal(sb, sa)
+    # the asynchronous call fills alternate belief buffers on an upload stream (overlapping a running sweep) and swaps them in:
+    # a stream of new beliefs queued back to back with the sweeps, a snapshot / restore and a deepcopy in the swapped state
+    x1 = [capi.pinned_empty((70, 2)) for _ in range(3)]
+    for i, x in enumerate(x1):
+        x[:] = x0 + 0.01 * (i + 1)
+    for x in x1:
+        capi.check(Ga.lib.i2c_set_initial_state(Ga._h, capi.ptr(x), capi.ptr(s0)))
+        Ga.learn(1)
+        capi.check(Gb.lib.i2c_set_initial_state_async(Gb._h, capi.ptr(x), capi.ptr(s0)))
+        Gb.run(1, capi.PH_LEARN, collect=False)  # queued behind the upload, no host synchronisation in between
+    assert np.array_equal(Ga.field("K"), Gb.field("K")) and np.array_equal(Ga.alpha, Gb.alpha)
+    assert np.array_equal(Gb.get_initial_state()[0], x1[-1])
+    snap = Gb.snapshot()
+    Gb.learn(1)
+    K1 = Gb.field("K")
+    capi.check(Gb.lib.i2c_set_initial_state_async(Gb._h, capi.ptr(x1[0]), capi.ptr(s0)))  # swapped state again
+    Gb.restore(snap)
+    assert np.array_equal(Gb.get_initial_state()[0], x1[-1])
+    Gb.learn(1)
+    Ga.learn(1)
+    assert np.array_equal(Gb.field("K"), K1) and np.array_equal(Ga.field("K"), K1)
 
 
 def test_pipelined_metrics_read(i2c_b200):
