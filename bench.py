@@ -295,8 +295,8 @@ def run_cuda(args, rank, world, local_rank):
 
         Kd, kd, sd = g.policy_device_tensors()
         cost = torch.from_numpy(np.ascontiguousarray(h_m2[(Ke - 1) & 1][1])).to(Kd.device)
-        gathered = idist.gather_controllers(Kd, kd, sd, world * B, extra=(cost,))
-        assert gathered[0].shape[0] == world * B
+        gathered = idist.gather_controllers(Kd, kd, sd, world * B, extra=(cost,), dst=0)  # onto rank 0 (it writes the results)
+        assert (gathered[0].shape[0] == world * B) if rank == 0 else (gathered[0] is None)
         torch.cuda.synchronize(dev)
 
     parts = {}
@@ -391,7 +391,7 @@ def run_cuda(args, rank, world, local_rank):
                 "d2h_bytes_once": d2h_once, "steps": Ke, "ms_per_step": e2e_ms / Ke, "breakdown_ms_max_over_ranks": parts,
                 "what": "per step: H2D start-state belief (pinned), one learn_msgs through the C-ABI, D2H cost + alpha of every "
                         "problem (pipelined: step i+1 is queued before the host collects step i, i2c_get_last_metrics_async); after the last step, inside the timed region: D2H of K, k, sigK of this rank "
-                        "(once, on the copy stream)" + ("; concurrently the NCCL all_gather of controllers and costs over NVLink" if world > 1 else "")
+                        "(once, on the copy stream)" + ("; concurrently the NCCL gather of controllers and costs onto rank 0 over NVLink" if world > 1 else "")
                         + (f"; process bound to the {numa} CPUs local to its GPU" if numa else "")},
         "e2e_synchronous_steps": {"value": e2es_value, "unit": UNIT, "steps": Ks, "ms_per_step": e2es_ms / Ks,
                                   "what": "as e2e without the final controller read-back, but the host waits for cost + alpha of "

@@ -27,6 +27,12 @@ def _worker(rank, world, port, B, out_dir):
     s, e = idist.shard_range(B, world, rank)
     K, k, sg, cost = idist.gather_controllers(K_full[s:e], k_full[s:e], s_full[s:e], B, extra=(cost_full[s:e],))
     ok = all(torch.equal(a, b) for a, b in ((K, K_full), (k, k_full), (sg, s_full), (cost, cost_full)))
+    # gather onto rank 0 only (what the bench's final gather uses): shards land in their slices of the final tensor
+    got = idist.gather_controllers(K_full[s:e], k_full[s:e], s_full[s:e], B, extra=(cost_full[s:e],), dst=0)
+    if rank == 0:
+        ok = ok and all(torch.equal(a, b) for a, b in zip(got, (K_full, k_full, s_full, cost_full)))
+    else:
+        ok = ok and all(g is None for g in got)
     torch.save({"ok": ok, "range": (s, e)}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
