@@ -4,12 +4,12 @@
 
   python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the UNMODIFIED reference (oracle/_ref) on all host cores
-  python bench.py --workload dcp|quadrotor ...             # BASELINE configs[3] / configs[4] shards (fp64-bound rooflines)
+  python bench.py --workload dcp|quadrotor|cartpole ...    # BASELINE configs[3] / configs[4] shards, cart-pole 4096 x 200 (fp64-bound rooflines)
 
 One "step" = one EM iteration (I2cGraph.learn_msgs: forward + backward + M-step, i2c/i2c.py:1238-1245) over the
 whole batch; one problem-timestep update = one cell through one such iteration.  Under torchrun every rank owns an
 independent shard of problems (weak scaling, no data-path collective); the only collective is the final NCCL
-all_gather of controllers / costs, timed in the end-to-end leg.
+gather of controllers / costs, timed in the end-to-end leg.
 """
 import argparse
 import json
@@ -640,7 +640,7 @@ def mpc_leg(args, dev, rank, world, max_over_ranks, barrier, n_timed=20, with_em
 
 
 # ----------------------------------------------------------------------------- BASELINE configs[3] / configs[4]
-ALG = {"DoubleCartpoleKnown": (34473.0, 3400.0), "Quadrotor": (33105.0, 4160.0)}  # (flops, bytes) per update, SURVEY.md 8(d)
+ALG = {"DoubleCartpoleKnown": (34473.0, 3400.0), "Quadrotor": (33105.0, 4160.0), "CartpoleKnown": (11601.0, 1792.0)}  # (flops, bytes) per update, SURVEY.md 8(d)
 
 
 def _peaks(capi, dev):
@@ -743,21 +743,40 @@ def run_workload(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- double cart-pole, covariance control
-    env = "DoubleCartpoleKnown"
-    B, T = args.problems if args.problems != 4096 else 2048, args.horizon if args.horizon != 200 else 500
-    sf = 1e-3
-    Q = sf * np.diag([1.0, 1.0, 100.0, 1.0, 100.0, 10.0, 1.0, 1.0])
-    R = sf * np.diag([0.1])
-    mu_t, sig_t = np.zeros(6), np.diag([0.01, 0.005, 0.005, 0.05, 0.05, 0.05])
     rng = np.random.default_rng(4321 + rank)
-    e = i2c_b200.envs.make(env)
-    x0 = e.x0 + 0.05 * rng.normal(size=(B, 6))
-    mu_u = 1e-2 * rng.normal(size=(B, T, 1))
-    g = i2c_b200.BatchedI2c(env, B, T, Q, R, Q, 0.05, 0.99, mu_u, np.eye(1), mu_t, sig_t, x0=x0, device=dev,
-                            max_iters=max(K, W, 1))
-    g.set_cell_flag(capi.CELL_EXPERT, False)
-    g.propagate()  # the initial propagate of nonlinear_covariance_control.py:105-113
+    if args.workload == "cartpole":
+        # ---- cart-pole swing-up (the north star's second target system; hyper-parameters of cartpole_known_quad.py:23-34)
+        env = "CartpoleKnown"
+        B, T = args.problems, args.horizon
+        e = i2c_b200.envs.make(env)
+        Q, R = np.diag([1.0, 1.0, 100.0, 10.0, 1.0]), np.diag([1.0])
+        x0 = e.x0 + 0.05 * rng.normal(size=(B, 4))
+        mu_u = 1e-2 * rng.normal(size=(B, T, 1))
+        g = i2c_b200.BatchedI2c(env, B, T, Q, R, Q, 80.0, 0.0, mu_u, np.eye(1), x0=x0, device=dev, max_iters=max(K, W, 1))
+        what = (f"cart-pole swing-up cubature i2c, {B} problems/GPU x T={T} (the north star's second target system; "
+                f"hyper-parameters of cartpole_known_quad.py)")
+        n_rec = 26 + 26 + 54
+    else:
+        # ---- double cart-pole, covariance control
+        env = "DoubleCartpoleKnown"
+        B, T = args.problems if args.problems != 4096 else 2048, args.horizon if args.horizon != 200 else 500
+        sf = 1e-3
+        Q = sf * np.diag([1.0, 1.0, 100.0, 1.0, 100.0, 10.0, 1.0, 1.0])
+        R = sf * np.diag([0.1])
+        mu_t, sig_t = np.zeros(6), np.diag([0.01, 0.005, 0.005, 0.05, 0.05, 0.05])
+        e = i2c_b200.envs.make(env)
+        x0 = e.x0 + 0.05 * rng.normal(size=(B, 6))
+        mu_u = 1e-2 * rng.normal(size=(B, T, 1))
+        g = i2c_b200.BatchedI2c(env, B, T, Q, R, Q, 0.05, 0.99, mu_u, np.eye(1), mu_t, sig_t, x0=x0, device=dev,
+                                max_iters=max(K, W, 1))
+        g.set_cell_flag(capi.CELL_EXPERT, False)
+        g.propagate()  # the initial propagate of nonlinear_covariance_control.py:105-113
+        what = (f"double cart-pole cubature i2c + covariance control, {B} problems/GPU x T={T} (BASELINE "
+                f"configs[3] = 16384 x 500 over 8 GPUs); EM iteration = forward + backward + M-step WITHOUT the "
+                f"in-loop propagate (infeasible for the reference algorithm on these inputs, DESIGN.md section 4); "
+                f"initial propagate() run once before")
+        n_rec = 44 + 44 + 104
+    dx = e.dim_x
     g.run(W, capi.PH_LEARN, collect=False)
     if rank == 0:
         sampler.start()
@@ -778,9 +797,9 @@ def run_workload(args, rank, world, local_rank):
     n_fail = int(np.count_nonzero(g.status()[0]))
     # end to end: per step H2D belief + one learn_msgs + D2H cost / alpha; controllers once at the end
     pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()  # noqa: E731
-    h_x0, h_s0, h_m = pin(B, 6), pin(B, 6, 6), pin(2, B)
+    h_x0, h_s0, h_m = pin(B, dx), pin(B, dx, dx), pin(2, B)
     h_x0[:], h_s0[:] = g.x0, g.sig_x0
-    h_K, h_k, h_s = pin(B, T, 1, 6), pin(B, T, 1), pin(B, T, 1, 1)
+    h_K, h_k, h_s = pin(B, T, 1, dx), pin(B, T, 1), pin(B, T, 1, 1)
     L = g.lib
     Ke = max(3, min(K, 10))
 
@@ -813,11 +832,8 @@ def run_workload(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": world * B * T * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"double cart-pole cubature i2c + covariance control, {B} problems/GPU x T={T} (BASELINE "
-                                   f"configs[3] = 16384 x 500 over 8 GPUs); EM iteration = forward + backward + M-step WITHOUT the "
-                                   f"in-loop propagate (infeasible for the reference algorithm on these inputs, DESIGN.md section 4); "
-                                   f"initial propagate() run once before",
-                       "l2": "records of one iteration = %.0f MB > 126 MB L2" % ((44 + 44 + 104) * 8 * B * T / 1e6),
+            "config": {"workload": what,
+                       "l2": "records of one iteration = %.0f MB > 126 MB L2" % (n_rec * 8 * B * T / 1e6),
                        "failed_problems": n_fail},
             "clocks": clocks,
             "e2e": {"value": world * B * T * Ke / (e2e_ms * 1e-3), "unit": UNIT, "steps": Ke,
@@ -828,7 +844,7 @@ def run_workload(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": F * rate_gpu / 1e12, "peak": fp64, "unit": "TFLOP/s",
                          "frac": F * rate_gpu / 1e12 / fp64, "traffic": None, "peak_source": src,
-                         "kernel": "em_team_kernel<EnvDoubleCartpole,8,HOT>" if B <= 148 * 32 else "em_kernel<EnvDoubleCartpole>",
+                         "kernel": ("em_team_kernel<%s,8,HOT>" if B <= 148 * 32 else "em_kernel<%s>") % (("Env" + env[:-5],) * 1),
                          "kernel_ms_per_launch": kernel_ms, "algorithmic_flops_per_update": F,
                          "algorithmic_bytes_per_update": Bb, "hbm_frac": Bb * rate_gpu / 1e9 / hbm}}
     print(json.dumps(line), flush=True)
@@ -880,7 +896,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100,
                     help="EM iterations of the end-to-end leg (default 100: the whole job of BASELINE configs[2], SURVEY.md 8d; "
                          "0 = --steps); the controllers are read back / gathered once after the last one")
-    ap.add_argument("--workload", default="pendulum", choices=["pendulum", "dcp", "quadrotor"],
+    ap.add_argument("--workload", default="pendulum", choices=["pendulum", "dcp", "quadrotor", "cartpole"],
                     help="pendulum = BASELINE configs[2] (the judged line); dcp / quadrotor = per-GPU shards of configs[3] / [4]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

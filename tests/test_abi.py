@@ -65,3 +65,20 @@ def test_no_cpu_fallback(built, has_cuda):
         built.quadrature("PendulumKnown", "observe", np.zeros((1, 3)), np.eye(3))
     with pytest.raises(KeyError):
         built.envs.make("FurutaKnown")
+
+
+def test_header_is_c99_and_c_consumer_links(built, has_cuda, tmp_path):
+    """include/i2c_b200.h is plain C (gcc -std=c99 -pedantic), and a C program (tests/c_abi/consumer.c) links against the
+    library without Python / torch; without a GPU its i2c_create is refused loudly (exit code 3): no CPU fallback."""
+    import subprocess
+
+    libdir = os.path.dirname(built.capi.LIB_PATH)
+    exe = os.path.join(str(tmp_path), "consumer")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi", "consumer.c"), "-L" + libdir, "-li2c_b200",
+                           "-Wl,-rpath," + libdir, "-lm", "-o", exe])
+    r = subprocess.run([exe, "8", "10", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if has_cuda:
+        assert r.returncode == 0 and r.stdout.startswith("ok B=8 T=10 n_iter=2 failed=0"), r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stdout, r.stdout + r.stderr

@@ -8,6 +8,7 @@ python bench.py > $out/${tag}_bench_default.json 2> $out/${tag}_bench_default.er
 python bench.py --impl reference --steps 20 --warmup 3 > $out/${tag}_bench_reference_arm.json 2> $out/${tag}_bench_reference_arm.err
 python bench.py --workload dcp --steps 10 > $out/${tag}_bench_dcp.json 2> $out/${tag}_bench_dcp.err
 python bench.py --workload quadrotor --steps 20 > $out/${tag}_bench_quadrotor.json 2> $out/${tag}_bench_quadrotor.err
+python bench.py --workload cartpole --steps 10 > $out/${tag}_bench_cartpole.json 2> $out/${tag}_bench_cartpole.err
 : > $out/${tag}_env_sweep.jsonl
 for c in "PendulumKnown 512 200 20" "PendulumKnown 2048 200 20" "PendulumKnown 4096 200 20" "PendulumKnown 4736 200 20" "PendulumKnown 8192 200 20" \
          "PendulumKnown 16384 200 10" "PendulumKnown 32768 200 10" "PendulumKnown 56832 200 10" "PendulumKnown 65536 200 10" "PendulumKnown 100000 100 10" "PendulumKnown 262144 100 10" \
