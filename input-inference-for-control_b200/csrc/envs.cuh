@@ -51,6 +51,7 @@ struct Trig {
 struct EnvLinear {
   static constexpr int DX = 2, DU = 1, DZ = 3, DZT = 2, NP = 8, DY = 0, NA = 0;
   static constexpr bool HAS_TERM = true, LINEAR = true;
+  static constexpr bool J_HANDOFF = false;  // smoother gain computed by a helper warp (i2c_kernels.cuh: JOFF)
   static constexpr int NJ = 0;
   using TrigT = Trig<NA>;
   template <class TT> __device__ static void offsets(const double*, double, TT&) {}
@@ -120,6 +121,7 @@ static __constant__ double kCartpole[10] = {-0.127 * 0.3365, (0.37 + 0.127) * 9.
 struct EnvPendulum {
   static constexpr int DX = 2, DU = 1, DZ = 4, DZT = 3, NP = 0, DY = 0, NA = 1;
   static constexpr bool HAS_TERM = true, LINEAR = false;
+  static constexpr bool J_HANDOFF = false;  // smoother gain computed by a helper warp (i2c_kernels.cuh: JOFF)
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
   static constexpr int NJ = 1;
@@ -178,6 +180,7 @@ struct EnvPendulum {
 struct EnvPendulumActReg : EnvPendulum {
   static constexpr int DZ = 1, DZT = 1;
   static constexpr bool HAS_TERM = false;
+  static constexpr bool J_HANDOFF = false;  // smoother gain computed by a helper warp (i2c_kernels.cuh: JOFF)
   static constexpr int OBS_NL = 0, OBS_JMAX = -1;
   __host__ __device__ static constexpr int obs_src(int) { return 2; }
   __host__ __device__ static constexpr int term_src(int) { return 0; }
@@ -191,6 +194,7 @@ struct EnvPendulumActReg : EnvPendulum {
 struct EnvCartpole {
   static constexpr int DX = 4, DU = 1, DZ = 6, DZT = 5, NP = 0, DY = 0, NA = 1;
   static constexpr bool HAS_TERM = true, LINEAR = false;
+  static constexpr bool J_HANDOFF = true;  // smoother gain computed by a helper warp (i2c_kernels.cuh: JOFF)
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
   static constexpr int NJ = 2;
@@ -262,6 +266,7 @@ struct EnvCartpole {
 struct EnvDoubleCartpole {
   static constexpr int DX = 6, DU = 1, DZ = 9, DZT = 8, NP = 0, DY = 0, NA = 2;
   static constexpr bool HAS_TERM = true, LINEAR = false;
+  static constexpr bool J_HANDOFF = false;  // smoother gain computed by a helper warp (i2c_kernels.cuh: JOFF)
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
   static constexpr int NJ = 3;
@@ -390,6 +395,7 @@ struct EnvDoubleCartpole {
 struct EnvQuadrotor {
   static constexpr int DX = 6, DU = 2, DZ = 8, DZT = 6, NP = 0, DY = 8, NA = 1;
   static constexpr bool HAS_TERM = true, LINEAR = false;
+  static constexpr bool J_HANDOFF = false;  // smoother gain computed by a helper warp (i2c_kernels.cuh: JOFF)
   __host__ __device__ static constexpr double obsE(int, int) { return 0.0; }
   __host__ __device__ static constexpr double obsF(int, int) { return 0.0; }
   static constexpr int NJ = 3;

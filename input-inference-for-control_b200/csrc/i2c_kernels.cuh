@@ -149,6 +149,9 @@ __device__ __forceinline__ double lds_f64(unsigned addr_s) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr_s));
   return v;
 }
+__device__ __forceinline__ void sts_f64(unsigned addr_s, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr_s), "d"(v) : "memory");
+}
 // read-only tables (written once before a block-wide barrier): plain asm, the compiler may move / merge these loads
 __device__ __forceinline__ double lds_f64_ro(unsigned addr_s) {
   double v;
@@ -582,6 +585,21 @@ struct Worker {
   unsigned bar_phase;  // one parity bit per mbarrier
   bool pipe_ready = false;  // the warp's mbarriers are initialised already (em_ticket_kernel: once per warp, not per work item)
   unsigned ztab_s, ftab_s;  // HOT: shared addresses of the [T][DZ] cell targets and the [T] {flags, index} table
+  // J_dyn hand-off (HOT team kernels, n >= 5): the smoother gain J = S_xy S_x3^{-1} (i2c.py:425-428) is only read by the backward
+  // sweep, so warp 0 -- whose forward cell is the critical path -- does not compute it: it leaves S_xy and the factor of
+  // S_x3 in one of two shared-memory slots and helper warp 1 does the substitutions and the record stores behind it.
+  // Measured (round 2): cart-pole 4096 x 200 0.74 -> 0.66 ms per iteration (the forward cell loses its register spills);
+  // double cart-pole and quadrotor: no gain (5.03 -> 5.07 ms, 1.01 -> 1.04 ms) -- enabled per environment (Env::J_HANDOFF).
+  // The slots live in the part of the staging area the record ring does not use (no extra shared memory: the two resident
+  // blocks of the 4-warp variant must keep fitting).
+  static constexpr bool JOFF = HOT && Env::J_HANDOFF;
+  static constexpr int JELEMS = N * DX + TRI(DX) + DX;
+  // slot k & 1 for the k-th cell; mbarriers bars[JBAR + s] ("full": the 32 lanes of warp 0 arrive after their stores) and
+  // bars[JBAR + 2 + s] ("empty": the 32 lanes of warp 1 arrive after their loads), phase parity (k >> 1) & 1
+  static constexpr int JBAR = 2 * LY::RING;
+  static_assert(!JOFF || JBAR + 4 <= kNumBars, "no mbarriers left for the J_dyn hand-off");
+  unsigned jslot_s = 0;  // shared address of the slots (lane offset included)
+  unsigned jcount = 0;   // forward cells handed over (warp 0) / served (warp 1) so far in this launch
 
   __device__ Worker(const KParams& p_, int tile_, int lane_, double* stage_, uint64_t* bars_)
       : p(p_), tile(tile_), lane(lane_), b(tile_ * TILE + lane_), stage(stage_), bars(bars_), bar_phase(0), ring_q(0), ring_ready(false), ring_ready2(false) {
@@ -702,6 +720,10 @@ struct Worker {
     for (int i = 0; i < RING; ++i) {
       mbar_init(bars + i, 1);            // full: the producer's arrive.expect_tx
       mbar_init(bars + RING + i, TILE);  // empty: every lane of warp 0 arrives after its last read of the slot
+    }
+    if constexpr (JOFF) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mbar_init(bars + JBAR + i, TILE);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -984,7 +1006,7 @@ struct Worker {
   // whole horizon beforehand (sweep_is_plain) -- so neither branch exists in the loop body.
   // With PLAIN the trigonometric context of the cost-feature transform comes in through octx and is re-evaluated for the
   // NEXT cell at the end, from the outgoing message.  PS = element stride of the prior record at pr (1: register copy).
-  template <bool PLAIN = false, int PS = TILE>
+  template <bool PLAIN = false, int PS = TILE, bool JO = false>
   __device__ __forceinline__ void forward_cell(int it, int t, int flags, double alpha, bool aux, const double* pr,
                                                Carry<DX>& c, LogAcc& ent_x, TrigT* octx = nullptr, double* fr_in = nullptr) {
     double mu[N], Sig[TRI(N)], L[TRI(N)], invd[N];
@@ -1187,15 +1209,31 @@ struct Worker {
       }
       if (!chol_rows<DX>(c.L, c.invd)) fail(I2C_FAIL_CHOL_X3, it, t);
       // J_dyn = Sxy Sig_x3^{-1}  (n x dx)
+      if constexpr (JO) {
+        // hand S_xy and the factor over to helper warp 1 (jdyn_serve); slot reuse two cells later: the helper is at most
+        // one cell behind (checked, never waited for in practice: a J job is ~5 % of a cell)
+        const unsigned sl = jcount & 1u, par = (jcount >> 1) & 1u;
+        mbar_wait_s(bars_s + 8u * (JBAR + 2 + sl), par ^ 1u);  // passes at once for the first use of a slot
+        const unsigned js = jslot_s + sl * (JELEMS * TILE * 8);
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        double w[DX];
+        for (int i = 0; i < N * DX; ++i) sts_f64(js + i * (TILE * 8), Sxy[i]);
 #pragma unroll
-        for (int a = 0; a < DX; ++a) w[a] = Sxy[i * DX + a];
-        fwd_subst<DX>(c.L, c.invd, w);
-        bwd_subst<DX>(c.L, c.invd, w);
+        for (int i = 0; i < TRI(DX); ++i) sts_f64(js + (N * DX + i) * (TILE * 8), c.L[i]);
 #pragma unroll
-        for (int a = 0; a < DX; ++a) fr[(LY::F_J + i * DX + a) * TILE] = w[a];
+        for (int i = 0; i < DX; ++i) sts_f64(js + (N * DX + TRI(DX) + i) * (TILE * 8), c.invd[i]);
+        mbar_arrive_s(bars_s + 8u * (JBAR + sl));
+        ++jcount;
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double w[DX];
+#pragma unroll
+          for (int a = 0; a < DX; ++a) w[a] = Sxy[i * DX + a];
+          fwd_subst<DX>(c.L, c.invd, w);
+          bwd_subst<DX>(c.L, c.invd, w);
+#pragma unroll
+          for (int a = 0; a < DX; ++a) fr[(LY::F_J + i * DX + a) * TILE] = w[a];
+        }
       }
     }
     // ---- terminal cost update on the outgoing message (i2c.py:430-443)
@@ -1237,6 +1275,36 @@ struct Worker {
   __device__ __forceinline__ void obs_trig(const Carry<DX>& c, TrigT& o) const {
     Env::center(c.m, o);
     Env::offsets(c.L, p.sf_n, o);
+  }
+
+  // helper warp 1, during the forward sweep: the J_dyn rows of the T cells warp 0 hands over (see JOFF)
+  __device__ __forceinline__ void jdyn_serve(int T) {
+    for (int t = 0; t < T; ++t) {
+      const unsigned sl = jcount & 1u, par = (jcount >> 1) & 1u;
+      while (!mbar_test_s(bars_s + 8u * (JBAR + sl), par)) __nanosleep(500);  // a J job is not urgent: poll rarely
+      const unsigned js = jslot_s + sl * (JELEMS * TILE * 8);
+      double Lx[TRI(DX)], ix[DX];
+#pragma unroll
+      for (int i = 0; i < TRI(DX); ++i) Lx[i] = lds_f64(js + (N * DX + i) * (TILE * 8));
+#pragma unroll
+      for (int i = 0; i < DX; ++i) ix[i] = lds_f64(js + (N * DX + TRI(DX) + i) * (TILE * 8));
+      double* fr = rec(p.filt, t, LY::E_FILT);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double w[DX];
+#pragma unroll
+        for (int a = 0; a < DX; ++a) w[a] = lds_f64(js + (i * DX + a) * (TILE * 8));
+        if (i == N - 1) mbar_arrive_s(bars_s + 8u * (JBAR + 2 + sl));  // the slot is in registers
+        fwd_subst<DX>(Lx, ix, w);
+        bwd_subst<DX>(Lx, ix, w);
+#pragma unroll
+        for (int a = 0; a < DX; ++a) fr[(LY::F_J + i * DX + a) * TILE] = w[a];
+      }
+      ++jcount;
+    }
+    // the J rows are read back by the copy warp's bulk copies after the block-wide barrier that ends the forward sweep
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
   }
 
   // ---------------------------------------------------------------------------------- backward cell
@@ -2072,9 +2140,9 @@ struct Worker {
               if constexpr (RCOPY) {
                 double pr[LY::E_STAGE_POST];
                 ring_read<LY::E_STAGE_POST>(pr);
-                forward_cell<true, 1>(it, t, 0, alpha, aux, pr, c, ent_x, &octx, fc.ptr);
+                forward_cell<true, 1, JOFF>(it, t, 0, alpha, aux, pr, c, ent_x, &octx, fc.ptr);
               } else {
-                forward_cell<true>(it, t, 0, alpha, aux, ring_view(), c, ent_x, &octx, fc.ptr);
+                forward_cell<true, TILE, JOFF>(it, t, 0, alpha, aux, ring_view(), c, ent_x, &octx, fc.ptr);
                 ring_release();
               }
               fc.next();
@@ -2084,9 +2152,9 @@ struct Worker {
             if constexpr (RCOPY) {
               double pr[LY::E_STAGE_POST];
               ring_read<LY::E_STAGE_POST>(pr);
-              forward_cell<false, 1>(it, t, staged_flags(nullptr, t, flipped), alpha, aux, pr, c, ent_x);
+              forward_cell<false, 1, JOFF>(it, t, staged_flags(nullptr, t, flipped), alpha, aux, pr, c, ent_x);
             } else {
-              forward_cell(it, t, staged_flags(nullptr, t, flipped), alpha, aux, ring_view(), c, ent_x);
+              forward_cell<false, TILE, JOFF>(it, t, staged_flags(nullptr, t, flipped), alpha, aux, ring_view(), c, ent_x);
               ring_release();
             }
           }
@@ -2108,6 +2176,9 @@ struct Worker {
           for (int t = 0; t < T; ++t) ring_produce(prior, LY::E_POST, LY::E_STAGE_POST, t);
         }
         __syncwarp();
+      }
+      if constexpr (PROD && JOFF) {
+        if (w == 1 && (p.phases & I2C_PH_FORWARD)) jdyn_serve(T);
       }
       if (p.phases & I2C_PH_BACKWARD) {
         double m3m[DX], S3m[TRI(DX)];
@@ -2479,6 +2550,12 @@ __global__ void __launch_bounds__(W * TILE, 8 / W) em_team_kernel(const __grid_c
     __syncthreads();
     wk.ztab_s = smem_addr(ztab);
     wk.ftab_s = smem_addr(ftab);
+    using WK = Worker<Env, true, false, false, HOT>;
+    if constexpr (WK::JOFF) {
+      // [2][JELEMS][32] hand-over slots in the tail of the staging area (the ring takes RING * E_STAGE of its E_TEAM_STAGE rows)
+      static_assert(Lay<Env>::RING * Lay<Env>::E_STAGE + 2 * WK::JELEMS <= Lay<Env>::E_TEAM_STAGE, "no room for the J_dyn slots");
+      wk.jslot_s = smem_addr(stage_smem + (size_t)Lay<Env>::RING * Lay<Env>::E_STAGE * TILE + lane);
+    }
   }
   wk.template run_impl<true>(w, W, red, 0, pin.n_iter);
 }
@@ -2487,6 +2564,7 @@ template <class Env, int W, int HOT>
 static int launch_em_team_v(const KParams& p, cudaStream_t s) {
   // staging + mbarriers + reduction + progress counter (+ HOT: target / flag table of the horizon)
   const size_t smem = ((size_t)(Lay<Env>::E_TEAM_STAGE + 7 * W) * TILE + kNumBars + 2 + (HOT ? (size_t)p.T * (Env::DZ + 1) : 0)) * sizeof(double);
+
   if (int e = allow_big_smem<em_team_kernel<Env, W, HOT>>()) return e;
   KParams q = p;
   q.stage_meta = Lay<Env>::STAGED;
