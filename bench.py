@@ -803,20 +803,26 @@ def run_workload(args, rank, world, local_rank):
     L = g.lib
     Ke = max(3, min(K, 10))
 
+    m_ids = np.array([capi.METRICS["alpha"], capi.METRICS["cost_m"]], np.int32)
+    h_m2 = [h_m, pin(2, B)]
+
     def e2e_run(n):
-        for _ in range(n):
+        # as the pendulum line: belief upload into the alternate buffers, one learn_msgs, pipelined read of cost + alpha
+        for i in range(n):
             capi.check(L.i2c_set_initial_state_async(g._h, capi.ptr(h_x0), capi.ptr(h_s0)))
             capi.check(L.i2c_run(g._h, 1, capi.PH_LEARN))
-            capi.check(L.i2c_get_metric(g._h, capi.METRICS["alpha"], capi.ptr(h_m[0:1]), 1))
-            capi.check(L.i2c_get_metric(g._h, capi.METRICS["cost_m"], capi.ptr(h_m[1:2]), 1))
+            capi.check(L.i2c_get_last_metrics_async(g._h, capi.ptr(m_ids), 2, capi.ptr(h_m2[i & 1]), i & 1))
+            if i > 0:
+                capi.check(L.i2c_metrics_wait(g._h, (i - 1) & 1))
+        capi.check(L.i2c_metrics_wait(g._h, (n - 1) & 1))
         capi.check(L.i2c_get_policy_async(g._h, capi.ptr(h_K), capi.ptr(h_k), capi.ptr(h_s)))
-        capi.check(L.i2c_copy_wait(g._h))
         if dist is not None:
             from i2c_b200 import dist as idist
 
             Kd, kd, sd = g.policy_device_tensors()
-            idist.gather_controllers(Kd, kd, sd, world * B)
+            idist.gather_controllers(Kd, kd, sd, world * B, dst=0)
             torch.cuda.synchronize(dev)
+        capi.check(L.i2c_copy_wait(g._h))
 
     e2e_run(1)
     barrier()
@@ -839,8 +845,8 @@ def run_workload(args, rank, world, local_rank):
             "e2e": {"value": world * B * T * Ke / (e2e_ms * 1e-3), "unit": UNIT, "steps": Ke,
                     "h2d_bytes_per_step": h_x0.nbytes + h_s0.nbytes, "d2h_bytes_per_step": h_m.nbytes,
                     "d2h_bytes_once": h_K.nbytes + h_k.nbytes + h_s.nbytes,
-                    "what": "per step H2D belief + learn_msgs + D2H cost / alpha; K, k, sigK read back once after the last step"
-                            + (" + NCCL all_gather" if world > 1 else "")},
+                    "what": "per step H2D belief + learn_msgs + D2H cost / alpha (pipelined); K, k, sigK read back once after the last "
+                            "step" + (", overlapped with the NCCL gather onto rank 0" if world > 1 else "")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": F * rate_gpu / 1e12, "peak": fp64, "unit": "TFLOP/s",
                          "frac": F * rate_gpu / 1e12 / fp64, "traffic": None, "peak_source": src,
