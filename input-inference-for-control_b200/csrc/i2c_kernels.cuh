@@ -2285,6 +2285,43 @@ struct Worker {
           // cells [0, T - n_main) (in head order i = T-1-t) belong to the helpers, the rest to warp 0
           const int i0 = main_warp ? T - n_main : w - 1, di = main_warp ? 1 : H;
           const int i1 = main_warp ? T : (copy_warp ? 0 : T - n_main);
+          if (W == 4 && N <= 3) {  // (n = 5: the 20 prefetch registers make the tail spill -- cart-pole 8192 x 200: 0.86 -> 0.98 ms)
+            // 4-warp teams (two blocks per SM) are bound by their two tail warps, and ~40 % of a tail was the L2 round trip
+            // of the posterior it starts with (profiles/r02l source view: long_scoreboard).  Software pipeline: the posterior
+            // of this warp's NEXT cell is requested before the current tail is computed -- whenever its head has been
+            // published already, which is the rule when the tails are the bottleneck.
+            double mun[N], Sign[TRI(N)];
+            bool have = false;
+            for (int i = i0; i < i1; i += di) {
+              const int t = T - 1 - i;
+              double mu[N], Sig[TRI(N)];
+              if (have) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) mu[k] = mun[k];
+#pragma unroll
+                for (int k = 0; k < TRI(N); ++k) Sig[k] = Sign[k];
+              } else {
+                if (!main_warp) {
+                  while (progress_read(prog) <= i) __nanosleep(64);
+                }
+                const double* po = rec(post, t, LY::E_POST);
+#pragma unroll
+                for (int k = 0; k < N; ++k) mu[k] = __ldcg(po + (LY::P_MU + k) * TILE);
+#pragma unroll
+                for (int k = 0; k < TRI(N); ++k) Sig[k] = __ldcg(po + (LY::P_SIG + k) * TILE);
+              }
+              const int in = i + di;
+              have = in < i1 && (main_warp || progress_read(prog) > in);
+              if (have) {
+                const double* pn = rec(post, T - 1 - in, LY::E_POST);
+#pragma unroll
+                for (int k = 0; k < N; ++k) mun[k] = __ldcg(pn + (LY::P_MU + k) * TILE);
+#pragma unroll
+                for (int k = 0; k < TRI(N); ++k) Sign[k] = __ldcg(pn + (LY::P_SIG + k) * TILE);
+              }
+              backward_tail(it, t, aux, nullptr, mu, Sig, st);
+            }
+          } else {
           for (int i = i0; i < i1; i += di) {
             if (!main_warp) {
               while (progress_read(prog) <= i) __nanosleep(64);
@@ -2297,6 +2334,7 @@ struct Worker {
 #pragma unroll
             for (int k = 0; k < TRI(N); ++k) Sig[k] = __ldcg(po + (LY::P_SIG + k) * TILE);
             backward_tail(it, t, aux, nullptr, mu, Sig, st);
+          }
           }
           if constexpr (BULK) {  // K, k, sigK written here are read back by warp 0's bulk copies in the next forward sweep
             __threadfence();
