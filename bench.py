@@ -473,7 +473,10 @@ def run_cuda(args, rank, world, local_rank):
             line["cpu_baseline"] = port
         if mpc is not None:
             line["mpc"]["cpu_baseline"] = mpc_cpu_baseline(cores)
-        line["config1"] = config1_leg()
+        try:
+            line["config1"] = config1_leg()
+        except Exception as e:  # a side leg must never cost the headline line
+            line["config1"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
