@@ -403,7 +403,7 @@ def run_cuda(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": NCU_DRAM_BYTES_PER_UPDATE * B * T * K if (B == 4096 and T == 200) else None,
-                     "traffic_source": "ncu dram bytes/update (profiles/r02l_ncu_full_em_team_kernel_pendulum_4096.txt) x updates "
+                     "traffic_source": "ncu dram bytes/update (profiles/r02l_ncu_full_em_team_kernel_pendulum_4096.txt; final build: r02z, 418 B) x updates "
                                        "per launch; algorithmic bytes per launch = %.4g" % (B_ALG * B * T * K),
                      "peak_source": peak_src,
                      "kernel": "em_team_kernel<EnvPendulum,8,HOT>" if B <= 148 * 32 else "em_kernel<EnvPendulum>",
